@@ -1,0 +1,207 @@
+"""Batched entry points of the hot path (SURVEY 8b "additive batched API").
+
+Thin host code over the C ABI: argument checking, buffer allocation with torch, stream plumbing.
+All tensors live on one sm_100 CUDA device; every call is stream-ordered and does not synchronise.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+NONE, PASS = -2, -1
+MODE_MCTS, MODE_SELFPLAY = 0, 1
+FLAG_POLICY, FLAG_VALUE, FLAG_SIMT = 1, 2, 4
+
+
+def _want(t, dtype, shape, name, device=None):
+    if not isinstance(t, torch.Tensor) or t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+        raise ValueError(f"{name}: expected contiguous {dtype} tensor of shape {tuple(shape)}")
+    if device is not None and t.device != device:
+        raise ValueError(f"{name}: expected device {device}, got {t.device}")
+
+
+class Positions:
+    """A batch of go.Game states on the device (go.py:51-66): board, ko, last_move, turn, _libs."""
+
+    def __init__(self, boards, ko, last, turn, libs=None, done=None):
+        dev = _lib.require_device(boards.device)
+        B = boards.shape[0]
+        _want(boards, torch.int8, (B, 81), "boards", dev)
+        for t, n in ((ko, "ko"), (last, "last"), (turn, "turn")):
+            _want(t, torch.int16, (B,), n, dev)
+        if libs is not None:
+            _want(libs, torch.uint8, (B, 81), "libs", dev)
+        self.boards, self.ko, self.last, self.turn, self.libs = boards, ko, last, turn, libs
+        self.done = torch.zeros(B, dtype=torch.uint8, device=dev) if done is None else done
+        self.device, self.B = dev, B
+
+    @classmethod
+    def empty(cls, B, device, track_libs=True):
+        dev = _lib.require_device(device)
+        return cls(torch.zeros(B, 81, dtype=torch.int8, device=dev), torch.full((B,), -1, dtype=torch.int16, device=dev),
+                   torch.full((B,), NONE, dtype=torch.int16, device=dev), torch.zeros(B, dtype=torch.int16, device=dev),
+                   torch.zeros(B, 81, dtype=torch.uint8, device=dev) if track_libs else None)
+
+    @classmethod
+    def from_numpy(cls, boards, ko, last, turn, device, libs=None):
+        dev = _lib.require_device(device)
+        f = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+        return cls(f(boards, np.int8).reshape(-1, 81), f(ko, np.int16), f(last, np.int16), f(turn, np.int16),
+                   None if libs is None else f(libs, np.uint8).reshape(-1, 81))
+
+
+def features_batch(pos, fresh_libs=None, want=("conv", "legal", "libs"), out=None):
+    """nnet.features for a batch (kernel a).
+
+    fresh_libs: True -> treat every position as a fresh go.Game (exact liberties);
+                False -> apply the lazy update to pos.libs (the carried Game._libs);
+                None  -> fresh iff pos.libs is None.
+    want: any of "conv" (fp16 operand for policy_value_batch), "f32" ([B,27,9,9] float32, what
+          nnet.features returns), "u8" ([B,27,81] uint8), "legal", "libs".
+    Returns a dict with the requested tensors.  When the liberty cache is carried and "libs" is
+    requested, pos.libs is replaced by the updated cache.
+    """
+    L = _lib.lib()
+    dev, B = pos.device, pos.B
+    fresh = pos.libs is None if fresh_libs is None else fresh_libs
+    if not fresh and pos.libs is None:
+        raise ValueError("fresh_libs=False needs pos.libs")
+    out = {} if out is None else out
+    if "conv" in want and "conv" not in out:
+        out["conv"] = torch.empty(L.bk_feats_conv_bytes(B), dtype=torch.uint8, device=dev)
+    if "f32" in want and "f32" not in out:
+        out["f32"] = torch.empty(B, 27, 9, 9, dtype=torch.float32, device=dev)
+    if "u8" in want and "u8" not in out:
+        out["u8"] = torch.empty(B, 27, 81, dtype=torch.uint8, device=dev)
+    if "legal" in want and "legal" not in out:
+        out["legal"] = torch.empty(B, 81, dtype=torch.uint8, device=dev)
+    if "libs" in want and "libs" not in out:
+        spare = getattr(pos, "_libs_spare", None)
+        out["libs"] = spare if spare is not None else torch.empty(B, 81, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.bk_encode(_lib.ptr(pos.boards), _lib.ptr(pos.ko), _lib.ptr(pos.last), _lib.ptr(pos.turn),
+                         None if fresh else _lib.ptr(pos.libs), _lib.ptr(out.get("conv")), _lib.ptr(out.get("f32")),
+                         _lib.ptr(out.get("u8")), _lib.ptr(out.get("legal")), _lib.ptr(out.get("libs")), B,
+                         _lib.stream_ptr(dev))
+    _lib.check(rc, "bk_encode")
+    _lib.count_launch()
+    if "libs" in want:
+        # the kernel never updates the cache in place: swap the buffers (a fresh position adopts its exact
+        # liberties as the cache, exactly like Game._libs after the first get_liberties call)
+        pos._libs_spare, pos.libs = pos.libs, out["libs"]
+    return out
+
+
+class PackedNet:
+    """Device-resident weight blob of one PolicyNet / ValueNet (BatchNorm folded, fp16 conv operands)."""
+
+    def __init__(self, state_dict, device, is_value=None):
+        dev = _lib.require_device(device)
+        L = _lib.lib()
+        sd = {k: (v.detach().cpu().double() if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v)).double())
+              for k, v in state_dict.items()}
+        self.is_value = ("lin1.weight" in sd) if is_value is None else is_value
+        eps = 1e-5
+        ws, bs = [], []
+        for i in (0, 3, 6, 9, 12, 15, 18):        # Conv2d at conv.i, BatchNorm2d at conv.(i+1)  (nnet.py:31-52)
+            w, b = sd[f"conv.{i}.weight"], sd[f"conv.{i}.bias"]
+            s = sd[f"conv.{i + 1}.weight"] / torch.sqrt(sd[f"conv.{i + 1}.running_var"] + eps)
+            ws.append(w * s[:, None, None, None])
+            bs.append((b - sd[f"conv.{i + 1}.running_mean"]) * s + sd[f"conv.{i + 1}.bias"])
+        f32 = lambda t: np.ascontiguousarray(t.float().numpy())
+        w0, w16 = f32(ws[0]), f32(torch.stack(ws[1:]))
+        bias = f32(torch.stack(bs))
+        head_w, head_b = f32(sd["conv.21.weight"].reshape(128)), f32(sd["conv.21.bias"].reshape(81))
+        vtail = None
+        if self.is_value:
+            s0 = sd["bn.weight"] / torch.sqrt(sd["bn.running_var"] + eps)
+            t0 = sd["bn.bias"] - sd["bn.running_mean"] * s0
+            s1 = sd["lin_bn.weight"] / torch.sqrt(sd["lin_bn.running_var"] + eps)
+            w1 = sd["lin1.weight"] * s1[:, None]
+            b1 = (sd["lin1.bias"] - sd["lin_bn.running_mean"]) * s1 + sd["lin_bn.bias"]
+            vtail = f32(torch.cat([s0.reshape(1), t0.reshape(1), sd["lin2.bias"].reshape(1), w1.reshape(-1), b1,
+                                   sd["lin2.weight"].reshape(-1)]))
+        blob = np.zeros(L.bk_weights_blob_bytes(), np.uint8)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        _lib.check(L.bk_weights_pack(p(w0), p(w16), p(bias), p(head_w), p(head_b), p(vtail), p(blob)), "bk_weights_pack")
+        self.blob = torch.from_numpy(blob).to(dev)
+        self.device = dev
+
+
+def policy_value_batch(feats_conv, B, policy=None, value=None, want_logits=True, simt=False, _extra_flags=0):
+    """PolicyNet / ValueNet forward for B positions (kernel b).
+
+    feats_conv: the "conv" output of features_batch.  policy / value: PackedNet or None.
+    Returns (logits [B,81] | None, probs [B,81] | None, value [B] | None), float32.
+    """
+    L = _lib.lib()
+    if policy is None and value is None:
+        raise ValueError("need a policy net, a value net, or both")
+    dev = (policy or value).device
+    if feats_conv.device != dev or feats_conv.numel() < L.bk_feats_conv_bytes(B):
+        raise ValueError("feats_conv: wrong device or too small for B")
+    logits = torch.empty(B, 81, dtype=torch.float32, device=dev) if (policy is not None and want_logits) else None
+    probs = torch.empty(B, 81, dtype=torch.float32, device=dev) if policy is not None else None
+    val = torch.empty(B, dtype=torch.float32, device=dev) if value is not None else None
+    flags = (FLAG_POLICY if policy is not None else 0) | (FLAG_VALUE if value is not None else 0) | \
+            (FLAG_SIMT if simt else 0) | _extra_flags
+    with torch.cuda.device(dev):
+        rc = L.bk_forward(_lib.ptr(feats_conv), _lib.ptr(policy.blob if policy else None),
+                          _lib.ptr(value.blob if value else None), _lib.ptr(logits), _lib.ptr(probs), _lib.ptr(val),
+                          B, flags, _lib.stream_ptr(dev))
+    _lib.check(rc, "bk_forward")
+    _lib.count_launch()
+    return logits, probs, val
+
+
+def playout_step(pos, probs, mode, max_turn, seed=0, game0=0, q_inj=None, moves_out=None):
+    """One playout move for every unfinished board (kernel c); updates `pos` in place, returns moves int16 [B]."""
+    L = _lib.lib()
+    dev, B = pos.device, pos.B
+    _want(probs, torch.float32, (B, 81), "probs", dev)
+    qv = 0
+    if q_inj is not None:
+        if q_inj.dtype != torch.float32 or q_inj.dim() != 3 or q_inj.shape[0] != B or q_inj.shape[2] != 81 \
+                or not q_inj.is_contiguous() or q_inj.device != dev:
+            raise ValueError("q_inj: expected contiguous float32 [B, n, 81] on the same device")
+        qv = q_inj.shape[1]
+    if moves_out is None:
+        moves_out = torch.empty(B, dtype=torch.int16, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.bk_playout_step(_lib.ptr(pos.boards), _lib.ptr(pos.ko), _lib.ptr(pos.last), _lib.ptr(pos.turn),
+                               _lib.ptr(pos.libs), _lib.ptr(pos.done), _lib.ptr(probs), _lib.ptr(q_inj), qv,
+                               C.c_uint64(seed), C.c_uint32(game0), mode, max_turn, _lib.ptr(moves_out), B,
+                               _lib.stream_ptr(dev))
+    _lib.check(rc, "bk_playout_step")
+    _lib.count_launch()
+    return moves_out
+
+
+def score_batch(boards, komi=5.5):
+    """Game.score() and the +-1 reward for a batch: returns (score float32 [B], reward int8 [B])."""
+    L = _lib.lib()
+    dev = _lib.require_device(boards.device)
+    B = boards.shape[0]
+    _want(boards, torch.int8, (B, 81), "boards", dev)
+    score = torch.empty(B, dtype=torch.float32, device=dev)
+    reward = torch.empty(B, dtype=torch.int8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.bk_score(_lib.ptr(boards), C.c_float(komi), _lib.ptr(score), _lib.ptr(reward), B, _lib.stream_ptr(dev))
+    _lib.check(rc, "bk_score")
+    _lib.count_launch()
+    return score, reward
+
+
+def exp_draws(seed, game0, move, tr, B, device):
+    """The counter-based Exp(1) stream as the kernels see it: float32 [B,81]."""
+    L = _lib.lib()
+    dev = _lib.require_device(device)
+    q = torch.empty(B, 81, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.bk_exp_draws(C.c_uint64(seed), C.c_uint32(game0), C.c_uint32(move), C.c_uint32(tr), _lib.ptr(q), B,
+                            _lib.stream_ptr(dev))
+    _lib.check(rc, "bk_exp_draws")
+    _lib.count_launch()
+    return q

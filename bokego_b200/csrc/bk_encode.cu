@@ -1,0 +1,154 @@
+// bk_encode.cu -- kernel (a): batched board -> 27 feature planes, one warp per 9x9 board.
+//
+// Replaces nnet.features (/root/reference/bokego/nnet.py:182-262) and the go.py routines it calls
+// (get_legal_moves go.py:245-260, get_liberties go.py:220-243, get_caps go.py:404-418).
+// Integer only; bit-exact against the reference in both liberty-cache modes.
+//
+// Work split: the board's two colour sets are built with warp ballots into 81-bit bit-boards that
+// every lane keeps in registers; lane l then owns squares l, l+32, l+64 and evaluates each of them
+// on its own (group flood fill by iterated dilation, capture / liberty counts by popcount).  No
+// shared memory, no atomics.  Outputs are optional (null pointer = skip):
+//   feats_conv  fp16 operand layout of the conv kernel: [group of 5 boards][4 channel chunks]
+//               [605 rows][8 channels]; row = 121*board_in_group + 22 + 11*x + y, i.e. a stride-11
+//               raster with two zero columns and two zero rows between boards, so that every tap of
+//               the 5x5 first layer is a pure row shift.  Pad rows/columns and channels 27..31 are 0.
+//   feats_f32   float32 [B][27][9][9], what nnet.features returns
+//   planes_u8   uint8   [B][27][81], the same values as bytes
+//   legal_out   uint8   [B][81]   (plane 5)
+//   libs_out    uint8   [B][81]   Game._libs after the call
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bk_bitboard.cuh"
+#include "bk_layout.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t half_bits(int n)   // fp16 bit pattern of a small non-negative integer
+{
+    return (uint32_t)__half_as_ushort(__int2half_rn(n));
+}
+
+__device__ __forceinline__ uint32_t pack2(int lo, int hi) { return half_bits(lo) | (half_bits(hi) << 16); }
+
+__global__ void __launch_bounds__(128)
+bk_encode_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ ko_arr,
+                 const int16_t *__restrict__ last_arr, const int16_t *__restrict__ turn_arr,
+                 const uint8_t *__restrict__ libs_in, uint4 *__restrict__ feats_conv,
+                 float *__restrict__ feats_f32, uint8_t *__restrict__ planes_u8,
+                 uint8_t *__restrict__ legal_out, uint8_t *__restrict__ libs_out, int B, int slots)
+{
+    const int slot = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (slot >= slots) return;
+
+    uint4 *conv_base = nullptr;
+    if (feats_conv) {
+        const int g = slot / BK_GROUP, bi = slot - g * BK_GROUP;
+        conv_base = feats_conv + (size_t)g * (BK_F_CHUNKS * BK_F_ROWS_G) + bi * BK_F_ROWS_B;
+        // zero rows/columns of this board's block (and the whole block for a slot past the batch)
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int r = lane; r < BK_F_ROWS_B; r += 32) {
+            const bool pad = r < 22 || ((r - 22) % 11) >= 9 || slot >= B;
+            if (pad) {
+#pragma unroll
+                for (int c = 0; c < BK_F_CHUNKS; ++c) conv_base[c * BK_F_ROWS_G + r] = z;
+            }
+        }
+    }
+    if (slot >= B) return;
+    const int b = slot;
+
+    // ---- load the position, build the bit-boards ------------------------------------------------
+    const int ko = ko_arr[b], last = last_arr[b], turn = turn_arr[b];
+    uint32_t bl[3], wh[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int p = lane + 32 * k;
+        const int v = p < BK_NSQ ? (int)boards[(size_t)b * BK_NSQ + p] : 0;
+        bl[k] = __ballot_sync(0xffffffffu, v == 1);
+        wh[k] = __ballot_sync(0xffffffffu, v == -1);
+    }
+    BB black, white;
+    black.w[0] = bl[0] & BK_M27;
+    black.w[1] = ((bl[0] >> 27) | (bl[1] << 5)) & BK_M27;
+    black.w[2] = ((bl[1] >> 22) | (bl[2] << 10)) & BK_M27;
+    white.w[0] = wh[0] & BK_M27;
+    white.w[1] = ((wh[0] >> 27) | (wh[1] << 5)) & BK_M27;
+    white.w[2] = ((wh[1] >> 22) | (wh[2] << 10)) & BK_M27;
+    const bool blk = (turn & 1) == 0;
+    const BB own = blk ? black : white, opp = blk ? white : black;
+    const bool carried = libs_in != nullptr;
+    const bool stale = carried && last >= 0 && libs_in[(size_t)b * BK_NSQ + last] == 0;
+
+    // ---- per-square evaluation --------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int p = lane + 32 * k;
+        if (p >= BK_NSQ) break;
+        const bool mine = bb_test(own, p), theirs = bb_test(opp, p);
+        int lib;
+        if (carried) lib = bb_lazy_lib_of(black, white, last, stale, p, (int)libs_in[(size_t)b * BK_NSQ + p]);
+        else lib = bb_exact_lib_of(black, white, p);
+        int la = 0, cp = 0;
+        bool lg = false;
+        if (!mine && !theirs) {
+            const Cand c = bb_candidate(own, opp, p, nullptr, nullptr);
+            lg = bb_listed_legal(own, opp, ko, p, c);
+            if (lg) { la = c.libs_after; cp = c.caps; }
+        }
+        if (libs_out) libs_out[(size_t)b * BK_NSQ + p] = (uint8_t)lib;
+        if (legal_out) legal_out[(size_t)b * BK_NSQ + p] = (uint8_t)lg;
+
+        // plane values (nnet.py:249-262): planes 6..12 / 13..19 / 20..26 hold min(v,7) in slot min(v,7)-1
+        const int l7 = lib > 6 ? 7 : lib, a7 = la > 6 ? 7 : la, c7 = cp > 6 ? 7 : cp;
+        int v[32];
+        v[0] = mine; v[1] = theirs; v[2] = (!mine && !theirs); v[3] = blk; v[4] = (p == last); v[5] = lg;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            v[6 + i] = (l7 == i + 1) ? l7 : 0;
+            v[13 + i] = (a7 == i + 1) ? a7 : 0;
+            v[20 + i] = (c7 == i + 1) ? c7 : 0;
+        }
+#pragma unroll
+        for (int i = 27; i < 32; ++i) v[i] = 0;
+
+        if (planes_u8) {
+#pragma unroll
+            for (int c = 0; c < 27; ++c) planes_u8[((size_t)b * 27 + c) * BK_NSQ + p] = (uint8_t)v[c];
+        }
+        if (feats_f32) {
+#pragma unroll
+            for (int c = 0; c < 27; ++c) feats_f32[((size_t)b * 27 + c) * BK_NSQ + p] = (float)v[c];
+        }
+        if (conv_base) {
+            const int x = p / 9, y = p - 9 * x;
+            const int r = 22 + 11 * x + y;
+#pragma unroll
+            for (int c = 0; c < BK_F_CHUNKS; ++c) {
+                uint4 o;
+                o.x = pack2(v[8 * c + 0], v[8 * c + 1]);
+                o.y = pack2(v[8 * c + 2], v[8 * c + 3]);
+                o.z = pack2(v[8 * c + 4], v[8 * c + 5]);
+                o.w = pack2(v[8 * c + 6], v[8 * c + 7]);
+                conv_base[c * BK_F_ROWS_G + r] = o;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int bk_encode(const int8_t *boards, const int16_t *ko, const int16_t *last, const int16_t *turn,
+                                const uint8_t *libs_in, void *feats_conv, float *feats_f32, uint8_t *planes_u8,
+                                uint8_t *legal_out, uint8_t *libs_out, int B, cudaStream_t stream)
+{
+    if (B <= 0) return 0;
+    const int slots = feats_conv ? ((B + BK_GROUP - 1) / BK_GROUP) * BK_GROUP : B;
+    const int warps_per_block = 4;
+    const int grid = (slots + warps_per_block - 1) / warps_per_block;
+    bk_encode_kernel<<<grid, warps_per_block * 32, 0, stream>>>(boards, ko, last, turn, libs_in, (uint4 *)feats_conv,
+                                                                 feats_f32, planes_u8, legal_out, libs_out, B, slots);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}

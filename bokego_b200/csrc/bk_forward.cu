@@ -1,0 +1,714 @@
+// bk_forward.cu -- kernel (b): PolicyNet / ValueNet forward for batches of 9x9 positions on sm_100a.
+//
+// Replaces PolicyNet.forward (/root/reference/bokego/nnet.py:19-57), ValueNet.forward (nnet.py:59-113),
+// Conv2dUntiedBias.forward (nnet.py:175-180) and SOFT (nnet.py:16) in eval mode, BatchNorm folded.
+//
+// One persistent CTA per SM.  A work item is one trunk (policy or value) over a group of 5 boards:
+//   * activations of the whole group (5 x 100 padded rows x 128 ch, fp16) stay in shared memory for all
+//     7 conv layers; each layer is an implicit GEMM  D[512 rows, 128 co] += A[rows + tap shift, ci] * W[tap]
+//     issued as tcgen05.mma (cta_group::1, kind::f16, M=128, N=128, K=16) with fp32 accumulators for the
+//     four 128-row tiles resident in TMEM (4 x 128 = 512 columns);
+//   * weights stream L2 -> shared memory as 16 KiB K-slabs (cp.async.bulk + mbarrier, 3 stages); every slab
+//     is used by all four tiles before its slot is recycled;
+//   * the epilogue warps pull accumulators out of TMEM (tcgen05.ld), add the folded bias, apply ReLU, round to
+//     fp16 and write the next layer's operand in place; after the last layer they compute the 1x1 head with
+//     the untied bias and finish with the 81-way softmax (policy) or the small dense tail + tanh (value).
+// Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4), warp 8 = bulk-copy
+// producer (+ TMEM allocation), warp 9 = MMA issuer (one elected lane).
+//
+// A plain CUDA-core kernel over the same packed operands (BK_FWD_SIMT) exists to validate the packing and
+// the tensor-core path against each other on the GPU; it is not a fallback and is never selected implicitly.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "bk_layout.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------
+// shared-memory plan of the tcgen05 kernel
+// ------------------------------------------------------------------------------------------------------
+constexpr int A_MARGIN = 12;                       // zero rows in front of GEMM row 0 (|tap shift| <= 11)
+constexpr int A_ROWS = A_MARGIN + 512 + 12;        // 536
+constexpr int A_LBO = A_ROWS * 16;                 // bytes between consecutive 8-channel chunks
+constexpr int A_BYTES = 16 * A_LBO;                // 137,216
+constexpr int F_MARGIN = 24;                       // |5x5 tap shift| <= 24
+constexpr int F_ROWS = F_MARGIN + BK_F_ROWS_G + 24;  // 653
+constexpr int F_LBO = F_ROWS * 16;
+constexpr int F_BYTES = BK_F_CHUNKS * F_LBO;       // 41,792
+constexpr int N_STAGES = 3;
+constexpr int OFF_A = 0;
+constexpr int OFF_F = OFF_A + A_BYTES;
+constexpr int OFF_W = OFF_F + F_BYTES;
+constexpr int OFF_MISC = OFF_W + N_STAGES * BK_STAGE_BYTES;   // 228,160
+// misc: barriers (16 x 8 B), tmem base, two float[512] scratch arrays
+constexpr int OFF_BAR = OFF_MISC;
+constexpr int OFF_TMEM = OFF_BAR + 128;
+constexpr int OFF_PART = OFF_TMEM + 16;            // float[512]: partial head sums of column half 1
+constexpr int OFF_LOGIT = OFF_PART + 2048;         // float[512]: head output per GEMM row
+constexpr int SMEM_BYTES = OFF_LOGIT + 2048;       // 232,400 <= 232,448
+static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KiB");
+
+enum { BAR_WFULL = 0, BAR_WEMPTY = 3, BAR_ACC = 6, BAR_ACT = 7, BAR_FFULL = 8, BAR_FEMPTY = 9 };
+
+constexpr int N_EPI_WARPS = 8;
+constexpr int WARP_PRODUCER = 8;
+constexpr int WARP_MMA = 9;
+constexpr int N_THREADS = 320;
+
+// instruction descriptor: D=f32 (bit 4), A=B=f16 (0), both K-major (0), N=128 (>>3 at bit 17), M=128 (>>4 at bit 24)
+constexpr uint32_t IDESC = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must end in a trap (launch error), never in a hung GPU.
+__device__ unsigned int *g_dbg = nullptr;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            if (g_dbg) {
+                g_dbg[0] = 0xDEAD0000u | (threadIdx.x & 0xFFFFu); g_dbg[1] = blockIdx.x; g_dbg[2] = bar; g_dbg[3] = parity;
+                g_dbg[4] = tag;
+                __threadfence_system();
+            }
+            asm volatile("trap;");
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive columns of 32-bit accumulators -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (sm_100 format: version field = 1).
+//   lbo = byte distance between the two 8-element K chunks of one MMA, sbo = between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16);
+    const uint32_t hi = (sbo >> 4) | (1u << 14);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// row bookkeeping
+// ------------------------------------------------------------------------------------------------------
+// layers 1..6: GEMM row r (0..511) -> is it a real square?  (in place: destination row = r)
+__device__ __forceinline__ bool act_row_valid(int r, int &board, int &sq)
+{
+    board = r / 100;
+    const int rem = r - 100 * board;
+    const int q = rem - 10;
+    const int x = q / 10, y = q - 10 * x;
+    sq = 9 * x + y;
+    return board < BK_GROUP && rem >= 10 && y < 9;
+}
+// layer 0: GEMM row r0 (0..639, stride-11 raster) -> destination activation row, or -1
+__device__ __forceinline__ int l0_dest_row(int r0)
+{
+    const int board = r0 / BK_F_ROWS_B;
+    const int rem = r0 - BK_F_ROWS_B * board;
+    if (board >= BK_GROUP || rem < 22) return -1;
+    const int q = rem - 22;
+    const int x = q / 11, y = q - 11 * x;
+    if (y >= 9) return -1;
+    return 100 * board + 10 + 10 * x + y;
+}
+
+__device__ __forceinline__ uint32_t relu_pack(float a, float b)
+{
+    const __half2 h = __floats2half2_rn(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// Final stage shared by both kernels: `logit` holds the 81 head outputs (1x1 conv + untied bias) of one
+// board; one warp turns them into probs (policy) or the scalar value (value net).
+__device__ __forceinline__ void finish_board(const float *logit, int net, const uint8_t *blob, float *logits_out,
+                                             float *probs_out, float *value_out, int lane)
+{
+    if (net == 0) {
+        float v[3], mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int p = lane + 32 * k;
+            v[k] = p < 81 ? logit[p] : -INFINITY;
+            mx = fmaxf(mx, v[k]);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float e[3], sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            e[k] = (lane + 32 * k) < 81 ? expf(v[k] - mx) : 0.0f;
+            sum += e[k];
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int p = lane + 32 * k;
+            if (p < 81) {
+                if (logits_out) logits_out[p] = v[k];
+                if (probs_out) probs_out[p] = e[k] / sum;
+            }
+        }
+    } else {
+        const float *vt = reinterpret_cast<const float *>(blob + BK_W_VT_OFF);
+        const float *w1t = reinterpret_cast<const float *>(blob + BK_W_VT_W1T_OFF);
+        const float *b1 = reinterpret_cast<const float *>(blob + BK_W_VT_B1_OFF);
+        const float *w2 = reinterpret_cast<const float *>(blob + BK_W_VT_W2_OFF);
+        const float s = __ldg(vt + 0), t = __ldg(vt + 1), b2 = __ldg(vt + 2);
+        float h0 = __ldg(b1 + lane), h1 = __ldg(b1 + lane + 32);
+        for (int p = 0; p < 81; ++p) {
+            const float a = fmaxf(fmaf(logit[p], s, t), 0.0f);
+            h0 = fmaf(__ldg(w1t + p * 64 + lane), a, h0);
+            h1 = fmaf(__ldg(w1t + p * 64 + lane + 32), a, h1);
+        }
+        float acc = fmaxf(h0, 0.0f) * __ldg(w2 + lane) + fmaxf(h1, 0.0f) * __ldg(w2 + lane + 32);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0 && value_out) *value_out = tanhf(acc + b2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// the tcgen05 kernel
+// ------------------------------------------------------------------------------------------------------
+struct FwdArgs {
+    const uint8_t *feats;      // [G][BK_F_GROUP_BYTES]
+    const uint8_t *blob[2];    // policy, value
+    float *logits, *probs, *value;
+    int B, G, n_nets, first_net;
+    int swap_lbo_sbo;          // diagnostic: exchange the two descriptor strides
+    float *dump;               // diagnostic: raw accumulators [640][128] of pass `dump_pass` (first work item of CTA 0)
+    int dump_pass;
+    unsigned int *dbg;         // host-mapped words written before a bounded wait traps
+};
+
+__global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdArgs args)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t sA = s_base + OFF_A, sF = s_base + OFF_F, sW = s_base + OFF_W, sBar = s_base + OFF_BAR;
+    float *part = reinterpret_cast<float *>(smem + OFF_PART);
+    float *logit = reinterpret_cast<float *>(smem + OFF_LOGIT);
+    const int n_items = args.G * args.n_nets;
+    if (threadIdx.x == 0 && args.dbg) g_dbg = args.dbg;
+
+    // ---- one-time setup: zero the operand buffers (pad rows must read as 0), barriers, TMEM ----------
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(smem);
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < (A_BYTES + F_BYTES) / 16; i += N_THREADS) z[i] = zero;
+        fence_proxy_async();
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < N_STAGES; ++s) { mbar_init(sBar + 8 * (BAR_WFULL + s), 1); mbar_init(sBar + 8 * (BAR_WEMPTY + s), 1); }
+        mbar_init(sBar + 8 * BAR_ACC, 1);
+        mbar_init(sBar + 8 * BAR_ACT, N_EPI_WARPS);
+        mbar_init(sBar + 8 * BAR_FFULL, 1);
+        mbar_init(sBar + 8 * BAR_FEMPTY, 1);
+        fence_barrier_init();
+    }
+    if (warp == WARP_PRODUCER) tmem_alloc(s_base + OFF_TMEM, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem + OFF_TMEM);
+
+    if (warp == WARP_PRODUCER) {
+        // =========================== bulk-copy producer ===========================
+        if (lane == 0) {
+            uint32_t wit = 0;   // weight stage counter over the whole kernel
+            auto load_feats = [&](int item) {
+                const int g = item / args.n_nets;
+                const uint8_t *src = args.feats + (size_t)g * BK_F_GROUP_BYTES;
+                mbar_arrive_expect_tx(sBar + 8 * BAR_FFULL, BK_F_GROUP_BYTES);
+#pragma unroll
+                for (int c = 0; c < BK_F_CHUNKS; ++c)
+                    bulk_g2s(sF + c * F_LBO + F_MARGIN * 16, src + (size_t)c * BK_F_ROWS_G * 16, BK_F_ROWS_G * 16,
+                             sBar + 8 * BAR_FFULL);
+            };
+            auto stream = [&](const uint8_t *src, int n_stages) {
+                for (int s = 0; s < n_stages; ++s, ++wit) {
+                    const uint32_t st = wit % N_STAGES, ph = (wit / N_STAGES) & 1u;
+                    mbar_wait(sBar + 8 * (BAR_WEMPTY + st), ph ^ 1u, 0x100u + wit);
+                    mbar_arrive_expect_tx(sBar + 8 * (BAR_WFULL + st), BK_STAGE_BYTES);
+                    bulk_g2s(sW + st * BK_STAGE_BYTES, src + (size_t)s * BK_STAGE_BYTES, BK_STAGE_BYTES,
+                             sBar + 8 * (BAR_WFULL + st));
+                }
+            };
+            int n_done = 0;
+            if ((int)blockIdx.x < n_items) load_feats(blockIdx.x);
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+                const uint8_t *blob = args.blob[args.first_net + item % args.n_nets];
+                stream(blob + BK_W_L0_OFF, BK_L0_STAGES);   // layer 0, tiles 0..3
+                stream(blob + BK_W_L0_OFF, BK_L0_STAGES);   // layer 0, tile 4
+                stream(blob + BK_W_L_OFF(1), BK_L_STAGES);
+                const int next = item + gridDim.x;
+                if (next < n_items) {                        // prefetch the next group's planes
+                    mbar_wait(sBar + 8 * BAR_FEMPTY, n_done & 1u, 0x200u);
+                    load_feats(next);
+                }
+                for (int l = 2; l <= 6; ++l) stream(blob + BK_W_L_OFF(l), BK_L_STAGES);
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            uint32_t wit = 0, pass = 0, n_done = 0;
+            const uint32_t a_lbo = args.swap_lbo_sbo ? 128u : (uint32_t)A_LBO, a_sbo = args.swap_lbo_sbo ? (uint32_t)A_LBO : 128u;
+            const uint32_t f_lbo = args.swap_lbo_sbo ? 128u : (uint32_t)F_LBO, f_sbo = args.swap_lbo_sbo ? (uint32_t)F_LBO : 128u;
+            const uint32_t w_lbo = args.swap_lbo_sbo ? 128u : 2048u, w_sbo = args.swap_lbo_sbo ? 2048u : 128u;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+                mbar_wait(sBar + 8 * BAR_FFULL, n_done & 1u, 0x300u);
+                for (int ps = 0; ps < 8; ++ps, ++pass) {
+                    // ps 0: layer 0 tiles 0..3; ps 1: layer 0 tile 4; ps 2..7: layers 1..6
+                    if (pass > 0) mbar_wait(sBar + 8 * BAR_ACT, (pass - 1) & 1u, 0x400u + pass);   // operands written, TMEM drained
+                    tc_fence_after();
+                    const bool l0 = ps < 2;
+                    const int n_stages = l0 ? BK_L0_STAGES : BK_L_STAGES;
+                    const int tile0 = ps == 1 ? 4 : 0, n_tiles = ps == 1 ? 1 : 4;
+                    for (int s = 0; s < n_stages; ++s, ++wit) {
+                        const uint32_t st = wit % N_STAGES, ph = (wit / N_STAGES) & 1u;
+                        mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x500u + wit);
+                        tc_fence_after();
+                        const uint32_t wbase = sW + st * BK_STAGE_BYTES;
+                        for (int t = 0; t < n_tiles; ++t) {
+                            const int row0 = 128 * (tile0 + t);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                uint64_t ad;
+                                if (l0) {
+                                    const int tap = 2 * s + (kk >> 1);
+                                    const int ti = tap / 5, tj = tap - 5 * ti;
+                                    const int off = tap < 25 ? (ti - 2) * 11 + (tj - 2) : 0;
+                                    ad = make_desc(sF + (kk & 1) * 2 * F_LBO + (F_MARGIN + row0 + off) * 16, f_lbo, f_sbo);
+                                } else {
+                                    const int tap = s >> 1;
+                                    const int ti = tap / 3, tj = tap - 3 * ti;
+                                    const int off = (ti - 1) * 10 + (tj - 1);
+                                    ad = make_desc(sA + ((s & 1) * 8 + kk * 2) * A_LBO + (A_MARGIN + row0 + off) * 16, a_lbo, a_sbo);
+                                }
+                                const uint64_t bd = make_desc(wbase + kk * 2 * 2048, w_lbo, w_sbo);
+                                umma_f16(tmem + (uint32_t)(t * 128), ad, bd, IDESC, (s | kk) != 0);
+                            }
+                        }
+                        umma_commit(sBar + 8 * (BAR_WEMPTY + st));   // slab consumed -> producer may refill
+                    }
+                    if (ps == 1) umma_commit(sBar + 8 * BAR_FEMPTY);   // feature planes no longer needed
+                    umma_commit(sBar + 8 * BAR_ACC);                   // accumulators of this pass complete
+                }
+            }
+        }
+    } else {
+        // =========================== epilogue warps ===========================
+        const int quad = warp & 3, half = warp >> 2;
+        const uint32_t t_lane = tmem + ((uint32_t)(32 * quad) << 16);
+        uint32_t pass = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int net = args.first_net + item % args.n_nets, g = item / args.n_nets;
+            const uint8_t *blob = args.blob[net];
+            const float4 *bias4 = reinterpret_cast<const float4 *>(blob + BK_W_BIAS_OFF);
+            for (int ps = 0; ps < 8; ++ps, ++pass) {
+                const int layer = ps < 2 ? 0 : ps - 1;
+                const int tile0 = ps == 1 ? 4 : 0, n_tiles = ps == 1 ? 1 : 4;
+                mbar_wait(sBar + 8 * BAR_ACC, pass & 1u, 0x600u + pass);
+                tc_fence_after();
+                float hs[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // layer 6: this thread's half of the head dot product, per tile
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (t >= n_tiles) break;
+                    const int r = 128 * (tile0 + t) + 32 * quad + lane;   // GEMM row of this thread
+                    int dest, board = 0, sq = 0;
+                    if (layer == 0) dest = l0_dest_row(r);
+                    else dest = act_row_valid(r, board, sq) ? r : -1;
+                    float hsum = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        uint32_t v[32];
+                        tmem_ld32(t_lane + (uint32_t)(t * 128 + half * 64 + j * 32), v);
+                        tc_wait_ld();
+                        const int co0 = half * 64 + j * 32;
+                        if (args.dump && blockIdx.x == 0 && item == 0 && ps == args.dump_pass) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) args.dump[(size_t)r * 128 + co0 + i] = __uint_as_float(v[i]);
+                        }
+                        if (layer < 6) {
+                            if (dest >= 0) {
+#pragma unroll
+                                for (int c8 = 0; c8 < 4; ++c8) {
+                                    const float4 b0 = __ldg(bias4 + layer * 32 + (co0 >> 2) + c8 * 2);
+                                    const float4 b1 = __ldg(bias4 + layer * 32 + (co0 >> 2) + c8 * 2 + 1);
+                                    uint4 o;
+                                    o.x = relu_pack(__uint_as_float(v[c8 * 8 + 0]) + b0.x, __uint_as_float(v[c8 * 8 + 1]) + b0.y);
+                                    o.y = relu_pack(__uint_as_float(v[c8 * 8 + 2]) + b0.z, __uint_as_float(v[c8 * 8 + 3]) + b0.w);
+                                    o.z = relu_pack(__uint_as_float(v[c8 * 8 + 4]) + b1.x, __uint_as_float(v[c8 * 8 + 5]) + b1.y);
+                                    o.w = relu_pack(__uint_as_float(v[c8 * 8 + 6]) + b1.z, __uint_as_float(v[c8 * 8 + 7]) + b1.w);
+                                    const int chunk = (co0 >> 3) + c8;
+                                    *reinterpret_cast<uint4 *>(smem + OFF_A + chunk * A_LBO + (A_MARGIN + dest) * 16) = o;
+                                }
+                            }
+                        } else {
+                            const float4 *hw4 = reinterpret_cast<const float4 *>(blob + BK_W_HEADW_OFF);
+#pragma unroll
+                            for (int c4 = 0; c4 < 8; ++c4) {
+                                const float4 b = __ldg(bias4 + layer * 32 + (co0 >> 2) + c4);
+                                const float4 w = __ldg(hw4 + (co0 >> 2) + c4);
+                                hsum = fmaf(fmaxf(__uint_as_float(v[c4 * 4 + 0]) + b.x, 0.0f), w.x, hsum);
+                                hsum = fmaf(fmaxf(__uint_as_float(v[c4 * 4 + 1]) + b.y, 0.0f), w.y, hsum);
+                                hsum = fmaf(fmaxf(__uint_as_float(v[c4 * 4 + 2]) + b.z, 0.0f), w.z, hsum);
+                                hsum = fmaf(fmaxf(__uint_as_float(v[c4 * 4 + 3]) + b.w, 0.0f), w.w, hsum);
+                            }
+                        }
+                    }
+                    hs[t] = hsum;
+                    if (layer == 6 && half == 1) part[r] = hsum;
+                }
+                if (layer == 6) {
+                    // combine the two column halves: 1x1 conv 128->1 plus the per-square bias
+                    named_bar_sync(1, N_EPI_WARPS * 32);
+                    if (half == 0) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int r = 128 * t + 32 * quad + lane;
+                            int board, sq;
+                            if (act_row_valid(r, board, sq)) {
+                                const float hb = __ldg(reinterpret_cast<const float *>(blob + BK_W_HEADB_OFF) + sq);
+                                logit[board * 81 + sq] = hs[t] + part[r] + hb;
+                            }
+                        }
+                    }
+                    named_bar_sync(1, N_EPI_WARPS * 32);
+                }
+                // this pass's TMEM reads are complete and the operand writes are visible to the tensor core
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sBar + 8 * BAR_ACT);
+                if (layer == 6) {
+                    // logit[] holds 5 boards x 81 head outputs
+                    if (warp < BK_GROUP) {
+                        const int b = g * BK_GROUP + warp;
+                        if (b < args.B)
+                            finish_board(logit + warp * 81, net, blob, args.logits ? args.logits + (size_t)b * 81 : nullptr,
+                                         args.probs ? args.probs + (size_t)b * 81 : nullptr,
+                                         args.value ? args.value + b : nullptr, lane);
+                    }
+                    named_bar_sync(1, N_EPI_WARPS * 32);   // logit[] is reused by the next item
+                }
+            }
+        }
+    }
+
+    // ---- teardown ----------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_PRODUCER) { __syncwarp(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// validation kernel: the same packed operands on CUDA cores, one CTA per (board, net), thread = out channel
+// ------------------------------------------------------------------------------------------------------
+constexpr int SIMT_FIN_BYTES = 169 * 32 * 2;          // 13x13 padded input, 32 ch
+constexpr int SIMT_ACT_BYTES = 121 * 128 * 2;         // 11x11 padded activations, 128 ch
+constexpr int SIMT_SMEM = SIMT_FIN_BYTES + 2 * SIMT_ACT_BYTES + 4 * 81 * 4 + 96 * 4;
+
+__global__ void __launch_bounds__(128) bk_forward_simt_kernel(const FwdArgs args)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __half *fin = reinterpret_cast<__half *>(smem);
+    __half *act0 = reinterpret_cast<__half *>(smem + SIMT_FIN_BYTES);
+    __half *act1 = reinterpret_cast<__half *>(smem + SIMT_FIN_BYTES + SIMT_ACT_BYTES);
+    float *red = reinterpret_cast<float *>(smem + SIMT_FIN_BYTES + 2 * SIMT_ACT_BYTES);   // [4][81]
+    float *logit = red + 4 * 81;
+    const int item = blockIdx.x;
+    const int b = item / args.n_nets, net = args.first_net + item % args.n_nets;
+    const int co = threadIdx.x, lane = co & 31, warp = co >> 5;
+    const uint8_t *blob = args.blob[net];
+    const int g = b / BK_GROUP, bi = b - g * BK_GROUP;
+
+    for (int i = co; i < (SIMT_FIN_BYTES + 2 * SIMT_ACT_BYTES) / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0u;
+    __syncthreads();
+    // unpack this board's planes from the conv layout into a 13x13 zero-padded raster
+    const uint4 *src = reinterpret_cast<const uint4 *>(args.feats + (size_t)g * BK_F_GROUP_BYTES);
+    for (int i = co; i < 81 * BK_F_CHUNKS; i += 128) {
+        const int p = i / BK_F_CHUNKS, c = i - p * BK_F_CHUNKS;
+        const int x = p / 9, y = p - 9 * x;
+        const uint4 v = src[c * BK_F_ROWS_G + bi * BK_F_ROWS_B + 22 + 11 * x + y];
+        *reinterpret_cast<uint4 *>(fin + ((x + 2) * 13 + (y + 2)) * 32 + c * 8) = v;
+    }
+    __syncthreads();
+
+    float acc[81];
+    const float *bias = reinterpret_cast<const float *>(blob + BK_W_BIAS_OFF);
+    __half *in = act0, *out = act1;
+    for (int layer = 0; layer < 7; ++layer) {
+#pragma unroll
+        for (int p = 0; p < 81; ++p) acc[p] = 0.0f;
+        const int ntap = layer == 0 ? 25 : 9, nchunk = layer == 0 ? 4 : 16, kw = layer == 0 ? 5 : 3;
+        const uint8_t *wl = blob + (layer == 0 ? BK_W_L0_OFF : BK_W_L_OFF(layer));
+        for (int tap = 0; tap < ntap; ++tap) {
+            const int ti = tap / kw, tj = tap - kw * ti;
+            for (int c = 0; c < nchunk; ++c) {
+                const int k = tap * nchunk * 8 + c * 8;
+                const uint4 wv = *reinterpret_cast<const uint4 *>(wl + (size_t)(k >> 6) * BK_STAGE_BYTES + ((k & 63) >> 3) * 2048 + co * 16);
+                const __half2 *wh = reinterpret_cast<const __half2 *>(&wv);
+                const float2 w01 = __half22float2(wh[0]), w23 = __half22float2(wh[1]), w45 = __half22float2(wh[2]),
+                             w67 = __half22float2(wh[3]);
+#pragma unroll
+                for (int p = 0; p < 81; ++p) {
+                    const int x = p / 9, y = p - 9 * (p / 9);
+                    const uint4 av = layer == 0
+                                         ? *reinterpret_cast<const uint4 *>(fin + ((x + ti) * 13 + (y + tj)) * 32 + c * 8)
+                                         : *reinterpret_cast<const uint4 *>(in + ((x + ti) * 11 + (y + tj)) * 128 + c * 8);
+                    const __half2 *ah = reinterpret_cast<const __half2 *>(&av);
+                    const float2 a01 = __half22float2(ah[0]), a23 = __half22float2(ah[1]), a45 = __half22float2(ah[2]),
+                                 a67 = __half22float2(ah[3]);
+                    float s = acc[p];
+                    s = fmaf(a01.x, w01.x, s); s = fmaf(a01.y, w01.y, s);
+                    s = fmaf(a23.x, w23.x, s); s = fmaf(a23.y, w23.y, s);
+                    s = fmaf(a45.x, w45.x, s); s = fmaf(a45.y, w45.y, s);
+                    s = fmaf(a67.x, w67.x, s); s = fmaf(a67.y, w67.y, s);
+                    acc[p] = s;
+                }
+            }
+        }
+        const float bv = bias[layer * 128 + co];
+        if (layer < 6) {
+#pragma unroll
+            for (int p = 0; p < 81; ++p) {
+                const int x = p / 9, y = p - 9 * (p / 9);
+                out[((x + 1) * 11 + (y + 1)) * 128 + co] = __float2half_rn(fmaxf(acc[p] + bv, 0.0f));
+            }
+            __syncthreads();
+            __half *tmp = in; in = out; out = tmp;
+            if (layer == 0) { in = act1; out = act0; }
+        } else {
+            const float hw = reinterpret_cast<const float *>(blob + BK_W_HEADW_OFF)[co];
+#pragma unroll
+            for (int p = 0; p < 81; ++p) {
+                float v = fmaxf(acc[p] + bv, 0.0f) * hw;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) red[warp * 81 + p] = v;
+            }
+            __syncthreads();
+            if (co < 81)
+                logit[co] = red[co] + red[81 + co] + red[162 + co] + red[243 + co] +
+                            reinterpret_cast<const float *>(blob + BK_W_HEADB_OFF)[co];
+            __syncthreads();
+            if (warp == 0)
+                finish_board(logit, net, blob, args.logits ? args.logits + (size_t)b * 81 : nullptr,
+                             args.probs ? args.probs + (size_t)b * 81 : nullptr, args.value ? args.value + b : nullptr, lane);
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+static inline uint16_t f2h(float f)
+{
+    const __half h = __float2half_rn(f);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+}
+
+// Packs BatchNorm-folded fp32 parameters into the blob described in bk_layout.h (host memory -> host memory).
+//   w0 [128][27][5][5], w16 [6][128][128][3][3], bias [7][128], head_w [128], head_b [81],
+//   vtail (nullable) = {bn_scale, bn_shift, lin2_b, W1'[64][81], b1'[64], w2[64]}
+extern "C" int bk_weights_pack(const float *w0, const float *w16, const float *bias, const float *head_w,
+                               const float *head_b, const float *vtail, void *blob_out)
+{
+    if (!w0 || !w16 || !bias || !head_w || !head_b || !blob_out) return -1;
+    uint8_t *blob = static_cast<uint8_t *>(blob_out);
+    memset(blob, 0, BK_W_BLOB_BYTES);
+    uint16_t *h0 = reinterpret_cast<uint16_t *>(blob + BK_W_L0_OFF);
+    for (int co = 0; co < 128; ++co)
+        for (int ci = 0; ci < 27; ++ci)
+            for (int tap = 0; tap < 25; ++tap) {
+                const int k = tap * 32 + ci;
+                h0[(size_t)(k >> 6) * (BK_STAGE_BYTES / 2) + ((k & 63) >> 3) * 1024 + co * 8 + (k & 7)] =
+                    f2h(w0[(co * 27 + ci) * 25 + tap]);
+            }
+    for (int l = 1; l <= 6; ++l) {
+        uint16_t *hl = reinterpret_cast<uint16_t *>(blob + BK_W_L_OFF(l));
+        const float *wl = w16 + (size_t)(l - 1) * 128 * 128 * 9;
+        for (int co = 0; co < 128; ++co)
+            for (int ci = 0; ci < 128; ++ci)
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int k = tap * 128 + ci;
+                    hl[(size_t)(k >> 6) * (BK_STAGE_BYTES / 2) + ((k & 63) >> 3) * 1024 + co * 8 + (k & 7)] =
+                        f2h(wl[((size_t)co * 128 + ci) * 9 + tap]);
+                }
+    }
+    memcpy(blob + BK_W_BIAS_OFF, bias, 7 * 128 * 4);
+    memcpy(blob + BK_W_HEADW_OFF, head_w, 128 * 4);
+    memcpy(blob + BK_W_HEADB_OFF, head_b, 81 * 4);
+    if (vtail) {
+        float *vt = reinterpret_cast<float *>(blob + BK_W_VT_OFF);
+        vt[0] = vtail[0]; vt[1] = vtail[1]; vt[2] = vtail[2]; vt[3] = 0.0f;
+        float *w1t = reinterpret_cast<float *>(blob + BK_W_VT_W1T_OFF);
+        const float *w1 = vtail + 3;
+        for (int j = 0; j < 64; ++j)
+            for (int p = 0; p < 81; ++p) w1t[p * 64 + j] = w1[j * 81 + p];
+        memcpy(blob + BK_W_VT_B1_OFF, vtail + 3 + 64 * 81, 64 * 4);
+        memcpy(blob + BK_W_VT_W2_OFF, vtail + 3 + 64 * 81 + 64, 64 * 4);
+    }
+    return 0;
+}
+
+static unsigned int *g_dbg_host = nullptr;   // pinned, device-visible; survives a trapped kernel
+
+extern "C" int bk_debug_words(unsigned int *out8)
+{
+    for (int i = 0; i < 8; ++i) out8[i] = g_dbg_host ? g_dbg_host[i] : 0u;
+    return g_dbg_host ? 0 : -1;
+}
+
+static int forward_impl(const void *feats_conv, const void *blob_policy, const void *blob_value, float *logits,
+                        float *probs, float *value, int B, int flags, cudaStream_t stream, float *dump, int dump_pass);
+
+extern "C" int bk_forward_debug(const void *feats_conv, const void *blob_policy, const void *blob_value, float *logits,
+                                float *probs, float *value, int B, int flags, cudaStream_t stream, float *dump, int dump_pass)
+{
+    return forward_impl(feats_conv, blob_policy, blob_value, logits, probs, value, B, flags, stream, dump, dump_pass);
+}
+
+extern "C" int bk_forward(const void *feats_conv, const void *blob_policy, const void *blob_value, float *logits,
+                          float *probs, float *value, int B, int flags, cudaStream_t stream)
+{
+    return forward_impl(feats_conv, blob_policy, blob_value, logits, probs, value, B, flags, stream, nullptr, -1);
+}
+
+static int forward_impl(const void *feats_conv, const void *blob_policy, const void *blob_value, float *logits,
+                        float *probs, float *value, int B, int flags, cudaStream_t stream, float *dump, int dump_pass)
+{
+    if (B <= 0) return 0;
+    const bool do_p = flags & BK_FWD_POLICY, do_v = flags & BK_FWD_VALUE;
+    if (!do_p && !do_v) return -1;
+    if ((do_p && !blob_policy) || (do_v && (!blob_value || !value)) || !feats_conv) return -1;
+    FwdArgs a;
+    a.feats = static_cast<const uint8_t *>(feats_conv);
+    a.blob[0] = static_cast<const uint8_t *>(blob_policy);
+    a.blob[1] = static_cast<const uint8_t *>(blob_value);
+    a.logits = logits; a.probs = probs; a.value = value;
+    a.B = B; a.G = (B + BK_GROUP - 1) / BK_GROUP;
+    a.n_nets = (do_p ? 1 : 0) + (do_v ? 1 : 0);
+    a.first_net = do_p ? 0 : 1;
+    a.swap_lbo_sbo = (flags & 0x100) ? 1 : 0;
+    a.dump = dump; a.dump_pass = dump_pass;
+    if (!g_dbg_host) {
+        if (cudaHostAlloc((void **)&g_dbg_host, 64, cudaHostAllocMapped) != cudaSuccess) g_dbg_host = nullptr;
+        else memset(g_dbg_host, 0, 64);
+    }
+    a.dbg = nullptr;
+    if (g_dbg_host) cudaHostGetDevicePointer((void **)&a.dbg, g_dbg_host, 0);
+    cudaError_t e;
+    if (flags & BK_FWD_SIMT) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            e = cudaFuncSetAttribute(bk_forward_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SIMT_SMEM);
+            if (e != cudaSuccess) return -3;
+            attr_done = true;
+        }
+        bk_forward_simt_kernel<<<B * a.n_nets, 128, SIMT_SMEM, stream>>>(a);
+    } else {
+        static int n_sm = 0;
+        if (!n_sm) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            e = cudaFuncSetAttribute(bk_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+            if (e != cudaSuccess) { n_sm = 0; return -3; }
+        }
+        const int n_items = a.G * a.n_nets;
+        const int grid = n_items < n_sm ? n_items : n_sm;
+        bk_forward_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, stream>>>(a);
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}

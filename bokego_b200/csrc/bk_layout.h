@@ -1,0 +1,53 @@
+/* bk_layout.h -- data layouts shared by the kernels, the weight packer and the host code.
+ *
+ * Conv work item = one trunk (policy or value) over a GROUP of 5 boards.
+ *
+ * Feature operand (written by bk_encode, read by layer 0), per group, fp16:
+ *     [4 channel chunks][605 rows][8 channels]           (38,720 bytes, contiguous)
+ *     row = 121*board + 22 + 11*x + y : stride-11 raster, columns 9,10 and the first two rows of
+ *     every board are zero, so a 5x5 tap (i,j) is the row shift (i-2)*11 + (j-2).
+ *
+ * Activation operand (on chip only), fp16, 128 channels:
+ *     [16 channel chunks][536 rows][8 channels], row = 12 + 100*board + 10 + 10*x + y :
+ *     stride-10 raster with one zero column, one zero row above every board; a 3x3 tap (i,j) is the
+ *     row shift (i-1)*10 + (j-1).  GEMM rows 0..511 = 4 M-tiles of 128; 405 of them are real squares.
+ *
+ * Both are "K-major, no swizzle" UMMA operands whose 8-row core matrices are contiguous in M
+ * (stride-byte-offset 128) -- so a row-shifted window is just a different start address.
+ *
+ * Weight blob (per net), bytes:
+ *     layer 0 : 13 stages x 16 KiB      K = tap*32 + ci  (25 taps, ci padded 27->32, K padded 800->832)
+ *     layer l : 18 stages x 16 KiB      K = tap*128 + ci (l = 1..6)
+ *               one stage = 64 K-values for all 128 output channels: [8 k-chunks][128 co][8 k] fp16
+ *     then fp32: bias[7][128] (BatchNorm folded), head_w[128], head_b[96] (81 used),
+ *     value tail: {bn_scale, bn_shift, lin2_b, 0}, W1T[81][64] (BN1d folded, transposed), b1[64], w2[64]
+ */
+#ifndef BK_LAYOUT_H
+#define BK_LAYOUT_H
+
+#define BK_GROUP 5
+#define BK_F_CHUNKS 4
+#define BK_F_ROWS_B 121
+#define BK_F_ROWS_G 605
+#define BK_F_GROUP_BYTES (BK_F_CHUNKS * BK_F_ROWS_G * 16)
+
+#define BK_STAGE_BYTES 16384
+#define BK_L0_STAGES 13
+#define BK_L_STAGES 18
+#define BK_W_L0_OFF 0
+#define BK_W_L_OFF(l) (BK_L0_STAGES * BK_STAGE_BYTES + ((l) - 1) * BK_L_STAGES * BK_STAGE_BYTES)
+#define BK_W_BIAS_OFF (BK_L0_STAGES * BK_STAGE_BYTES + 6 * BK_L_STAGES * BK_STAGE_BYTES) /* 1,982,464 */
+#define BK_W_HEADW_OFF (BK_W_BIAS_OFF + 7 * 128 * 4)
+#define BK_W_HEADB_OFF (BK_W_HEADW_OFF + 128 * 4)
+#define BK_W_VT_OFF (BK_W_HEADB_OFF + 96 * 4)
+#define BK_W_VT_W1T_OFF (BK_W_VT_OFF + 16)
+#define BK_W_VT_B1_OFF (BK_W_VT_W1T_OFF + 81 * 64 * 4)
+#define BK_W_VT_W2_OFF (BK_W_VT_B1_OFF + 64 * 4)
+#define BK_W_BLOB_BYTES (((BK_W_VT_W2_OFF + 64 * 4) + 127) / 128 * 128)
+
+/* bk_forward flags */
+#define BK_FWD_POLICY 1      /* run the policy trunk: logits + probs */
+#define BK_FWD_VALUE 2       /* run the value trunk: value */
+#define BK_FWD_SIMT 4        /* validation path: plain CUDA-core kernel instead of tcgen05 */
+
+#endif

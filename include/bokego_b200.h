@@ -1,0 +1,94 @@
+/* bokego_b200.h -- C ABI of libbokego_b200.so: the B200 (sm_100a) implementation of BokeGo's batched
+ * leaf-evaluation / playout hot path.
+ *
+ * The reference (meiji163/bokego) is pure Python and has no FFI; the interface each entry point
+ * replaces is therefore a Python function of the reference, cited per function below
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add to bokego/nnet.py / bokego/mcts.py to bind them.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says host; buffers are caller-allocated,
+ *     contiguous, and owned by the caller; the library allocates nothing and keeps no global state
+ *     apart from one-time kernel attributes;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value: 0 = ok, BK_ERR_ARG = bad argument, BK_ERR_DEVICE = not an sm_100 device,
+ *     BK_ERR_LAUNCH = CUDA launch error (see cudaGetLastError);
+ *   - batched calls never fail per board: per-board conditions come back in masks / move codes.
+ *
+ * Position encoding (mirrors go.Game, go.py:51-66): board int8[81], index 9*x+y, +1 = 'X' (black),
+ * -1 = 'O' (white), 0 = '.'; ko int16 (-1 = None); last int16 (-1 = PASS, -2 = None); turn int16
+ * (even = black to move); libs uint8[81] = Game._libs (lazy liberty cache, go.py:220-243).
+ */
+#ifndef BOKEGO_B200_H
+#define BOKEGO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BK_OK 0
+#define BK_ERR_ARG (-1)
+#define BK_ERR_DEVICE (-2)
+#define BK_ERR_LAUNCH (-3)
+
+/* bk_forward flags */
+#define BK_FLAG_POLICY 1   /* policy trunk: logits + softmax probabilities */
+#define BK_FLAG_VALUE 2    /* value trunk: tanh value */
+#define BK_FLAG_SIMT 4     /* validation only: CUDA-core kernel over the same packed operands */
+
+/* move codes written by bk_playout_step */
+#define BK_MOVE_PASS (-1)
+#define BK_MOVE_NONE (-2)      /* self-play flavour: no legal move, game stopped (selfplay.py:44-45) */
+#define BK_MOVE_FINISHED (-3)  /* board was already done */
+#define BK_MOVE_NO_DRAWS (-4)  /* injected draw buffer exhausted */
+
+int bk_version(void);
+const char *bk_strerror(int code);
+/* 0 when the current device is sm_100 (B200); BK_ERR_DEVICE otherwise.  There is no other path. */
+int bk_device_check(void);
+
+/* ---- (a) feature planes: nnet.features (bokego/nnet.py:182-262) for B positions ----------------
+ * libs_in == NULL  -> fresh Game objects (exact liberties);  otherwise the carried Game._libs.
+ * Outputs (each may be NULL): feats_conv = fp16 operand of bk_forward, bk_feats_conv_bytes(B) bytes;
+ * feats_f32 = float32 [B][27][9][9] exactly as nnet.features returns; planes_u8 = same values as
+ * uint8 [B][27][81]; legal_out uint8 [B][81] (Game.get_legal_moves, go.py:245-260);
+ * libs_out uint8 [B][81] (Game._libs after the call). */
+size_t bk_feats_conv_bytes(int B);
+int bk_encode(const int8_t *boards, const int16_t *ko, const int16_t *last, const int16_t *turn,
+              const uint8_t *libs_in, void *feats_conv, float *feats_f32, uint8_t *planes_u8,
+              uint8_t *legal_out, uint8_t *libs_out, int B, void *stream);
+
+/* ---- (b) nets: PolicyNet.forward (nnet.py:19-57), ValueNet.forward (nnet.py:59-113), SOFT (nnet.py:16)
+ * Weights: fold BatchNorm on the host, then bk_weights_pack (HOST pointers in, HOST blob out, blob is
+ * bk_weights_blob_bytes() long) and copy the blob to the device once per net.
+ *   w0 [128][27][5][5], w16 [6][128][128][3][3], bias [7][128], head_w [128] (conv.21.weight),
+ *   head_b [81] (conv.21.bias), vtail NULL for a PolicyNet, else
+ *   {bn_scale, bn_shift, lin2_bias, W1[64][81], b1[64], w2[64]} with BatchNorm folded.
+ * bk_forward: logits/probs float32 [B][81] (may be NULL), value float32 [B]. */
+size_t bk_weights_blob_bytes(void);
+int bk_weights_pack(const float *w0, const float *w16, const float *bias, const float *head_w,
+                    const float *head_b, const float *vtail, void *blob_host_out);
+int bk_forward(const void *feats_conv, const void *blob_policy, const void *blob_value, float *logits,
+               float *probs, float *value, int B, int flags, void *stream);
+
+/* ---- (c) playout stepping ------------------------------------------------------------------------
+ * mode 0: Go_MCTS.get_move + make_move + is_game_over (bokego/mcts.py:340-364)
+ * mode 1: legal_sample + playout loop (bin/selfplay.py:18-47)
+ * State is updated in place; done[b] != 0 boards are skipped.  probs float32 [B][81] are used as given.
+ * Random draws: q_inj != NULL -> float32 [B][q_vecs][81] Exp(1) variates (what torch.multinomial
+ * would draw); else the counter-based stream keyed (seed, game0 + b, turn, try). */
+int bk_playout_step(int8_t *boards, int16_t *ko, int16_t *last, int16_t *turn, uint8_t *libs,
+                    uint8_t *done, const float *probs, const float *q_inj, int q_vecs, uint64_t seed,
+                    uint32_t game0, int mode, int max_turn, int16_t *moves_out, int B, void *stream);
+/* Game.score (go.py:202-218) minus komi, and Go_MCTS.reward's +-1 (mcts.py:330-338) */
+int bk_score(const int8_t *boards, float komi, float *score_out, int8_t *reward_out, int B, void *stream);
+/* the counter-based Exp(1) stream itself: q float32 [B][81] for (seed, game0 + b, move, try) */
+int bk_exp_draws(uint64_t seed, uint32_t game0, uint32_t move, uint32_t tr, float *q, int B, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,132 @@
+"""CPU emulation of the conv kernel's data path: the packed weight blob (bk_weights_pack, a host function of
+the shared library), the feature / activation operand layouts, the tap row shifts and the row bookkeeping of
+bk_forward.cu -- executed with numpy instead of tcgen05.  Comparing the result with the reference's logits
+proves the index arithmetic before a GPU is involved.  CPU only."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from oracle import nets as onets
+
+GROUP, F_ROWS_B, F_ROWS_G = 5, 121, 605
+A_MARGIN, A_ROWS, F_MARGIN, F_ROWS = 12, 536, 24, 653
+STAGE_H = 8192                      # halfs per 16 KiB stage
+L0_STAGES, L_STAGES = 13, 18
+
+
+def _fold(sd):
+    """BatchNorm folding exactly as bokego_b200.batched.PackedNet does it"""
+    ws, bs = [], []
+    for i in (0, 3, 6, 9, 12, 15, 18):
+        w, b = torch.from_numpy(sd[f"conv.{i}.weight"]).double(), torch.from_numpy(sd[f"conv.{i}.bias"]).double()
+        s = torch.from_numpy(sd[f"conv.{i + 1}.weight"]).double() / torch.sqrt(
+            torch.from_numpy(sd[f"conv.{i + 1}.running_var"]).double() + 1e-5)
+        ws.append(w * s[:, None, None, None])
+        bs.append((b - torch.from_numpy(sd[f"conv.{i + 1}.running_mean"]).double()) * s
+                  + torch.from_numpy(sd[f"conv.{i + 1}.bias"]).double())
+    f32 = lambda t: np.ascontiguousarray(t.float().numpy())
+    return f32(ws[0]), f32(torch.stack(ws[1:])), f32(torch.stack(bs)), \
+        f32(torch.from_numpy(sd["conv.21.weight"]).reshape(128)), f32(torch.from_numpy(sd["conv.21.bias"]).reshape(81))
+
+
+def _pack(sd):
+    from bokego_b200 import _lib
+    L = _lib.lib()
+    w0, w16, bias, hw, hb = _fold(sd)
+    blob = np.zeros(L.bk_weights_blob_bytes(), np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.bk_weights_pack(p(w0), p(w16), p(bias), p(hw), p(hb), None, p(blob)) == 0
+    return blob, bias, hw, hb
+
+
+def _stage(blob, byte_off, s):
+    """one 16 KiB K-slab -> float32 [64 k][128 co]"""
+    h = blob[byte_off + s * 16384: byte_off + (s + 1) * 16384].view(np.float16).astype(np.float32)
+    return h.reshape(8, 128, 8).transpose(0, 2, 1).reshape(64, 128)      # [kchunk][co][k8] -> [k][co]
+
+
+def _emulate(planes_u8, blob, bias, hw, hb):
+    """planes uint8 [5,27,81] (one group) -> logits [5,81] following bk_forward.cu step by step"""
+    F = np.zeros((4, F_ROWS, 8), np.float32)
+    for b in range(planes_u8.shape[0]):
+        for p in range(81):
+            r = F_MARGIN + F_ROWS_B * b + 22 + 11 * (p // 9) + p % 9
+            v = np.zeros(32, np.float32); v[:27] = planes_u8[b, :, p]
+            F[:, r, :] = v.reshape(4, 8)
+    A = np.zeros((16, A_ROWS, 8), np.float32)
+    # ---- layer 0: two passes (tiles 0..3, tile 4), 13 stages of two 5x5 taps ----
+    D = np.zeros((640, 128), np.float32)
+    for s in range(L0_STAGES):
+        W = _stage(blob, 0, s)
+        for kk in range(4):
+            tap = 2 * s + (kk >> 1)
+            off = (tap // 5 - 2) * 11 + (tap % 5 - 2) if tap < 25 else 0
+            c0 = (kk & 1) * 2
+            rows = F_MARGIN + np.arange(640) + off
+            ok = rows < F_ROWS                                   # rows past the buffer feed invalid outputs only
+            a = np.zeros((640, 16), np.float32)
+            a[ok] = np.concatenate([F[c0, rows[ok]], F[c0 + 1, rows[ok]]], axis=1)
+            D += a @ W[kk * 16:(kk + 1) * 16]
+    for r0 in range(640):
+        board, rem = divmod(r0, F_ROWS_B)
+        if board >= GROUP or rem < 22:
+            continue
+        x, y = divmod(rem - 22, 11)
+        if y >= 9:
+            continue
+        dest = 100 * board + 10 + 10 * x + y
+        o = np.maximum(D[r0] + bias[0], 0).astype(np.float16).astype(np.float32)
+        A[:, A_MARGIN + dest, :] = o.reshape(16, 8)
+    # ---- layers 1..6 ----
+    for layer in range(1, 7):
+        off_b = L0_STAGES * 16384 + (layer - 1) * L_STAGES * 16384
+        D = np.zeros((512, 128), np.float32)
+        for s in range(L_STAGES):
+            W = _stage(blob, off_b, s)
+            tap = s >> 1
+            off = (tap // 3 - 1) * 10 + (tap % 3 - 1)
+            rows = A_MARGIN + np.arange(512) + off
+            for kk in range(4):
+                c0 = (s & 1) * 8 + kk * 2
+                a = np.concatenate([A[c0, rows], A[c0 + 1, rows]], axis=1)
+                D += a @ W[kk * 16:(kk + 1) * 16]
+        logits = np.zeros((GROUP, 81), np.float32)
+        for r in range(512):
+            board, rem = divmod(r, 100)
+            if board >= GROUP or rem < 10 or (rem - 10) % 10 >= 9:
+                continue
+            act = np.maximum(D[r] + bias[layer], 0)
+            if layer < 6:
+                A[:, A_MARGIN + r, :] = act.astype(np.float16).astype(np.float32).reshape(16, 8)
+            else:
+                sq = 9 * ((rem - 10) // 10) + (rem - 10) % 10
+                logits[board, sq] = act @ hw + hb[sq]
+    return logits
+
+
+def test_emulated_kernel_matches_reference_logits(positions, nets_golden, sd17):
+    blob, bias, hw, hb = _pack(sd17)
+    src = nets_golden["src"]
+    for g0 in (0, 5):
+        planes = positions["feats"][src[g0:g0 + 5]]
+        got = _emulate(planes, blob, bias, hw, hb)
+        want = nets_golden["logits17"][g0:g0 + 5]
+        assert np.abs(got - want).max() < 5e-2
+        assert (got.argmax(1) == want.argmax(1)).all()
+
+
+def test_partial_group_is_isolated(positions, nets_golden, sd17):
+    """boards of a group do not leak into each other: a group holding 2 boards gives the same rows"""
+    blob, bias, hw, hb = _pack(sd17)
+    src = nets_golden["src"]
+    full = _emulate(positions["feats"][src[0:5]], blob, bias, hw, hb)
+    part = _emulate(positions["feats"][src[0:2]], blob, bias, hw, hb)
+    assert np.array_equal(full[:2], part[:2])
+
+
+def test_blob_size_and_value_tail(sd_value):
+    from bokego_b200 import _lib
+    L = _lib.lib()
+    assert L.bk_weights_blob_bytes() == 2008320 and L.bk_feats_conv_bytes(4096) == 820 * 38720
+    assert L.bk_feats_conv_bytes(1) == 38720 and L.bk_feats_conv_bytes(0) == 0
