@@ -33,6 +33,8 @@ def _sig(L):
     L.bk_weights_pack.argtypes = [vp] * 7
     L.bk_encode.restype = i32
     L.bk_encode.argtypes = [vp] * 10 + [i32, vp]
+    L.bk_repack_f32.restype = i32
+    L.bk_repack_f32.argtypes = [vp, vp, i32, vp]
     L.bk_forward.restype = i32
     L.bk_forward.argtypes = [vp] * 6 + [i32, i32, vp]
     L.bk_forward_debug.restype = i32

@@ -94,6 +94,20 @@ def features_batch(pos, fresh_libs=None, want=("conv", "legal", "libs"), out=Non
     return out
 
 
+def repack_planes(feats_f32):
+    """float32 [B,27,9,9] planes on the device -> the fp16 operand of policy_value_batch"""
+    L = _lib.lib()
+    dev = _lib.require_device(feats_f32.device)
+    B = feats_f32.shape[0]
+    _want(feats_f32, torch.float32, (B, 27, 9, 9), "feats_f32", dev)
+    conv = torch.empty(L.bk_feats_conv_bytes(B), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.bk_repack_f32(_lib.ptr(feats_f32), _lib.ptr(conv), B, _lib.stream_ptr(dev))
+    _lib.check(rc, "bk_repack_f32")
+    _lib.count_launch()
+    return conv
+
+
 class PackedNet:
     """Device-resident weight blob of one PolicyNet / ValueNet (BatchNorm folded, fp16 conv operands)."""
 

@@ -138,13 +138,59 @@ bk_encode_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ 
     }
 }
 
+// float32 planes [B][27][81] (what nnet.features returns) -> the conv kernel's fp16 operand layout.
+// Used by the drop-in PolicyNet/ValueNet.forward, whose argument is the reference's float tensor.
+__global__ void __launch_bounds__(128)
+bk_repack_kernel(const float *__restrict__ feats_f32, uint4 *__restrict__ feats_conv, int B, int slots)
+{
+    const int slot = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (slot >= slots) return;
+    const int g = slot / BK_GROUP, bi = slot - g * BK_GROUP;
+    uint4 *base = feats_conv + (size_t)g * (BK_F_CHUNKS * BK_F_ROWS_G) + bi * BK_F_ROWS_B;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int r = lane; r < BK_F_ROWS_B; r += 32) {
+        const int q = r - 22;
+        const int x = q / 11, y = q - 11 * x;
+        const bool pad = r < 22 || y >= 9 || slot >= B;
+        if (pad) {
+#pragma unroll
+            for (int c = 0; c < BK_F_CHUNKS; ++c) base[c * BK_F_ROWS_G + r] = z;
+        } else {
+            const float *src = feats_f32 + (size_t)slot * 27 * BK_NSQ + 9 * x + y;
+#pragma unroll
+            for (int c = 0; c < BK_F_CHUNKS; ++c) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = (8 * c + e) < 27 ? src[(8 * c + e) * BK_NSQ] : 0.0f;
+                uint4 o;
+                const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+                const __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+                o.x = *reinterpret_cast<const uint32_t *>(&h0); o.y = *reinterpret_cast<const uint32_t *>(&h1);
+                o.z = *reinterpret_cast<const uint32_t *>(&h2); o.w = *reinterpret_cast<const uint32_t *>(&h3);
+                base[c * BK_F_ROWS_G + r] = o;
+            }
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int bk_repack_f32(const float *feats_f32, void *feats_conv, int B, cudaStream_t stream)
+{
+    if (B <= 0) return 0;
+    if (!feats_f32 || !feats_conv) return -1;
+    const int slots = ((B + BK_GROUP - 1) / BK_GROUP) * BK_GROUP;
+    bk_repack_kernel<<<(slots + 3) / 4, 128, 0, stream>>>(feats_f32, (uint4 *)feats_conv, B, slots);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
 
 extern "C" int bk_encode(const int8_t *boards, const int16_t *ko, const int16_t *last, const int16_t *turn,
                                 const uint8_t *libs_in, void *feats_conv, float *feats_f32, uint8_t *planes_u8,
                                 uint8_t *legal_out, uint8_t *libs_out, int B, cudaStream_t stream)
 {
     if (B <= 0) return 0;
+    if (!boards || !ko || !last || !turn) return -1;
     const int slots = feats_conv ? ((B + BK_GROUP - 1) / BK_GROUP) * BK_GROUP : B;
     const int warps_per_block = 4;
     const int grid = (slots + warps_per_block - 1) / warps_per_block;

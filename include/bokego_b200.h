@@ -61,6 +61,10 @@ int bk_encode(const int8_t *boards, const int16_t *ko, const int16_t *last, cons
               const uint8_t *libs_in, void *feats_conv, float *feats_f32, uint8_t *planes_u8,
               uint8_t *legal_out, uint8_t *libs_out, int B, void *stream);
 
+/* float32 planes [B][27][9][9] (the tensor nnet.features returns and PolicyNet.forward receives,
+ * nnet.py:54-57) -> the fp16 operand of bk_forward.  Values are rounded to fp16 (exact for feature planes). */
+int bk_repack_f32(const float *feats_f32, void *feats_conv, int B, void *stream);
+
 /* ---- (b) nets: PolicyNet.forward (nnet.py:19-57), ValueNet.forward (nnet.py:59-113), SOFT (nnet.py:16)
  * Weights: fold BatchNorm on the host, then bk_weights_pack (HOST pointers in, HOST blob out, blob is
  * bk_weights_blob_bytes() long) and copy the blob to the device once per net.

@@ -14,6 +14,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """make sure the in-tree shared libraries match the sources (no-op when they are up to date)"""
+    from bokego_b200 import build as b
+    b.build()
+    from oracle import cpu as ocpu
+    ocpu.build()
+
+
 def _load(name):
     return dict(np.load(os.path.join(GOLDEN, name)))
 
