@@ -38,7 +38,7 @@ def _sig(L):
     L.bk_forward.restype = i32
     L.bk_forward.argtypes = [vp] * 6 + [i32, i32, vp]
     L.bk_forward_debug.restype = i32
-    L.bk_forward_debug.argtypes = [vp] * 6 + [i32, i32, vp, vp, i32]
+    L.bk_forward_debug.argtypes = [vp] * 6 + [i32, i32, vp, vp, i32, vp]
     L.bk_debug_words.restype = i32
     L.bk_debug_words.argtypes = [vp]
     L.bk_playout_step.restype = i32

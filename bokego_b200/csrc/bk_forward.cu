@@ -3,18 +3,23 @@
 // Replaces PolicyNet.forward (/root/reference/bokego/nnet.py:19-57), ValueNet.forward (nnet.py:59-113),
 // Conv2dUntiedBias.forward (nnet.py:175-180) and SOFT (nnet.py:16) in eval mode, BatchNorm folded.
 //
-// One persistent CTA per SM.  A work item is one trunk (policy or value) over a group of 5 boards:
-//   * activations of the whole group (5 x 100 padded rows x 128 ch, fp16) stay in shared memory for all
-//     7 conv layers; each layer is an implicit GEMM  D[512 rows, 128 co] += A[rows + tap shift, ci] * W[tap]
-//     issued as tcgen05.mma (cta_group::1, kind::f16, M=128, N=128, K=16) with fp32 accumulators for the
-//     four 128-row tiles resident in TMEM (4 x 128 = 512 columns);
+// One persistent CTA per SM.  A work item is one trunk (policy or value) over up to 5 boards of one group:
+//   * activations of the item (<= 5 x 100 padded rows x 128 ch, fp16) stay in shared memory for all 7 conv
+//     layers; each layer is an implicit GEMM  D[rows, 128 co] += A[rows + tap shift, ci] * W[tap]  issued as
+//     tcgen05.mma (cta_group::1, kind::f16, M=128, N=128, K=16) with fp32 accumulators for up to four 128-row
+//     tiles resident in TMEM (4 x 128 = 512 columns);
 //   * weights stream L2 -> shared memory as 16 KiB K-slabs (cp.async.bulk + mbarrier, 3 stages); every slab
-//     is used by all four tiles before its slot is recycled;
-//   * the epilogue warps pull accumulators out of TMEM (tcgen05.ld), add the folded bias, apply ReLU, round to
-//     fp16 and write the next layer's operand in place; after the last layer they compute the 1x1 head with
-//     the untied bias and finish with the 81-way softmax (policy) or the small dense tail + tanh (value).
-// Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4), warp 8 = bulk-copy
-// producer (+ TMEM allocation), warp 9 = MMA issuer (one elected lane).
+//     is used by all tiles of the pass before its slot is recycled;
+//   * the folded bias enters through the tensor core as well: two extra K rows (bias split into fp16 hi + lo)
+//     multiplied by a constant all-ones operand, so the accumulators leave TMEM ready for ReLU;
+//   * 16 epilogue warps (one thread per GEMM row: TMEM lane quarter = warp % 4, tile = warp / 4) pull the
+//     accumulators out of TMEM (tcgen05.ld), apply ReLU, round to fp16 and write the next layer's operand in
+//     place; after the last layer they compute the 1x1 head with the untied bias and finish with the 81-way
+//     softmax (policy) or the small dense tail + tanh (value).
+// Warp roles: warps 0-15 epilogue, warp 16 = bulk-copy producer (+ TMEM allocation), warp 17 = MMA issuer
+// (warp-uniform control flow, lane 0 issues).
+// Items that do not fill a whole round of the grid are split into smaller board ranges (fewer M tiles each)
+// so that the last round, and small batches, spread over more SMs.
 //
 // A plain CUDA-core kernel over the same packed operands (BK_FWD_SIMT) exists to validate the packing and
 // the tensor-core path against each other on the GPU; it is not a fallback and is never selected implicitly.
@@ -31,35 +36,37 @@ namespace {
 // shared-memory plan of the tcgen05 kernel
 // ------------------------------------------------------------------------------------------------------
 constexpr int A_MARGIN = 12;                       // zero rows in front of GEMM row 0 (|tap shift| <= 11)
-constexpr int A_ROWS = A_MARGIN + 512 + 12;        // 536
+constexpr int A_ROWS = A_MARGIN + 512;             // 524: the rows behind a chunk are the next chunk's margin
 constexpr int A_LBO = A_ROWS * 16;                 // bytes between consecutive 8-channel chunks
-constexpr int A_BYTES = 16 * A_LBO;                // 137,216
+constexpr int A_BYTES = 16 * A_LBO;                // 134,144
 constexpr int F_MARGIN = 24;                       // |5x5 tap shift| <= 24
-constexpr int F_ROWS = F_MARGIN + BK_F_ROWS_G + 24;  // 653
+constexpr int F_ROWS = F_MARGIN + BK_F_ROWS_G;     // 629
 constexpr int F_LBO = F_ROWS * 16;
-constexpr int F_BYTES = BK_F_CHUNKS * F_LBO;       // 41,792
+constexpr int F_BYTES = (BK_F_CHUNKS * F_LBO + F_MARGIN * 16 + 127) / 128 * 128;   // 40,704 (+ zero rows behind chunk 3)
 constexpr int N_STAGES = 3;
+constexpr int ONES_BYTES = 4096;                   // [2 k-chunks][128 rows][8]: 1.0 in k = 0, 1
 constexpr int OFF_A = 0;
-constexpr int OFF_F = OFF_A + A_BYTES;
+constexpr int OFF_F = OFF_A + A_BYTES;             // F's front margin doubles as the rows behind A's last chunk
 constexpr int OFF_W = OFF_F + F_BYTES;
-constexpr int OFF_MISC = OFF_W + N_STAGES * BK_STAGE_BYTES;   // 228,160
-// misc: barriers (16 x 8 B), tmem base, two float[512] scratch arrays
-constexpr int OFF_BAR = OFF_MISC;
+constexpr int OFF_ONES = OFF_W + N_STAGES * BK_STAGE_BYTES;
+constexpr int OFF_BAR = OFF_ONES + ONES_BYTES;     // barriers (16 x 8 B)
 constexpr int OFF_TMEM = OFF_BAR + 128;
-constexpr int OFF_PART = OFF_TMEM + 16;            // float[512]: partial head sums of column half 1
-constexpr int OFF_LOGIT = OFF_PART + 2048;         // float[512]: head output per GEMM row
-constexpr int SMEM_BYTES = OFF_LOGIT + 2048;       // 232,400 <= 232,448
+constexpr int OFF_LOGIT = OFF_TMEM + 16;           // float[5][81]: head output per square
+constexpr int SMEM_BYTES = OFF_LOGIT + 1664;       // 229,904
 static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KiB");
+static_assert(OFF_W % 128 == 0 && OFF_ONES % 128 == 0, "operand alignment");
 
 enum { BAR_WFULL = 0, BAR_WEMPTY = 3, BAR_ACC = 6, BAR_ACT = 7, BAR_FFULL = 8, BAR_FEMPTY = 9 };
 
-constexpr int N_EPI_WARPS = 8;
-constexpr int WARP_PRODUCER = 8;
-constexpr int WARP_MMA = 9;
-constexpr int N_THREADS = 320;
+constexpr int N_EPI_WARPS = 16;
+constexpr int WARP_PRODUCER = 16;
+constexpr int WARP_MMA = 17;
+constexpr int N_THREADS = 576;
 
 // instruction descriptor: D=f32 (bit 4), A=B=f16 (0), both K-major (0), N=128 (>>3 at bit 17), M=128 (>>4 at bit 24)
 constexpr uint32_t IDESC = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// high word of every shared-memory matrix descriptor used here: stride between 8-row groups = 128 B, version 1
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
 
 // ------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -128,13 +135,14 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
 {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accum)
 {
+    const uint64_t adesc = ((uint64_t)DESC_HI << 32) | a_lo, bdesc = ((uint64_t)DESC_HI << 32) | b_lo;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accum)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar)
@@ -155,49 +163,143 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr)
         : "memory");
 }
+// one elected lane of a converged warp (the compiler then knows a single thread issues what follows)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// K-major, no-swizzle shared-memory matrix descriptor (sm_100 format: version field = 1).
-//   lbo = byte distance between the two 8-element K chunks of one MMA, sbo = between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+// Low word of a K-major, no-swizzle shared-memory matrix descriptor: start address and the byte distance
+// between the two 8-element K chunks of one MMA.  Rows are 16 B apart, so adding n to the word moves the
+// operand window n rows down (all shared-memory addresses are below 2^18).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo)
 {
-    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16);
-    const uint32_t hi = (sbo >> 4) | (1u << 14);
-    return ((uint64_t)hi << 32) | lo;
+    return ((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16);
 }
 
 // ------------------------------------------------------------------------------------------------------
-// row bookkeeping
+// work items, passes, row bookkeeping
 // ------------------------------------------------------------------------------------------------------
-// layers 1..6: GEMM row r (0..511) -> is it a real square?  (in place: destination row = r)
-__device__ __forceinline__ bool act_row_valid(int r, int &board, int &sq)
+struct FwdArgs {
+    const uint8_t *feats;      // [G][BK_F_GROUP_BYTES]
+    const uint8_t *blob[2];    // policy, value
+    float *logits, *probs, *value;
+    int B, G, n_nets, first_net;
+    int n_items;               // G * n_nets (group, net) pairs
+    int n_whole;               // the first n_whole pairs are one item each; the rest are split ...
+    int split;                 // ... into `split` board ranges each
+    int n_virtual;             // n_whole + (n_items - n_whole) * split
+    float *dump;               // diagnostic: raw accumulators [640][128] of pass `dump_pass` (first item of CTA 0)
+    int dump_pass;
+    long long *prof;           // diagnostic: clock64 stamps of CTA 0, 4 per pass
+    unsigned int *dbg;         // host-mapped words written before a bounded wait traps
+};
+
+struct Item { int g, net, lo, nb; };
+
+// virtual item index -> (group, net, first board, board count); false when the range is empty
+__device__ __forceinline__ bool decode_item(const FwdArgs &a, int v, Item &it)
+{
+    int pair = v, lo = 0, hi = BK_GROUP;
+    if (v >= a.n_whole) {
+        const int j = v - a.n_whole;
+        pair = a.n_whole + j / a.split;
+        const int piece = j - (j / a.split) * a.split;
+        lo = piece * BK_GROUP / a.split;
+        hi = (piece + 1) * BK_GROUP / a.split;
+    }
+    it.g = pair / a.n_nets;
+    it.net = a.first_net + (pair - it.g * a.n_nets);
+    const int in_group = min(BK_GROUP, a.B - BK_GROUP * it.g);
+    it.lo = min(lo, in_group);
+    it.nb = min(hi, in_group) - it.lo;
+    return it.nb > 0;
+}
+
+// A full item takes 8 passes (layer 0 needs five 128-row tiles but TMEM holds four), a smaller one 7.
+struct Pass { int layer, tile0, n_tiles, n_stages; bool l0_last; };
+__device__ __forceinline__ int n_passes(int nb) { return nb == BK_GROUP ? 8 : 7; }
+__device__ __forceinline__ Pass pass_info(int nb, int ps)
+{
+    Pass p;
+    const int nt = (100 * nb - 1 + 127) >> 7;           // tiles of the stride-10 raster (layers 1..6)
+    if (nb == BK_GROUP) {
+        p.layer = ps < 2 ? 0 : ps - 1;
+        p.tile0 = ps == 1 ? 4 : 0;
+        p.n_tiles = ps == 0 ? 4 : (ps == 1 ? 1 : nt);
+        p.l0_last = ps == 1;
+    } else {
+        p.layer = ps;
+        p.tile0 = 0;
+        p.n_tiles = ps == 0 ? (121 * nb - 2 + 127) >> 7 : nt;   // tiles of the stride-11 raster (layer 0)
+        p.l0_last = ps == 0;
+    }
+    p.n_stages = p.layer == 0 ? BK_L0_STAGES : BK_L_STAGES + 1;
+    return p;
+}
+
+// layers 1..6: GEMM row r (0..511) -> is it a real square of boards 0..nb-1?  (in place: destination row = r)
+__device__ __forceinline__ bool act_row_valid(int r, int nb, int &board, int &sq)
 {
     board = r / 100;
     const int rem = r - 100 * board;
     const int q = rem - 10;
     const int x = q / 10, y = q - 10 * x;
     sq = 9 * x + y;
-    return board < BK_GROUP && rem >= 10 && y < 9;
+    return board < nb && rem >= 10 && y < 9;
 }
 // layer 0: GEMM row r0 (0..639, stride-11 raster) -> destination activation row, or -1
-__device__ __forceinline__ int l0_dest_row(int r0)
+__device__ __forceinline__ int l0_dest_row(int r0, int nb)
 {
     const int board = r0 / BK_F_ROWS_B;
     const int rem = r0 - BK_F_ROWS_B * board;
-    if (board >= BK_GROUP || rem < 22) return -1;
+    if (board >= nb || rem < 22) return -1;
     const int q = rem - 22;
     const int x = q / 11, y = q - 11 * x;
     if (y >= 9) return -1;
     return 100 * board + 10 + 10 * x + y;
 }
 
-__device__ __forceinline__ uint32_t relu_pack(float a, float b)
+__device__ __forceinline__ uint32_t relu_pack(uint32_t a, uint32_t b)
 {
-    const __half2 h = __floats2half2_rn(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
+    const __half2 h = __hmax2(__floats2half2_rn(__uint_as_float(a), __uint_as_float(b)), __float2half2_rn(0.0f));
     return *reinterpret_cast<const uint32_t *>(&h);
+}
+// ReLU + fp16 rounding of 32 consecutive output channels of one row -> 4 chunks of the activation operand
+__device__ __forceinline__ void store_act32(uint8_t *smem, const uint32_t (&v)[32], int chunk0, int dest)
+{
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+        uint4 o;
+        o.x = relu_pack(v[c8 * 8 + 0], v[c8 * 8 + 1]);
+        o.y = relu_pack(v[c8 * 8 + 2], v[c8 * 8 + 3]);
+        o.z = relu_pack(v[c8 * 8 + 4], v[c8 * 8 + 5]);
+        o.w = relu_pack(v[c8 * 8 + 6], v[c8 * 8 + 7]);
+        *reinterpret_cast<uint4 *>(smem + OFF_A + (chunk0 + c8) * A_LBO + (A_MARGIN + dest) * 16) = o;
+    }
+}
+// 1x1 head conv: sum over 32 channels of relu(acc) * w
+__device__ __forceinline__ float head_dot32(const uint32_t (&v)[32], const float4 *hw4, float acc)
+{
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 w = __ldg(hw4 + c4);
+        acc = fmaf(fmaxf(__uint_as_float(v[c4 * 4 + 0]), 0.0f), w.x, acc);
+        acc = fmaf(fmaxf(__uint_as_float(v[c4 * 4 + 1]), 0.0f), w.y, acc);
+        acc = fmaf(fmaxf(__uint_as_float(v[c4 * 4 + 2]), 0.0f), w.z, acc);
+        acc = fmaf(fmaxf(__uint_as_float(v[c4 * 4 + 3]), 0.0f), w.w, acc);
+    }
+    return acc;
 }
 
 // Final stage shared by both kernels: `logit` holds the 81 head outputs (1x1 conv + untied bias) of one
@@ -253,33 +355,24 @@ __device__ __forceinline__ void finish_board(const float *logit, int net, const 
 // ------------------------------------------------------------------------------------------------------
 // the tcgen05 kernel
 // ------------------------------------------------------------------------------------------------------
-struct FwdArgs {
-    const uint8_t *feats;      // [G][BK_F_GROUP_BYTES]
-    const uint8_t *blob[2];    // policy, value
-    float *logits, *probs, *value;
-    int B, G, n_nets, first_net;
-    int swap_lbo_sbo;          // diagnostic: exchange the two descriptor strides
-    float *dump;               // diagnostic: raw accumulators [640][128] of pass `dump_pass` (first work item of CTA 0)
-    int dump_pass;
-    unsigned int *dbg;         // host-mapped words written before a bounded wait traps
-};
-
 __global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdArgs args)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
     const uint32_t s_base = smem_u32(smem);
     const uint32_t sA = s_base + OFF_A, sF = s_base + OFF_F, sW = s_base + OFF_W, sBar = s_base + OFF_BAR;
-    float *part = reinterpret_cast<float *>(smem + OFF_PART);
     float *logit = reinterpret_cast<float *>(smem + OFF_LOGIT);
-    const int n_items = args.G * args.n_nets;
+    const int grid = gridDim.x;
     if (threadIdx.x == 0 && args.dbg) g_dbg = args.dbg;
 
-    // ---- one-time setup: zero the operand buffers (pad rows must read as 0), barriers, TMEM ----------
+    // ---- one-time setup: zero the operand buffers (pad rows must read as 0), the ones operand, barriers, TMEM
     {
         uint4 *z = reinterpret_cast<uint4 *>(smem);
         const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
         for (int i = threadIdx.x; i < (A_BYTES + F_BYTES) / 16; i += N_THREADS) z[i] = zero;
+        uint4 *o = reinterpret_cast<uint4 *>(smem + OFF_ONES);
+        for (int i = threadIdx.x; i < ONES_BYTES / 16; i += N_THREADS)
+            o[i] = i < 128 ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : zero;      // k = 0, 1 -> 1.0 (fp16)
         fence_proxy_async();
     }
     if (threadIdx.x == 0) {
@@ -294,190 +387,197 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdAr
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem + OFF_TMEM);
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t *>(smem + OFF_TMEM), 0);
 
     if (warp == WARP_PRODUCER) {
         // =========================== bulk-copy producer ===========================
         if (lane == 0) {
             uint32_t wit = 0;   // weight stage counter over the whole kernel
-            auto load_feats = [&](int item) {
-                const int g = item / args.n_nets;
-                const uint8_t *src = args.feats + (size_t)g * BK_F_GROUP_BYTES;
-                mbar_arrive_expect_tx(sBar + 8 * BAR_FFULL, BK_F_GROUP_BYTES);
+            auto load_feats = [&](const Item &it) {
+                // rows of boards lo..lo+nb-1; a partial range is followed by 22 zero rows (board 0's top padding)
+                const uint8_t *src = args.feats + (size_t)it.g * BK_F_GROUP_BYTES;
+                const uint32_t n = (uint32_t)(BK_F_ROWS_B * it.nb) * 16u;
+                const uint32_t tail = it.nb < BK_GROUP ? 22u * 16u : 0u;
+                mbar_arrive_expect_tx(sBar + 8 * BAR_FFULL, BK_F_CHUNKS * (n + tail));
 #pragma unroll
-                for (int c = 0; c < BK_F_CHUNKS; ++c)
-                    bulk_g2s(sF + c * F_LBO + F_MARGIN * 16, src + (size_t)c * BK_F_ROWS_G * 16, BK_F_ROWS_G * 16,
-                             sBar + 8 * BAR_FFULL);
+                for (int c = 0; c < BK_F_CHUNKS; ++c) {
+                    const uint32_t dst = sF + c * F_LBO + F_MARGIN * 16;
+                    bulk_g2s(dst, src + ((size_t)c * BK_F_ROWS_G + BK_F_ROWS_B * it.lo) * 16, n, sBar + 8 * BAR_FFULL);
+                    if (tail) bulk_g2s(dst + n, src + (size_t)c * BK_F_ROWS_G * 16, tail, sBar + 8 * BAR_FFULL);
+                }
             };
-            auto stream = [&](const uint8_t *src, int n_stages) {
+            auto stream = [&](const uint8_t *src, int n_stages, uint32_t last_bytes) {
                 for (int s = 0; s < n_stages; ++s, ++wit) {
                     const uint32_t st = wit % N_STAGES, ph = (wit / N_STAGES) & 1u;
+                    const uint32_t bytes = s == n_stages - 1 ? last_bytes : (uint32_t)BK_STAGE_BYTES;
                     mbar_wait(sBar + 8 * (BAR_WEMPTY + st), ph ^ 1u, 0x100u + wit);
-                    mbar_arrive_expect_tx(sBar + 8 * (BAR_WFULL + st), BK_STAGE_BYTES);
-                    bulk_g2s(sW + st * BK_STAGE_BYTES, src + (size_t)s * BK_STAGE_BYTES, BK_STAGE_BYTES,
-                             sBar + 8 * (BAR_WFULL + st));
+                    mbar_arrive_expect_tx(sBar + 8 * (BAR_WFULL + st), bytes);
+                    bulk_g2s(sW + st * BK_STAGE_BYTES, src + (size_t)s * BK_STAGE_BYTES, bytes, sBar + 8 * (BAR_WFULL + st));
                 }
             };
+            Item it, nx;
             int n_done = 0;
-            if ((int)blockIdx.x < n_items) load_feats(blockIdx.x);
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
-                const uint8_t *blob = args.blob[args.first_net + item % args.n_nets];
-                stream(blob + BK_W_L0_OFF, BK_L0_STAGES);   // layer 0, tiles 0..3
-                stream(blob + BK_W_L0_OFF, BK_L0_STAGES);   // layer 0, tile 4
-                stream(blob + BK_W_L_OFF(1), BK_L_STAGES);
-                const int next = item + gridDim.x;
-                if (next < n_items) {                        // prefetch the next group's planes
+            if ((int)blockIdx.x < args.n_virtual && decode_item(args, blockIdx.x, it)) load_feats(it);
+            for (int v = blockIdx.x; v < args.n_virtual; v += grid) {
+                if (!decode_item(args, v, it)) continue;
+                const uint8_t *blob = args.blob[it.net];
+                stream(blob + BK_W_L0_OFF, BK_L0_STAGES, BK_STAGE_BYTES);
+                if (it.nb == BK_GROUP) stream(blob + BK_W_L0_OFF, BK_L0_STAGES, BK_STAGE_BYTES);   // layer 0, tile 4
+                stream(blob + BK_W_L_OFF(1), BK_L_STAGES + 1, BK_BIAS_STAGE_BYTES);
+                if (v + grid < args.n_virtual && decode_item(args, v + grid, nx)) {   // prefetch the next planes
                     mbar_wait(sBar + 8 * BAR_FEMPTY, n_done & 1u, 0x200u);
-                    load_feats(next);
+                    load_feats(nx);
                 }
-                for (int l = 2; l <= 6; ++l) stream(blob + BK_W_L_OFF(l), BK_L_STAGES);
+                for (int l = 2; l <= 6; ++l) stream(blob + BK_W_L_OFF(l), BK_L_STAGES + 1, BK_BIAS_STAGE_BYTES);
+                ++n_done;
             }
         }
     } else if (warp == WARP_MMA) {
-        // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            uint32_t wit = 0, pass = 0, n_done = 0;
-            const uint32_t a_lbo = args.swap_lbo_sbo ? 128u : (uint32_t)A_LBO, a_sbo = args.swap_lbo_sbo ? (uint32_t)A_LBO : 128u;
-            const uint32_t f_lbo = args.swap_lbo_sbo ? 128u : (uint32_t)F_LBO, f_sbo = args.swap_lbo_sbo ? (uint32_t)F_LBO : 128u;
-            const uint32_t w_lbo = args.swap_lbo_sbo ? 128u : 2048u, w_sbo = args.swap_lbo_sbo ? 2048u : 128u;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
-                mbar_wait(sBar + 8 * BAR_FFULL, n_done & 1u, 0x300u);
-                for (int ps = 0; ps < 8; ++ps, ++pass) {
-                    // ps 0: layer 0 tiles 0..3; ps 1: layer 0 tile 4; ps 2..7: layers 1..6
-                    if (pass > 0) mbar_wait(sBar + 8 * BAR_ACT, (pass - 1) & 1u, 0x400u + pass);   // operands written, TMEM drained
+        // =========================== MMA issuer (whole warp runs the loop, lane 0 issues) ===========================
+        uint32_t wit = 0, pass = 0, n_done = 0;
+        const uint32_t a_lo0 = desc_lo(sA + A_MARGIN * 16, A_LBO);
+        const uint32_t f_lo0 = desc_lo(sF + F_MARGIN * 16, F_LBO);
+        const uint32_t one_lo = desc_lo(s_base + OFF_ONES, 2048);
+        Item it;
+        for (int v = blockIdx.x; v < args.n_virtual; v += grid) {
+            if (!decode_item(args, v, it)) continue;
+            mbar_wait(sBar + 8 * BAR_FFULL, n_done & 1u, 0x300u);
+            ++n_done;
+            const int np = n_passes(it.nb);
+            for (int ps = 0; ps < np; ++ps, ++pass) {
+                const Pass pi = pass_info(it.nb, ps);
+                if (pass > 0) mbar_wait(sBar + 8 * BAR_ACT, (pass - 1) & 1u, 0x400u + pass);   // operands written, TMEM drained
+                tc_fence_after();
+                if (args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) args.prof[pass * 4 + 0] = clock64();
+                const bool l0 = pi.layer == 0;
+                for (int s = 0; s < pi.n_stages; ++s, ++wit) {
+                    const uint32_t st = wit % N_STAGES, ph = (wit / N_STAGES) & 1u;
+                    mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x500u + wit);
                     tc_fence_after();
-                    const bool l0 = ps < 2;
-                    const int n_stages = l0 ? BK_L0_STAGES : BK_L_STAGES;
-                    const int tile0 = ps == 1 ? 4 : 0, n_tiles = ps == 1 ? 1 : 4;
-                    for (int s = 0; s < n_stages; ++s, ++wit) {
-                        const uint32_t st = wit % N_STAGES, ph = (wit / N_STAGES) & 1u;
-                        mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x500u + wit);
-                        tc_fence_after();
-                        const uint32_t wbase = sW + st * BK_STAGE_BYTES;
-                        for (int t = 0; t < n_tiles; ++t) {
-                            const int row0 = 128 * (tile0 + t);
+                    const uint32_t w_lo = desc_lo(sW + st * BK_STAGE_BYTES, 2048);
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                uint64_t ad;
-                                if (l0) {
-                                    const int tap = 2 * s + (kk >> 1);
-                                    const int ti = tap / 5, tj = tap - 5 * ti;
-                                    const int off = tap < 25 ? (ti - 2) * 11 + (tj - 2) : 0;
-                                    ad = make_desc(sF + (kk & 1) * 2 * F_LBO + (F_MARGIN + row0 + off) * 16, f_lbo, f_sbo);
-                                } else {
-                                    const int tap = s >> 1;
-                                    const int ti = tap / 3, tj = tap - 3 * ti;
-                                    const int off = (ti - 1) * 10 + (tj - 1);
-                                    ad = make_desc(sA + ((s & 1) * 8 + kk * 2) * A_LBO + (A_MARGIN + row0 + off) * 16, a_lbo, a_sbo);
-                                }
-                                const uint64_t bd = make_desc(wbase + kk * 2 * 2048, w_lbo, w_sbo);
-                                umma_f16(tmem + (uint32_t)(t * 128), ad, bd, IDESC, (s | kk) != 0);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        uint32_t a_lo, row_step = 128u;
+                        if (l0) {
+                            const int tap = 2 * s + (kk >> 1);
+                            if (tap < 25) {
+                                const int ti = tap / 5, tj = tap - 5 * ti;
+                                a_lo = f_lo0 + (uint32_t)((kk & 1) * 2 * (F_LBO >> 4)) + (uint32_t)(128 * pi.tile0 + (ti - 2) * 11 + (tj - 2));
+                            } else {
+                                if (kk != 2) continue;                 // K rows 800, 801 hold the bias; the rest is padding
+                                a_lo = one_lo; row_step = 0u;
                             }
+                        } else if (s == BK_L_STAGES) {
+                            if (kk != 0) continue;                     // bias stage: K rows 0, 1
+                            a_lo = one_lo; row_step = 0u;
+                        } else {
+                            const int tap = s >> 1;
+                            const int ti = tap / 3, tj = tap - 3 * ti;
+                            a_lo = a_lo0 + (uint32_t)(((s & 1) * 8 + kk * 2) * (A_LBO >> 4)) + (uint32_t)((ti - 1) * 10 + (tj - 1));
                         }
-                        umma_commit(sBar + 8 * (BAR_WEMPTY + st));   // slab consumed -> producer may refill
+                        const uint32_t b_lo = w_lo + (uint32_t)(kk * 2 * (2048 >> 4));
+                        const uint32_t accum = (s | kk) != 0;
+                        if (elect_one()) {
+                            for (int t = 0; t < pi.n_tiles; ++t)
+                                umma_f16(tmem + (uint32_t)(t * 128), a_lo + (uint32_t)t * row_step, b_lo, accum);
+                        }
+                        __syncwarp();
                     }
-                    if (ps == 1) umma_commit(sBar + 8 * BAR_FEMPTY);   // feature planes no longer needed
-                    umma_commit(sBar + 8 * BAR_ACC);                   // accumulators of this pass complete
+                    if (elect_one()) umma_commit(sBar + 8 * (BAR_WEMPTY + st));   // slab consumed -> producer may refill
+                    __syncwarp();
                 }
+                if (elect_one()) {
+                    if (pi.l0_last) umma_commit(sBar + 8 * BAR_FEMPTY);   // feature planes no longer needed
+                    umma_commit(sBar + 8 * BAR_ACC);                      // accumulators of this pass complete
+                }
+                __syncwarp();
+                if (args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) args.prof[pass * 4 + 1] = clock64();
+                __syncwarp();
             }
         }
     } else {
         // =========================== epilogue warps ===========================
-        const int quad = warp & 3, half = warp >> 2;
+        const int quad = warp & 3, wq = warp >> 2;
         const uint32_t t_lane = tmem + ((uint32_t)(32 * quad) << 16);
         uint32_t pass = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int net = args.first_net + item % args.n_nets, g = item / args.n_nets;
-            const uint8_t *blob = args.blob[net];
-            const float4 *bias4 = reinterpret_cast<const float4 *>(blob + BK_W_BIAS_OFF);
-            for (int ps = 0; ps < 8; ++ps, ++pass) {
-                const int layer = ps < 2 ? 0 : ps - 1;
-                const int tile0 = ps == 1 ? 4 : 0, n_tiles = ps == 1 ? 1 : 4;
+        bool first = true;
+        Item it;
+        for (int v = blockIdx.x; v < args.n_virtual; v += grid) {
+            if (!decode_item(args, v, it)) continue;
+            const uint8_t *blob = args.blob[it.net];
+            const int np = n_passes(it.nb);
+            for (int ps = 0; ps < np; ++ps, ++pass) {
+                const Pass pi = pass_info(it.nb, ps);
                 mbar_wait(sBar + 8 * BAR_ACC, pass & 1u, 0x600u + pass);
                 tc_fence_after();
-                float hs[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // layer 6: this thread's half of the head dot product, per tile
+                const bool prof = args.prof && blockIdx.x == 0 && pass < 64 && threadIdx.x == 0;
+                if (prof) args.prof[pass * 4 + 2] = clock64();
+                const bool dump = args.dump && blockIdx.x == 0 && first && ps == args.dump_pass;
+                if (pi.tile0 == 4) {
+                    // second layer-0 pass: one tile, the 16 warps split it by row quarter x column quarter
+                    const int r0 = 512 + 32 * quad + lane;
+                    const int dest = l0_dest_row(r0, it.nb);
+                    uint32_t v0[32];
+                    tmem_ld32(t_lane + (uint32_t)(wq * 32), v0);
+                    tc_wait_ld();
+                    if (dump) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if (t >= n_tiles) break;
-                    const int r = 128 * (tile0 + t) + 32 * quad + lane;   // GEMM row of this thread
+                        for (int i = 0; i < 32; ++i) args.dump[(size_t)r0 * 128 + wq * 32 + i] = __uint_as_float(v0[i]);
+                    }
+                    if (dest >= 0) store_act32(smem, v0, wq * 4, dest);
+                } else if (wq < pi.n_tiles) {
+                    // one thread per GEMM row: all 128 output channels of row r
+                    const int r = 128 * wq + 32 * quad + lane;
                     int dest, board = 0, sq = 0;
-                    if (layer == 0) dest = l0_dest_row(r);
-                    else dest = act_row_valid(r, board, sq) ? r : -1;
+                    if (pi.layer == 0) dest = l0_dest_row(r, it.nb);
+                    else dest = act_row_valid(r, it.nb, board, sq) ? r : -1;
                     float hsum = 0.0f;
+                    const float4 *hw4 = reinterpret_cast<const float4 *>(blob + BK_W_HEADW_OFF);
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        uint32_t v[32];
-                        tmem_ld32(t_lane + (uint32_t)(t * 128 + half * 64 + j * 32), v);
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32(t_lane + (uint32_t)(wq * 128 + h * 64), v0);
+                        tmem_ld32(t_lane + (uint32_t)(wq * 128 + h * 64 + 32), v1);
                         tc_wait_ld();
-                        const int co0 = half * 64 + j * 32;
-                        if (args.dump && blockIdx.x == 0 && item == 0 && ps == args.dump_pass) {
+                        if (dump) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) args.dump[(size_t)r * 128 + co0 + i] = __uint_as_float(v[i]);
+                            for (int i = 0; i < 32; ++i) {
+                                args.dump[(size_t)r * 128 + h * 64 + i] = __uint_as_float(v0[i]);
+                                args.dump[(size_t)r * 128 + h * 64 + 32 + i] = __uint_as_float(v1[i]);
+                            }
                         }
-                        if (layer < 6) {
+                        if (pi.layer < 6) {
                             if (dest >= 0) {
-#pragma unroll
-                                for (int c8 = 0; c8 < 4; ++c8) {
-                                    const float4 b0 = __ldg(bias4 + layer * 32 + (co0 >> 2) + c8 * 2);
-                                    const float4 b1 = __ldg(bias4 + layer * 32 + (co0 >> 2) + c8 * 2 + 1);
-                                    uint4 o;
-                                    o.x = relu_pack(__uint_as_float(v[c8 * 8 + 0]) + b0.x, __uint_as_float(v[c8 * 8 + 1]) + b0.y);
-                                    o.y = relu_pack(__uint_as_float(v[c8 * 8 + 2]) + b0.z, __uint_as_float(v[c8 * 8 + 3]) + b0.w);
-                                    o.z = relu_pack(__uint_as_float(v[c8 * 8 + 4]) + b1.x, __uint_as_float(v[c8 * 8 + 5]) + b1.y);
-                                    o.w = relu_pack(__uint_as_float(v[c8 * 8 + 6]) + b1.z, __uint_as_float(v[c8 * 8 + 7]) + b1.w);
-                                    const int chunk = (co0 >> 3) + c8;
-                                    *reinterpret_cast<uint4 *>(smem + OFF_A + chunk * A_LBO + (A_MARGIN + dest) * 16) = o;
-                                }
+                                store_act32(smem, v0, h * 8, dest);
+                                store_act32(smem, v1, h * 8 + 4, dest);
                             }
                         } else {
-                            const float4 *hw4 = reinterpret_cast<const float4 *>(blob + BK_W_HEADW_OFF);
-#pragma unroll
-                            for (int c4 = 0; c4 < 8; ++c4) {
-                                const float4 b = __ldg(bias4 + layer * 32 + (co0 >> 2) + c4);
-                                const float4 w = __ldg(hw4 + (co0 >> 2) + c4);
-                                hsum = fmaf(fmaxf(__uint_as_float(v[c4 * 4 + 0]) + b.x, 0.0f), w.x, hsum);
-                                hsum = fmaf(fmaxf(__uint_as_float(v[c4 * 4 + 1]) + b.y, 0.0f), w.y, hsum);
-                                hsum = fmaf(fmaxf(__uint_as_float(v[c4 * 4 + 2]) + b.z, 0.0f), w.z, hsum);
-                                hsum = fmaf(fmaxf(__uint_as_float(v[c4 * 4 + 3]) + b.w, 0.0f), w.w, hsum);
-                            }
+                            hsum = head_dot32(v0, hw4 + h * 16, hsum);
+                            hsum = head_dot32(v1, hw4 + h * 16 + 8, hsum);
                         }
                     }
-                    hs[t] = hsum;
-                    if (layer == 6 && half == 1) part[r] = hsum;
-                }
-                if (layer == 6) {
-                    // combine the two column halves: 1x1 conv 128->1 plus the per-square bias
-                    named_bar_sync(1, N_EPI_WARPS * 32);
-                    if (half == 0) {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const int r = 128 * t + 32 * quad + lane;
-                            int board, sq;
-                            if (act_row_valid(r, board, sq)) {
-                                const float hb = __ldg(reinterpret_cast<const float *>(blob + BK_W_HEADB_OFF) + sq);
-                                logit[board * 81 + sq] = hs[t] + part[r] + hb;
-                            }
-                        }
-                    }
-                    named_bar_sync(1, N_EPI_WARPS * 32);
+                    if (pi.layer == 6 && dest >= 0)   // 1x1 conv 128->1 plus the per-square bias
+                        logit[board * 81 + sq] = hsum + __ldg(reinterpret_cast<const float *>(blob + BK_W_HEADB_OFF) + sq);
                 }
                 // this pass's TMEM reads are complete and the operand writes are visible to the tensor core
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(sBar + 8 * BAR_ACT);
-                if (layer == 6) {
-                    // logit[] holds 5 boards x 81 head outputs
-                    if (warp < BK_GROUP) {
-                        const int b = g * BK_GROUP + warp;
-                        if (b < args.B)
-                            finish_board(logit + warp * 81, net, blob, args.logits ? args.logits + (size_t)b * 81 : nullptr,
-                                         args.probs ? args.probs + (size_t)b * 81 : nullptr,
-                                         args.value ? args.value + b : nullptr, lane);
+                if (prof) args.prof[pass * 4 + 3] = clock64();
+                if (pi.layer == 6) {
+                    // logit[] holds nb boards x 81 head outputs; it is next written seven passes from now, and
+                    // every pass in between needs all 16 warps to have arrived, so no trailing barrier
+                    named_bar_sync(1, N_EPI_WARPS * 32);
+                    if (warp < it.nb) {
+                        const int b = it.g * BK_GROUP + it.lo + warp;
+                        finish_board(logit + warp * 81, it.net, blob, args.logits ? args.logits + (size_t)b * 81 : nullptr,
+                                     args.probs ? args.probs + (size_t)b * 81 : nullptr,
+                                     args.value ? args.value + b : nullptr, lane);
                     }
-                    named_bar_sync(1, N_EPI_WARPS * 32);   // logit[] is reused by the next item
                 }
             }
+            first = false;
         }
     }
 
@@ -597,6 +697,12 @@ static inline uint16_t f2h(float f)
     memcpy(&u, &h, 2);
     return u;
 }
+static inline float h2f(uint16_t u)
+{
+    __half h;
+    memcpy(&h, &u, 2);
+    return __half2float(h);
+}
 
 // Packs BatchNorm-folded fp32 parameters into the blob described in bk_layout.h (host memory -> host memory).
 //   w0 [128][27][5][5], w16 [6][128][128][3][3], bias [7][128], head_w [128], head_b [81],
@@ -615,8 +721,24 @@ extern "C" int bk_weights_pack(const float *w0, const float *w16, const float *b
                 h0[(size_t)(k >> 6) * (BK_STAGE_BYTES / 2) + ((k & 63) >> 3) * 1024 + co * 8 + (k & 7)] =
                     f2h(w0[(co * 27 + ci) * 25 + tap]);
             }
+    // folded bias as two extra K rows (fp16 hi + lo) that meet the all-ones operand: layer 0 in the spare
+    // tap slot (K = 800, 801), layers 1..6 in a short 19th stage (K rows 0, 1 of k-chunk 0)
+    for (int co = 0; co < 128; ++co) {
+        const float b = bias[co];
+        const uint16_t hi = f2h(b), lo = f2h(b - h2f(hi));
+        const int k = 800;
+        h0[(size_t)(k >> 6) * (BK_STAGE_BYTES / 2) + ((k & 63) >> 3) * 1024 + co * 8 + 0] = hi;
+        h0[(size_t)(k >> 6) * (BK_STAGE_BYTES / 2) + ((k & 63) >> 3) * 1024 + co * 8 + 1] = lo;
+    }
     for (int l = 1; l <= 6; ++l) {
         uint16_t *hl = reinterpret_cast<uint16_t *>(blob + BK_W_L_OFF(l));
+        uint16_t *hb = hl + (size_t)BK_L_STAGES * (BK_STAGE_BYTES / 2);
+        for (int co = 0; co < 128; ++co) {
+            const float b = bias[l * 128 + co];
+            const uint16_t hi = f2h(b), lo = f2h(b - h2f(hi));
+            hb[co * 8 + 0] = hi;
+            hb[co * 8 + 1] = lo;
+        }
         const float *wl = w16 + (size_t)(l - 1) * 128 * 128 * 9;
         for (int co = 0; co < 128; ++co)
             for (int ci = 0; ci < 128; ++ci)
@@ -651,22 +773,27 @@ extern "C" int bk_debug_words(unsigned int *out8)
 }
 
 static int forward_impl(const void *feats_conv, const void *blob_policy, const void *blob_value, float *logits,
-                        float *probs, float *value, int B, int flags, cudaStream_t stream, float *dump, int dump_pass);
+                        float *probs, float *value, int B, int flags, cudaStream_t stream, float *dump, int dump_pass,
+                        long long *prof);
 
+// diagnostics: dump = raw accumulators [640][128] of pass `dump_pass` of CTA 0's first item; prof = clock64 stamps of
+// CTA 0, four per pass {MMA issue start, MMA issue end, accumulators ready, epilogue done}, room for 64 passes
 extern "C" int bk_forward_debug(const void *feats_conv, const void *blob_policy, const void *blob_value, float *logits,
-                                float *probs, float *value, int B, int flags, cudaStream_t stream, float *dump, int dump_pass)
+                                float *probs, float *value, int B, int flags, cudaStream_t stream, float *dump, int dump_pass,
+                                long long *prof)
 {
-    return forward_impl(feats_conv, blob_policy, blob_value, logits, probs, value, B, flags, stream, dump, dump_pass);
+    return forward_impl(feats_conv, blob_policy, blob_value, logits, probs, value, B, flags, stream, dump, dump_pass, prof);
 }
 
 extern "C" int bk_forward(const void *feats_conv, const void *blob_policy, const void *blob_value, float *logits,
                           float *probs, float *value, int B, int flags, cudaStream_t stream)
 {
-    return forward_impl(feats_conv, blob_policy, blob_value, logits, probs, value, B, flags, stream, nullptr, -1);
+    return forward_impl(feats_conv, blob_policy, blob_value, logits, probs, value, B, flags, stream, nullptr, -1, nullptr);
 }
 
 static int forward_impl(const void *feats_conv, const void *blob_policy, const void *blob_value, float *logits,
-                        float *probs, float *value, int B, int flags, cudaStream_t stream, float *dump, int dump_pass)
+                        float *probs, float *value, int B, int flags, cudaStream_t stream, float *dump, int dump_pass,
+                        long long *prof)
 {
     if (B <= 0) return 0;
     const bool do_p = flags & BK_FWD_POLICY, do_v = flags & BK_FWD_VALUE;
@@ -680,8 +807,9 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
     a.B = B; a.G = (B + BK_GROUP - 1) / BK_GROUP;
     a.n_nets = (do_p ? 1 : 0) + (do_v ? 1 : 0);
     a.first_net = do_p ? 0 : 1;
-    a.swap_lbo_sbo = (flags & 0x100) ? 1 : 0;
-    a.dump = dump; a.dump_pass = dump_pass;
+    a.n_items = a.G * a.n_nets;
+    a.n_whole = a.n_items; a.split = 1; a.n_virtual = a.n_items;
+    a.dump = dump; a.dump_pass = dump_pass; a.prof = prof;
     if (!g_dbg_host) {
         if (cudaHostAlloc((void **)&g_dbg_host, 64, cudaHostAllocMapped) != cudaSuccess) g_dbg_host = nullptr;
         else memset(g_dbg_host, 0, 64);
@@ -706,8 +834,16 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
             e = cudaFuncSetAttribute(bk_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
             if (e != cudaSuccess) { n_sm = 0; return -3; }
         }
-        const int n_items = a.G * a.n_nets;
-        const int grid = n_items < n_sm ? n_items : n_sm;
+        // whole rounds of the grid take one (group, net) pair per CTA; the pairs of the last, partial round are
+        // split into board ranges so that it spreads over the idle SMs (fewer M tiles per CTA)
+        a.n_whole = (a.n_items / n_sm) * n_sm;
+        const int rest = a.n_items - a.n_whole;
+        if (rest > 0 && !(flags & BK_FWD_NOSPLIT)) {
+            a.split = n_sm / rest < BK_GROUP ? n_sm / rest : BK_GROUP;
+            if (a.split < 1) a.split = 1;
+        }
+        a.n_virtual = a.n_whole + rest * a.split;
+        const int grid = a.n_virtual < n_sm ? a.n_virtual : n_sm;
         bk_forward_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, stream>>>(a);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -3;

@@ -8,7 +8,7 @@
  *     every board are zero, so a 5x5 tap (i,j) is the row shift (i-2)*11 + (j-2).
  *
  * Activation operand (on chip only), fp16, 128 channels:
- *     [16 channel chunks][536 rows][8 channels], row = 12 + 100*board + 10 + 10*x + y :
+ *     [16 channel chunks][524 rows][8 channels], row = 12 + 100*board + 10 + 10*x + y :
  *     stride-10 raster with one zero column, one zero row above every board; a 3x3 tap (i,j) is the
  *     row shift (i-1)*10 + (j-1).  GEMM rows 0..511 = 4 M-tiles of 128; 405 of them are real squares.
  *
@@ -16,10 +16,13 @@
  * (stride-byte-offset 128) -- so a row-shifted window is just a different start address.
  *
  * Weight blob (per net), bytes:
- *     layer 0 : 13 stages x 16 KiB      K = tap*32 + ci  (25 taps, ci padded 27->32, K padded 800->832)
+ *     layer 0 : 13 stages x 16 KiB      K = tap*32 + ci  (25 taps, ci padded 27->32, K padded 800->832);
+ *                                       K = 800, 801 hold the folded bias as fp16 hi + lo
  *     layer l : 18 stages x 16 KiB      K = tap*128 + ci (l = 1..6)
+ *               + one 4 KiB bias stage  [2 k-chunks][128 co][8 k]: k = 0, 1 hold the folded bias as fp16 hi + lo
  *               one stage = 64 K-values for all 128 output channels: [8 k-chunks][128 co][8 k] fp16
- *     then fp32: bias[7][128] (BatchNorm folded), head_w[128], head_b[96] (81 used),
+ *               (the bias rows are multiplied by an all-ones operand, so the bias is added by the tensor core)
+ *     then fp32: bias[7][128] (BatchNorm folded; read by the validation kernel), head_w[128], head_b[96] (81 used),
  *     value tail: {bn_scale, bn_shift, lin2_b, 0}, W1T[81][64] (BN1d folded, transposed), b1[64], w2[64]
  */
 #ifndef BK_LAYOUT_H
@@ -35,8 +38,10 @@
 #define BK_L0_STAGES 13
 #define BK_L_STAGES 18
 #define BK_W_L0_OFF 0
-#define BK_W_L_OFF(l) (BK_L0_STAGES * BK_STAGE_BYTES + ((l) - 1) * BK_L_STAGES * BK_STAGE_BYTES)
-#define BK_W_BIAS_OFF (BK_L0_STAGES * BK_STAGE_BYTES + 6 * BK_L_STAGES * BK_STAGE_BYTES) /* 1,982,464 */
+#define BK_BIAS_STAGE_BYTES 4096
+#define BK_L_BYTES (BK_L_STAGES * BK_STAGE_BYTES + BK_BIAS_STAGE_BYTES)
+#define BK_W_L_OFF(l) (BK_L0_STAGES * BK_STAGE_BYTES + ((l) - 1) * BK_L_BYTES)
+#define BK_W_BIAS_OFF (BK_L0_STAGES * BK_STAGE_BYTES + 6 * BK_L_BYTES) /* 2,007,040 */
 #define BK_W_HEADW_OFF (BK_W_BIAS_OFF + 7 * 128 * 4)
 #define BK_W_HEADB_OFF (BK_W_HEADW_OFF + 128 * 4)
 #define BK_W_VT_OFF (BK_W_HEADB_OFF + 96 * 4)
@@ -49,5 +54,6 @@
 #define BK_FWD_POLICY 1      /* run the policy trunk: logits + probs */
 #define BK_FWD_VALUE 2       /* run the value trunk: value */
 #define BK_FWD_SIMT 4        /* validation path: plain CUDA-core kernel instead of tcgen05 */
+#define BK_FWD_NOSPLIT 8     /* measurement only: do not split the items of the last partial round */
 
 #endif

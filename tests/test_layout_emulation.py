@@ -10,7 +10,8 @@ import torch
 from oracle import nets as onets
 
 GROUP, F_ROWS_B, F_ROWS_G = 5, 121, 605
-A_MARGIN, A_ROWS, F_MARGIN, F_ROWS = 12, 536, 24, 653
+A_MARGIN, A_ROWS, F_MARGIN, F_ROWS = 12, 536, 24, 653   # emulation buffers (the kernel overlaps the margins)
+L_BYTES = 18 * 16384 + 4096          # 18 K-slabs + the short bias stage
 STAGE_H = 8192                      # halfs per 16 KiB stage
 L0_STAGES, L_STAGES = 13, 18
 
@@ -46,6 +47,16 @@ def _stage(blob, byte_off, s):
     return h.reshape(8, 128, 8).transpose(0, 2, 1).reshape(64, 128)      # [kchunk][co][k8] -> [k][co]
 
 
+def _bias_stage(blob, byte_off):
+    """the 4 KiB bias stage behind a layer's 18 slabs -> float32 [16 k][128 co]"""
+    h = blob[byte_off + 18 * 16384: byte_off + 18 * 16384 + 4096].view(np.float16).astype(np.float32)
+    return h.reshape(2, 128, 8).transpose(0, 2, 1).reshape(16, 128)
+
+
+ONES = np.zeros(16, np.float32)
+ONES[:2] = 1.0                       # the all-ones operand: k = 0, 1 of every row
+
+
 def _emulate(planes_u8, blob, bias, hw, hb):
     """planes uint8 [5,27,81] (one group) -> logits [5,81] following bk_forward.cu step by step"""
     F = np.zeros((4, F_ROWS, 8), np.float32)
@@ -61,7 +72,11 @@ def _emulate(planes_u8, blob, bias, hw, hb):
         W = _stage(blob, 0, s)
         for kk in range(4):
             tap = 2 * s + (kk >> 1)
-            off = (tap // 5 - 2) * 11 + (tap % 5 - 2) if tap < 25 else 0
+            if tap >= 25:
+                if kk == 2:                                      # K rows 800, 801: bias hi + lo times the ones operand
+                    D += np.tile(ONES, (640, 1)) @ W[kk * 16:(kk + 1) * 16]
+                continue
+            off = (tap // 5 - 2) * 11 + (tap % 5 - 2)
             c0 = (kk & 1) * 2
             rows = F_MARGIN + np.arange(640) + off
             ok = rows < F_ROWS                                   # rows past the buffer feed invalid outputs only
@@ -76,11 +91,11 @@ def _emulate(planes_u8, blob, bias, hw, hb):
         if y >= 9:
             continue
         dest = 100 * board + 10 + 10 * x + y
-        o = np.maximum(D[r0] + bias[0], 0).astype(np.float16).astype(np.float32)
+        o = np.maximum(D[r0], 0).astype(np.float16).astype(np.float32)
         A[:, A_MARGIN + dest, :] = o.reshape(16, 8)
     # ---- layers 1..6 ----
     for layer in range(1, 7):
-        off_b = L0_STAGES * 16384 + (layer - 1) * L_STAGES * 16384
+        off_b = L0_STAGES * 16384 + (layer - 1) * L_BYTES
         D = np.zeros((512, 128), np.float32)
         for s in range(L_STAGES):
             W = _stage(blob, off_b, s)
@@ -91,12 +106,13 @@ def _emulate(planes_u8, blob, bias, hw, hb):
                 c0 = (s & 1) * 8 + kk * 2
                 a = np.concatenate([A[c0, rows], A[c0 + 1, rows]], axis=1)
                 D += a @ W[kk * 16:(kk + 1) * 16]
+        D += np.tile(ONES, (512, 1)) @ _bias_stage(blob, off_b)
         logits = np.zeros((GROUP, 81), np.float32)
         for r in range(512):
             board, rem = divmod(r, 100)
             if board >= GROUP or rem < 10 or (rem - 10) % 10 >= 9:
                 continue
-            act = np.maximum(D[r] + bias[layer], 0)
+            act = np.maximum(D[r], 0)
             if layer < 6:
                 A[:, A_MARGIN + r, :] = act.astype(np.float16).astype(np.float32).reshape(16, 8)
             else:
@@ -128,5 +144,16 @@ def test_partial_group_is_isolated(positions, nets_golden, sd17):
 def test_blob_size_and_value_tail(sd_value):
     from bokego_b200 import _lib
     L = _lib.lib()
-    assert L.bk_weights_blob_bytes() == 2008320 and L.bk_feats_conv_bytes(4096) == 820 * 38720
+    assert L.bk_weights_blob_bytes() == 2032896 and L.bk_feats_conv_bytes(4096) == 820 * 38720
     assert L.bk_feats_conv_bytes(1) == 38720 and L.bk_feats_conv_bytes(0) == 0
+
+
+def test_bias_rows_reproduce_fp32_bias(sd17):
+    """the fp16 hi + lo split of the folded bias (added by the tensor core) carries ~22 bits"""
+    blob, bias, _, _ = _pack(sd17)
+    got0 = _stage(blob, 0, 12)[32:34].sum(0)                     # layer 0: K = 800, 801
+    assert np.abs(got0 - bias[0]).max() <= 2e-6 * max(1.0, np.abs(bias[0]).max())
+    for layer in range(1, 7):
+        b = _bias_stage(blob, L0_STAGES * 16384 + (layer - 1) * L_BYTES)
+        assert np.abs(b[:2].sum(0) - bias[layer]).max() <= 2e-6 * max(1.0, np.abs(bias[layer]).max())
+        assert not b[2:].any()

@@ -43,9 +43,9 @@ def main():
     L = _lib.lib()
     dump = torch.full((640, 128), float("nan"), dtype=torch.float32, device=dev)
     logits = torch.zeros(B, 81, device=dev); probs = torch.zeros(B, 81, device=dev)
-    flags = 1 | (0x100 if a.swap else 0)
+    flags = 1
     rc = L.bk_forward_debug(_lib.ptr(out["conv"]), _lib.ptr(pol.blob), None, _lib.ptr(logits), _lib.ptr(probs), None, B, flags,
-                            _lib.stream_ptr(dev), _lib.ptr(dump), a.ps)
+                            _lib.stream_ptr(dev), _lib.ptr(dump), a.ps, None)
     print("launch rc", rc)
     try:
         torch.cuda.synchronize()
