@@ -8,8 +8,8 @@
 //     layers; each layer is an implicit GEMM  D[rows, 128 co] += A[rows + tap shift, ci] * W[tap]  issued as
 //     tcgen05.mma (cta_group::1, kind::f16, M=128, N=128, K=16) with fp32 accumulators for up to four 128-row
 //     tiles resident in TMEM (4 x 128 = 512 columns);
-//   * weights stream L2 -> shared memory as 16 KiB K-slabs (cp.async.bulk + mbarrier, 3 stages); every slab
-//     is used by all tiles of the pass before its slot is recycled;
+//   * weights stream L2 -> shared memory in 8 KiB stages of two K steps (cp.async.bulk + mbarrier, a 48 KiB
+//     ring); every stage is used by all tiles of the pass before its slot is recycled;
 //   * the folded bias enters through the tensor core as well: two extra K rows (bias split into fp16 hi + lo)
 //     multiplied by a constant all-ones operand, so the accumulators leave TMEM ready for ReLU;
 //   * 16 epilogue warps (one thread per GEMM row: TMEM lane quarter = warp % 4, tile = warp / 4) pull the
@@ -43,20 +43,29 @@ constexpr int F_MARGIN = 24;                       // |5x5 tap shift| <= 24
 constexpr int F_ROWS = F_MARGIN + BK_F_ROWS_G;     // 629
 constexpr int F_LBO = F_ROWS * 16;
 constexpr int F_BYTES = (BK_F_CHUNKS * F_LBO + F_MARGIN * 16 + 127) / 128 * 128;   // 40,704 (+ zero rows behind chunk 3)
-constexpr int N_STAGES = 3;
+#ifndef BK_KSTEPS_PER_STAGE
+#define BK_KSTEPS_PER_STAGE 2
+#endif
+constexpr int KSTEP_BYTES = 4096;                  // B operand of one K=16 MMA: [2 k-chunks][128 co][8 k] fp16
+constexpr int KPS = BK_KSTEPS_PER_STAGE;           // K steps per pipeline stage
+constexpr int STAGE_BYTES = KPS * KSTEP_BYTES;
+constexpr int N_STAGES = 49152 / STAGE_BYTES;      // 48 KiB weight ring
+constexpr int L0_KSTEPS = 51;                      // 25 taps x 2 halves + the bias step
+constexpr int L_KSTEPS = 73;                       // 9 taps x 8 + the bias step
 constexpr int ONES_BYTES = 4096;                   // [2 k-chunks][128 rows][8]: 1.0 in k = 0, 1
 constexpr int OFF_A = 0;
 constexpr int OFF_F = OFF_A + A_BYTES;             // F's front margin doubles as the rows behind A's last chunk
 constexpr int OFF_W = OFF_F + F_BYTES;
-constexpr int OFF_ONES = OFF_W + N_STAGES * BK_STAGE_BYTES;
-constexpr int OFF_BAR = OFF_ONES + ONES_BYTES;     // barriers (16 x 8 B)
-constexpr int OFF_TMEM = OFF_BAR + 128;
+constexpr int OFF_ONES = OFF_W + N_STAGES * STAGE_BYTES;
+constexpr int OFF_BAR = OFF_ONES + ONES_BYTES;     // barriers (2 * N_STAGES + 4, 8 B each)
+constexpr int OFF_TMEM = OFF_BAR + 256;
 constexpr int OFF_LOGIT = OFF_TMEM + 16;           // float[5][81]: head output per square
 constexpr int SMEM_BYTES = OFF_LOGIT + 1664;       // 229,904
 static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KiB");
 static_assert(OFF_W % 128 == 0 && OFF_ONES % 128 == 0, "operand alignment");
 
-enum { BAR_WFULL = 0, BAR_WEMPTY = 3, BAR_ACC = 6, BAR_ACT = 7, BAR_FFULL = 8, BAR_FEMPTY = 9 };
+enum { BAR_WFULL = 0, BAR_WEMPTY = N_STAGES, BAR_ACC = 2 * N_STAGES, BAR_ACT, BAR_FFULL, BAR_FEMPTY, N_BARS };
+static_assert(N_BARS * 8 <= 256, "barrier area");
 
 constexpr int N_EPI_WARPS = 16;
 constexpr int WARP_PRODUCER = 16;
@@ -135,14 +144,14 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
 {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accum)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accum, uint32_t idesc = IDESC)
 {
     const uint64_t adesc = ((uint64_t)DESC_HI << 32) | a_lo, bdesc = ((uint64_t)DESC_HI << 32) | b_lo;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accum)
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar)
@@ -201,6 +210,7 @@ struct FwdArgs {
     int n_virtual;             // n_whole + (n_items - n_whole) * split
     float *dump;               // diagnostic: raw accumulators [640][128] of pass `dump_pass` (first item of CTA 0)
     int dump_pass;
+    int diag_nostream;         // diagnostic: the producer signals stages without copying weights
     long long *prof;           // diagnostic: clock64 stamps of CTA 0, 4 per pass
     unsigned int *dbg;         // host-mapped words written before a bounded wait traps
 };
@@ -227,7 +237,7 @@ __device__ __forceinline__ bool decode_item(const FwdArgs &a, int v, Item &it)
 }
 
 // A full item takes 8 passes (layer 0 needs five 128-row tiles but TMEM holds four), a smaller one 7.
-struct Pass { int layer, tile0, n_tiles, n_stages; bool l0_last; };
+struct Pass { int layer, tile0, n_tiles, n_ksteps; bool l0_last; };
 __device__ __forceinline__ int n_passes(int nb) { return nb == BK_GROUP ? 8 : 7; }
 __device__ __forceinline__ Pass pass_info(int nb, int ps)
 {
@@ -244,7 +254,7 @@ __device__ __forceinline__ Pass pass_info(int nb, int ps)
         p.n_tiles = ps == 0 ? (121 * nb - 2 + 127) >> 7 : nt;   // tiles of the stride-11 raster (layer 0)
         p.l0_last = ps == 0;
     }
-    p.n_stages = p.layer == 0 ? BK_L0_STAGES : BK_L_STAGES + 1;
+    p.n_ksteps = p.layer == 0 ? L0_KSTEPS : L_KSTEPS;
     return p;
 }
 
@@ -406,13 +416,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdAr
                     if (tail) bulk_g2s(dst + n, src + (size_t)c * BK_F_ROWS_G * 16, tail, sBar + 8 * BAR_FFULL);
                 }
             };
-            auto stream = [&](const uint8_t *src, int n_stages, uint32_t last_bytes) {
-                for (int s = 0; s < n_stages; ++s, ++wit) {
+            auto stream = [&](const uint8_t *src, int n_ksteps) {   // one layer's K steps, KPS per stage
+                for (int q = 0; q < n_ksteps; q += KPS, ++wit) {
                     const uint32_t st = wit % N_STAGES, ph = (wit / N_STAGES) & 1u;
-                    const uint32_t bytes = s == n_stages - 1 ? last_bytes : (uint32_t)BK_STAGE_BYTES;
+                    const uint32_t bytes = (uint32_t)min(KPS, n_ksteps - q) * KSTEP_BYTES;
                     mbar_wait(sBar + 8 * (BAR_WEMPTY + st), ph ^ 1u, 0x100u + wit);
+                    if ((args.diag_nostream & 1) && wit >= N_STAGES) {       // measurement only: skip the copy (wrong results)
+                        mbar_arrive(sBar + 8 * (BAR_WFULL + st));
+                        continue;
+                    }
                     mbar_arrive_expect_tx(sBar + 8 * (BAR_WFULL + st), bytes);
-                    bulk_g2s(sW + st * BK_STAGE_BYTES, src + (size_t)s * BK_STAGE_BYTES, bytes, sBar + 8 * (BAR_WFULL + st));
+                    bulk_g2s(sW + st * STAGE_BYTES, src + (size_t)q * KSTEP_BYTES, bytes, sBar + 8 * (BAR_WFULL + st));
                 }
             };
             Item it, nx;
@@ -421,23 +435,59 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdAr
             for (int v = blockIdx.x; v < args.n_virtual; v += grid) {
                 if (!decode_item(args, v, it)) continue;
                 const uint8_t *blob = args.blob[it.net];
-                stream(blob + BK_W_L0_OFF, BK_L0_STAGES, BK_STAGE_BYTES);
-                if (it.nb == BK_GROUP) stream(blob + BK_W_L0_OFF, BK_L0_STAGES, BK_STAGE_BYTES);   // layer 0, tile 4
-                stream(blob + BK_W_L_OFF(1), BK_L_STAGES + 1, BK_BIAS_STAGE_BYTES);
+                stream(blob + BK_W_L0_OFF, L0_KSTEPS);
+                if (it.nb == BK_GROUP) stream(blob + BK_W_L0_OFF, L0_KSTEPS);   // layer 0, tile 4
+                stream(blob + BK_W_L_OFF(1), L_KSTEPS);
                 if (v + grid < args.n_virtual && decode_item(args, v + grid, nx)) {   // prefetch the next planes
                     mbar_wait(sBar + 8 * BAR_FEMPTY, n_done & 1u, 0x200u);
                     load_feats(nx);
                 }
-                for (int l = 2; l <= 6; ++l) stream(blob + BK_W_L_OFF(l), BK_L_STAGES + 1, BK_BIAS_STAGE_BYTES);
+                for (int l = 2; l <= 6; ++l) stream(blob + BK_W_L_OFF(l), L_KSTEPS);
                 ++n_done;
             }
         }
     } else if (warp == WARP_MMA) {
-        // =========================== MMA issuer (whole warp runs the loop, lane 0 issues) ===========================
-        uint32_t wit = 0, pass = 0, n_done = 0;
+        // =========================== MMA issuer (whole warp runs the loop, one elected lane issues) ===========
+        // The tensor pipe queues only a few MMAs, so the scalar work between two stages has to stay well below
+        // the ~190 cycles the queue covers: descriptors are formed with adds of compile-time offsets, and one
+        // elected lane issues all MMAs of a stage plus the commit that hands the stage back to the producer.
+        static_assert(KPS == 2, "the issue loop is written for stages of two K steps");
+        uint32_t st = 0, ph = 0, pass = 0, n_done = 0;   // weight ring slot / phase
         const uint32_t a_lo0 = desc_lo(sA + A_MARGIN * 16, A_LBO);
         const uint32_t f_lo0 = desc_lo(sF + F_MARGIN * 16, F_LBO);
         const uint32_t one_lo = desc_lo(s_base + OFF_ONES, 2048);
+        const uint32_t w_lo0 = desc_lo(sW, 2048);
+        int n_tiles = 0;
+        // one stage: K steps with A windows a0 (and a1), B = the two 4 KiB halves of ring slot `st`
+        auto stage = [&](uint32_t a0, uint32_t a1, bool two, uint32_t row_step, uint32_t accum0) {
+            mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x500u + st);
+            tc_fence_after();
+            const uint32_t w_lo = w_lo0 + st * (STAGE_BYTES >> 4);
+            if (args.diag_nostream & 4) {   // measurement only: the same K steps as two N=256 MMAs (garbage results)
+                if (elect_one()) {
+                    const uint32_t id256 = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+                    for (int t = 0; t < 2; ++t) umma_f16(tmem + (uint32_t)(t * 256), a0 + (uint32_t)t * row_step, w_lo, accum0, id256);
+                    if (two) for (int t = 0; t < 2; ++t) umma_f16(tmem + (uint32_t)(t * 256), a1 + (uint32_t)t * row_step, w_lo + 128u, 1u, id256);
+                    umma_commit(sBar + 8 * (BAR_WEMPTY + st));
+                }
+                __syncwarp();
+                if (++st == N_STAGES) { st = 0; ph ^= 1u; }
+                return;
+            }
+            if (elect_one()) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (t < n_tiles) umma_f16(tmem + (uint32_t)(t * 128), a0 + (uint32_t)t * row_step, w_lo, accum0);
+                if (two) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (t < n_tiles) umma_f16(tmem + (uint32_t)(t * 128), a1 + (uint32_t)t * row_step, w_lo + (KSTEP_BYTES >> 4), 1u);
+                }
+                umma_commit(sBar + 8 * (BAR_WEMPTY + st));   // stage consumed -> producer may refill
+            }
+            __syncwarp();
+            if (++st == N_STAGES) { st = 0; ph ^= 1u; }
+        };
         Item it;
         for (int v = blockIdx.x; v < args.n_virtual; v += grid) {
             if (!decode_item(args, v, it)) continue;
@@ -446,46 +496,29 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdAr
             const int np = n_passes(it.nb);
             for (int ps = 0; ps < np; ++ps, ++pass) {
                 const Pass pi = pass_info(it.nb, ps);
+                n_tiles = pi.n_tiles;
                 if (pass > 0) mbar_wait(sBar + 8 * BAR_ACT, (pass - 1) & 1u, 0x400u + pass);   // operands written, TMEM drained
                 tc_fence_after();
                 if (args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) args.prof[pass * 4 + 0] = clock64();
-                const bool l0 = pi.layer == 0;
-                for (int s = 0; s < pi.n_stages; ++s, ++wit) {
-                    const uint32_t st = wit % N_STAGES, ph = (wit / N_STAGES) & 1u;
-                    mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x500u + wit);
-                    tc_fence_after();
-                    const uint32_t w_lo = desc_lo(sW + st * BK_STAGE_BYTES, 2048);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        uint32_t a_lo, row_step = 128u;
-                        if (l0) {
-                            const int tap = 2 * s + (kk >> 1);
-                            if (tap < 25) {
-                                const int ti = tap / 5, tj = tap - 5 * ti;
-                                a_lo = f_lo0 + (uint32_t)((kk & 1) * 2 * (F_LBO >> 4)) + (uint32_t)(128 * pi.tile0 + (ti - 2) * 11 + (tj - 2));
-                            } else {
-                                if (kk != 2) continue;                 // K rows 800, 801 hold the bias; the rest is padding
-                                a_lo = one_lo; row_step = 0u;
-                            }
-                        } else if (s == BK_L_STAGES) {
-                            if (kk != 0) continue;                     // bias stage: K rows 0, 1
-                            a_lo = one_lo; row_step = 0u;
-                        } else {
-                            const int tap = s >> 1;
-                            const int ti = tap / 3, tj = tap - 3 * ti;
-                            a_lo = a_lo0 + (uint32_t)(((s & 1) * 8 + kk * 2) * (A_LBO >> 4)) + (uint32_t)((ti - 1) * 10 + (tj - 1));
-                        }
-                        const uint32_t b_lo = w_lo + (uint32_t)(kk * 2 * (2048 >> 4));
-                        const uint32_t accum = (s | kk) != 0;
-                        if (elect_one()) {
-                            for (int t = 0; t < pi.n_tiles; ++t)
-                                umma_f16(tmem + (uint32_t)(t * 128), a_lo + (uint32_t)t * row_step, b_lo, accum);
-                        }
-                        __syncwarp();
+                if (pi.layer == 0) {
+                    const uint32_t fb = f_lo0 + (uint32_t)(128 * pi.tile0);
+                    for (int tap = 0; tap < 25; ++tap) {               // K steps 2*tap, 2*tap+1: channel chunks 0,1 / 2,3
+                        const int ti = tap / 5, tj = tap - 5 * ti;
+                        const uint32_t a = fb + (uint32_t)((ti - 2) * 11 + (tj - 2));
+                        stage(a, a + 2u * (F_LBO >> 4), true, 128u, tap != 0);
                     }
-                    if (elect_one()) umma_commit(sBar + 8 * (BAR_WEMPTY + st));   // slab consumed -> producer may refill
-                    __syncwarp();
+                } else {
+                    for (int tap = 0; tap < 9; ++tap) {                // K steps 8*tap .. 8*tap+7: channel chunks 2j, 2j+1
+                        const int ti = tap / 3, tj = tap - 3 * ti;
+                        uint32_t a = a_lo0 + (uint32_t)((ti - 1) * 10 + (tj - 1));
+                        if (args.diag_nostream & 2) a = a_lo0 - 4u;                     // measurement only: 128 B aligned windows
+#pragma unroll
+                        for (int part = 0; part < 4; ++part)
+                            stage(a + (uint32_t)(4 * part) * (A_LBO >> 4), a + (uint32_t)(4 * part + 2) * (A_LBO >> 4), true, 128u,
+                                  (tap | part) != 0);
+                    }
                 }
+                stage(one_lo, 0u, false, 0u, 1u);                      // bias rows x the all-ones operand
                 if (elect_one()) {
                     if (pi.l0_last) umma_commit(sBar + 8 * BAR_FEMPTY);   // feature planes no longer needed
                     umma_commit(sBar + 8 * BAR_ACC);                      // accumulators of this pass complete
@@ -810,6 +843,7 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
     a.n_items = a.G * a.n_nets;
     a.n_whole = a.n_items; a.split = 1; a.n_virtual = a.n_items;
     a.dump = dump; a.dump_pass = dump_pass; a.prof = prof;
+    a.diag_nostream = prof ? ((flags & 0x200) ? 1 : 0) | ((flags & 0x400) ? 2 : 0) | ((flags & 0x800) ? 4 : 0) : 0;
     if (!g_dbg_host) {
         if (cudaHostAlloc((void **)&g_dbg_host, 64, cudaHostAllocMapped) != cudaSuccess) g_dbg_host = nullptr;
         else memset(g_dbg_host, 0, 64);
