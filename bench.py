@@ -40,6 +40,16 @@ def load_nets():
     return sd17, sd19, sdv
 
 
+def ncu_traffic(kernel, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this kernel
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None when no capture exists for this batch size"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    e = json.load(open(p)).get(kernel)
+    return e["dram_bytes_per_launch"] if e and e.get("batch") == batch else None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -49,22 +59,57 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampled in the background during the timed region"""
+    """SM clock and throttle reasons sampled in a background thread DURING the timed region (NVML in-process, every
+    2 ms; nvidia-smi as a fallback when the bindings are missing)"""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], False
+        self.index, self.sm, self.mx, self.reasons, self.stop, self.n = index, [], [], set(), False, 0
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical(index))
+        except Exception:  # noqa: BLE001
+            self.nv = None
         self.t = threading.Thread(target=self.run, daemon=True)
+
+    @staticmethod
+    def _physical(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if index < len(ids) and ids[index].strip().isdigit():
+                return int(ids[index])
+        return index
 
     def run(self):
         while not self.stop:
             try:
+                if self.nv is not None:
+                    nv = self.nv
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                                      (0x4, "sw_power_cap")):
+                        if r & bit:
+                            self.reasons.add(name)
+                    self.n += 1
+                    time.sleep(0.002)
+                    continue
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                    capture_output=True, text=True, timeout=5).stdout.strip()
                 if o:
-                    self.rows.append([c.strip() for c in o.split(",")])
+                    c = [x.strip() for x in o.split(",")]
+                    self.sm.append(float(c[0])); self.mx.append(float(c[1])); self.n += 1
+                    for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                        if c[2 + i].lower().startswith("active"):
+                            self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
             time.sleep(0.05)
@@ -78,12 +123,9 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons), "samples": self.n,
+                "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 def synth_positions(bk, dev, n, seed):
@@ -185,7 +227,7 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    sd17, _, sdv = load_nets()
+    sd17, sd19, sdv = load_nets()
     pol, val = bk.PackedNet(sd17, dev), bk.PackedNet(sdv, dev)
     pos = synth_positions(bk, dev, B, seed=1 + rank)
     L = _lib.lib()
@@ -211,7 +253,7 @@ def run_ours(args, rank, world, local_rank):
         _, pr, v = bk.policy_value_batch(feats["conv"], B, pol, val, want_logits=False)
         h_probs.copy_(pr, non_blocking=True); h_value.copy_(v, non_blocking=True)
 
-    def timed(fn, n, warm):
+    def timed(fn, n, warm, flush_l2=True):
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
@@ -220,7 +262,8 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         for a, b in ev:
-            flush.zero_()                      # evict L2 between timed iterations (outside the timed span)
+            if flush_l2:
+                flush.zero_()                  # evict L2 between timed iterations (outside the timed span)
             a.record(); fn(); b.record()
         torch.cuda.synchronize()
         if dist:
@@ -244,6 +287,27 @@ def run_ours(args, rank, world, local_rank):
             bk.features_batch(pos, fresh_libs=True, want=("conv", "legal"), out=feats)
         e_tot, e_ms = timed(enc_only, args.steps, 1)
         e2e_tot, e2e_ms = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+        # secondary lines of the metric: self-play games/s (args.selfplay_games games sharded over the ranks: strong
+        # scaling, gather of the records inside the timed region) and --simulate playouts/s (weak scaling)
+        extra = {}
+        if not args.no_playouts:
+            from bokego_b200 import playout as po
+            pol19 = bk.PackedNet(sd19, dev)
+            lo, hi = po.shard_range(args.selfplay_games, rank, world)
+            sp = po.PlayoutGraph(hi - lo, dev, pol, bk.MODE_SELFPLAY, seed=1, game0=lo, policy_odd=pol19)
+
+            def selfplay_once():
+                res = sp.replay()
+                po.gather_records(res.records(), args.selfplay_games, rank, world)
+            sp_tot, sp_ms = timed(selfplay_once, 3, 1, flush_l2=False)
+            sim = po.PlayoutGraph(args.simulate_boards, dev, pol, bk.MODE_MCTS, seed=2, game0=rank * args.simulate_boards)
+            sim_tot, sim_ms = timed(lambda: sim.replay(), 2, 1, flush_l2=False)
+            extra = {"selfplay": {"games": args.selfplay_games, "games_per_s": args.selfplay_games * 3 / (1e-3 * sp_tot),
+                                  "ms_per_batch": sp_tot / 3, "moves_per_game": 72, "scaling": "strong",
+                                  "nets": "policy_17 (black) vs policy_19 (white)", "gather": "nccl all_gather of records" if world > 1 else "none",
+                                  "kernel_launches_per_batch": sp.launches},
+                     "simulate": {"boards_per_gpu": args.simulate_boards, "playouts_per_s": world * args.simulate_boards * 2 / (1e-3 * sim_tot),
+                                  "ms_per_batch": sim_tot / 2, "scaling": "weak", "max_turn": 80}}
     clocks = cs.summary()
     launches_timed = launches * args.steps // (args.steps + args.warmup)
 
@@ -264,7 +328,8 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": B * (81 + 6), "d2h_bytes_per_step": B * (81 * 4 + 4)},
             "gpu_launches": launches_timed,
             "roofline": {"kernel": "bk_forward_tc_kernel", "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": ach / tf_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / tf_peak, "traffic": ncu_traffic("bk_forward_tc_kernel", B), "peak_source": peak_src,
+                         "algorithmic_flop_per_launch": FLOP_VALID * B,
                          "achieved_dense_count": FLOP_DENSE * B / k_s / 1e12, "kernel_ms": 1e3 * k_s,
                          "encoder": {"kernel": "bk_encode_kernel", "bound": "hbm", "ms": float(np.mean(e_ms)),
                                      "achieved": 4461 * B / (1e-3 * float(np.mean(e_ms))) / 1e9, "peak": hbm_peak, "unit": "GB/s"}},
@@ -273,6 +338,7 @@ def run_ours(args, rank, world, local_rank):
             rate, cores, ts = cpu_rate(args.cpu_sample, sd17, sdv)
             line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_sample} positions, 1 pass ({ts[0]:.1f} s); C feature oracle (OpenMP) + fp32 torch CPU forward, {cores} threads"}
+        line.update(extra)
         print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
@@ -281,12 +347,15 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-playouts", action="store_true", help="skip the self-play / simulate secondary measurements")
+    ap.add_argument("--selfplay-games", type=int, default=4096)
+    ap.add_argument("--simulate-boards", type=int, default=65536)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

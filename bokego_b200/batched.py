@@ -144,7 +144,7 @@ class PackedNet:
         self.device = dev
 
 
-def policy_value_batch(feats_conv, B, policy=None, value=None, want_logits=True, simt=False, _extra_flags=0):
+def policy_value_batch(feats_conv, B, policy=None, value=None, want_logits=True, simt=False, _extra_flags=0, probs_out=None):
     """PolicyNet / ValueNet forward for B positions (kernel b).
 
     feats_conv: the "conv" output of features_batch.  policy / value: PackedNet or None.
@@ -157,7 +157,11 @@ def policy_value_batch(feats_conv, B, policy=None, value=None, want_logits=True,
     if feats_conv.device != dev or feats_conv.numel() < L.bk_feats_conv_bytes(B):
         raise ValueError("feats_conv: wrong device or too small for B")
     logits = torch.empty(B, 81, dtype=torch.float32, device=dev) if (policy is not None and want_logits) else None
-    probs = torch.empty(B, 81, dtype=torch.float32, device=dev) if policy is not None else None
+    probs = None
+    if policy is not None:
+        if probs_out is not None:
+            _want(probs_out, torch.float32, (B, 81), "probs_out", dev)
+        probs = probs_out if probs_out is not None else torch.empty(B, 81, dtype=torch.float32, device=dev)
     val = torch.empty(B, dtype=torch.float32, device=dev) if value is not None else None
     flags = (FLAG_POLICY if policy is not None else 0) | (FLAG_VALUE if value is not None else 0) | \
             (FLAG_SIMT if simt else 0) | _extra_flags
@@ -193,14 +197,19 @@ def playout_step(pos, probs, mode, max_turn, seed=0, game0=0, q_inj=None, moves_
     return moves_out
 
 
-def score_batch(boards, komi=5.5):
+def score_batch(boards, komi=5.5, out=None):
     """Game.score() and the +-1 reward for a batch: returns (score float32 [B], reward int8 [B])."""
     L = _lib.lib()
     dev = _lib.require_device(boards.device)
     B = boards.shape[0]
     _want(boards, torch.int8, (B, 81), "boards", dev)
-    score = torch.empty(B, dtype=torch.float32, device=dev)
-    reward = torch.empty(B, dtype=torch.int8, device=dev)
+    if out is not None:
+        score, reward = out
+        _want(score, torch.float32, (B,), "score", dev)
+        _want(reward, torch.int8, (B,), "reward", dev)
+    else:
+        score = torch.empty(B, dtype=torch.float32, device=dev)
+        reward = torch.empty(B, dtype=torch.int8, device=dev)
     with torch.cuda.device(dev):
         rc = L.bk_score(_lib.ptr(boards), C.c_float(komi), _lib.ptr(score), _lib.ptr(reward), B, _lib.stream_ptr(dev))
     _lib.check(rc, "bk_score")

@@ -81,6 +81,7 @@ bk_encode_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ 
     const BB own = blk ? black : white, opp = blk ? white : black;
     const bool carried = libs_in != nullptr;
     const bool stale = carried && last >= 0 && libs_in[(size_t)b * BK_NSQ + last] == 0;
+    __syncwarp();   // every lane has read libs_in[last]: libs_out may alias libs_in (each lane rewrites only its own squares)
 
     // ---- per-square evaluation --------------------------------------------------------------------
 #pragma unroll

@@ -1,0 +1,182 @@
+"""Whole playouts and self-play games on the device, sharded over ranks (SURVEY 8b `playout_batch`, 8e).
+
+One move step for every board of a batch = three kernel launches, boards resident in HBM:
+    bk_encode (carried liberty cache, in place)  ->  bk_forward (policy only)  ->  bk_playout_step
+which is exactly the loop of the reference's `MCTS._simulate` (/root/reference/bokego/mcts.py:195-206: `find_random_child`
+until terminal, then `reward`) and of `bin/selfplay.py:18-33` (`playout`: `legal_sample` for pi_1 / pi_2 alternately), run for
+all boards at once.  The steps of a whole game are captured once in a CUDA graph and replayed (the per-step work is small
+at self-play batch sizes, so launch latency matters).
+
+Games are independent: rank r of R owns the contiguous block of global game ids shard_range(n, r, R); the random stream is
+keyed by the GLOBAL id, so results do not depend on R.  The only communication is one all_gather of fixed-size records.
+"""
+import torch
+
+from . import _lib
+from .batched import (MODE_MCTS, MODE_SELFPLAY, Positions, features_batch, playout_step, policy_value_batch, score_batch)
+
+MCTS_MAX_TURN = 80        # mcts.py:13  (terminal iff turn > 80 or the move was PASS, mcts.py:362-364)
+SELFPLAY_MAX_TURN = 70    # bin/selfplay.py:16 (checked every two moves => 72 moves, selfplay.py:21-33)
+
+
+def shard_range(n, rank, world):
+    """contiguous block [lo, hi) of n units owned by `rank` of `world` (sizes differ by at most one)"""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class PlayoutResult:
+    """moves int16 [B, T] (BK_MOVE_* codes once a board is finished), n_moves int16 [B] (turn reached),
+    score float32 [B] (Game.score()), reward int8 [B] (+1 black wins, -1 otherwise)"""
+
+    def __init__(self, moves, n_moves, score, reward):
+        self.moves, self.n_moves, self.score, self.reward = moves, n_moves, score, reward
+
+    def records(self):
+        """fixed-size per-game records int16 [B, T + 3]: n_moves, reward, 2*score, moves..."""
+        head = torch.stack([self.n_moves.to(torch.int16), self.reward.to(torch.int16),
+                            torch.round(self.score * 2).to(torch.int16)], dim=1)
+        return torch.cat([head, self.moves], dim=1).contiguous()
+
+
+def n_steps_for(mode, max_turn, first_turn=0):
+    """number of move steps after which every board of the batch is finished"""
+    last = max_turn + (1 if mode == MODE_MCTS else 2)
+    return max(0, last - first_turn)
+
+
+def run_playouts(pos, policy, mode=MODE_MCTS, max_turn=None, seed=0, game0=0, policy_odd=None, n_steps=None,
+                 first_turn=0, komi=5.5, graph=True):
+    """Play every board of `pos` to the end with moves drawn from the policy net(s).
+
+    policy:     PackedNet used for every move, or for the moves made at even `turn` when policy_odd is given
+    policy_odd: PackedNet for the moves at odd turn (self-play of two nets; needs every board at the same turn parity,
+                `first_turn` states it)
+    mode:       MODE_MCTS (Go_MCTS.find_random_child, mcts.py:319-364) or MODE_SELFPLAY (legal_sample, selfplay.py:35-47)
+    Updates `pos` in place (pos.libs is allocated when absent: the first encode then takes exact liberties, like a fresh
+    Game) and returns a PlayoutResult.  Stream-ordered; does not synchronise.
+    """
+    dev, B = pos.device, pos.B
+    if max_turn is None:
+        max_turn = MCTS_MAX_TURN if mode == MODE_MCTS else SELFPLAY_MAX_TURN
+    if n_steps is None:
+        n_steps = n_steps_for(mode, max_turn, first_turn)
+    L = _lib.lib()
+    fresh_first = pos.libs is None
+    if fresh_first:
+        pos.libs = torch.zeros(B, 81, dtype=torch.uint8, device=dev)
+    moves = torch.empty(n_steps, B, dtype=torch.int16, device=dev)
+    bufs = {"conv": torch.empty(L.bk_feats_conv_bytes(B), dtype=torch.uint8, device=dev), "libs": pos.libs}
+    probs = torch.empty(B, 81, dtype=torch.float32, device=dev)
+
+    def step(k, fresh):
+        net = policy if (policy_odd is None or (first_turn + k) % 2 == 0) else policy_odd
+        features_batch(pos, fresh_libs=fresh, want=("conv", "libs"), out=bufs)
+        policy_value_batch(bufs["conv"], B, net, None, want_logits=False, probs_out=probs)
+        playout_step(pos, probs, mode, max_turn, seed=seed, game0=game0, moves_out=moves[k])
+
+    k0 = 0
+    if fresh_first and n_steps > 0:
+        step(0, True)
+        k0 = 1
+    if graph and n_steps - k0 > 0:
+        # warm-up launch outside capture is not needed: the library sets its kernel attributes on first use above or here
+        if k0 == 0:
+            step(0, False)
+            k0 = 1
+        g = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=dev)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cap):
+            with torch.cuda.graph(g, stream=cap):
+                for k in range(k0, n_steps):
+                    step(k, False)
+        torch.cuda.current_stream(dev).wait_stream(cap)
+        g.replay()
+    else:
+        for k in range(k0, n_steps):
+            step(k, False)
+    score, reward = score_batch(pos.boards, komi)
+    return PlayoutResult(moves.t().contiguous(), pos.turn.clone(), score, reward)
+
+
+class PlayoutGraph:
+    """Games from the empty board, captured once as a CUDA graph (state reset, every move step, scoring) and replayable:
+    the form used when the same batch of games is played repeatedly (benchmarks, fixed-size self-play workers).
+    Seed and first game id are kernel arguments and therefore fixed at capture."""
+
+    def __init__(self, B, device, policy, mode, max_turn=None, seed=0, game0=0, policy_odd=None, komi=5.5):
+        dev = _lib.require_device(device)
+        if max_turn is None:
+            max_turn = MCTS_MAX_TURN if mode == MODE_MCTS else SELFPLAY_MAX_TURN
+        self.pos = Positions.empty(B, dev)
+        self.n_steps = n_steps_for(mode, max_turn, 0)
+        L = _lib.lib()
+        pos = self.pos
+        self.moves = torch.empty(self.n_steps, B, dtype=torch.int16, device=dev)
+        bufs = {"conv": torch.empty(L.bk_feats_conv_bytes(B), dtype=torch.uint8, device=dev), "libs": pos.libs}
+        probs = torch.empty(B, 81, dtype=torch.float32, device=dev)
+        self.score = torch.empty(B, dtype=torch.float32, device=dev)
+        self.reward = torch.empty(B, dtype=torch.int8, device=dev)
+
+        def body():
+            pos.boards.zero_(); pos.ko.fill_(-1); pos.last.fill_(-2); pos.turn.zero_(); pos.done.zero_()
+            for k in range(self.n_steps):
+                net = policy if (policy_odd is None or k % 2 == 0) else policy_odd
+                features_batch(pos, fresh_libs=(k == 0), want=("conv", "libs"), out=bufs)
+                policy_value_batch(bufs["conv"], B, net, None, want_logits=False, probs_out=probs)
+                playout_step(pos, probs, mode, max_turn, seed=seed, game0=game0, moves_out=self.moves[k])
+            score_batch(pos.boards, komi, out=(self.score, self.reward))
+
+        # one eager step first: the library sets its kernel attributes on first use, which must not happen under capture
+        features_batch(pos, fresh_libs=True, want=("conv", "libs"), out=bufs)
+        policy_value_batch(bufs["conv"], B, policy, None, want_logits=False, probs_out=probs)
+        self.launches = 5 + 3 * self.n_steps + 1
+        self.graph = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=dev)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cap):
+            with torch.cuda.graph(self.graph, stream=cap):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(cap)
+
+    def replay(self):
+        self.graph.replay()
+        return PlayoutResult(self.moves.t(), self.pos.turn, self.score, self.reward)
+
+
+def self_play(n_games, policy_black, policy_white, device, seed=0, rank=0, world=1, graph=True):
+    """bin/selfplay.py:49-57 `self_play` for this rank's share of `n_games` games from the empty board; the result of a game
+    is the sign of Game.score() (gnugo is not available, SURVEY 8c shim 4).  Returns (lo, hi, PlayoutResult)."""
+    lo, hi = shard_range(n_games, rank, world)
+    pos = Positions.empty(hi - lo, device, track_libs=False)
+    res = run_playouts(pos, policy_black, MODE_SELFPLAY, SELFPLAY_MAX_TURN, seed=seed, game0=lo, policy_odd=policy_white,
+                       graph=graph)
+    return lo, hi, res
+
+
+def simulate(n_boards, policy, device, seed=0, rank=0, world=1, graph=True):
+    """`--simulate` playouts (mcts.py:195-206) from the empty board for this rank's share of `n_boards` boards"""
+    lo, hi = shard_range(n_boards, rank, world)
+    pos = Positions.empty(hi - lo, device, track_libs=False)
+    res = run_playouts(pos, policy, MODE_MCTS, MCTS_MAX_TURN, seed=seed, game0=lo, graph=graph)
+    return lo, hi, res
+
+
+def gather_records(local, n_total, rank, world, group=None):
+    """all_gather of the ranks' record blocks (int16 [n_local, W], block r = shard_range(n_total, r, world)) into the full
+    [n_total, W] tensor on every rank.  NCCL for CUDA tensors, gloo for CPU tensors; a no-op for world == 1."""
+    if world == 1:
+        return local
+    import torch.distributed as dist
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    width = local.shape[1]
+    most = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros(most, width, dtype=torch.int32, device=local.device)   # int32 on the wire: gloo has no int16
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([parts[r][: hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0).to(local.dtype)

@@ -55,7 +55,7 @@ int bk_device_check(void);
  * Outputs (each may be NULL): feats_conv = fp16 operand of bk_forward, bk_feats_conv_bytes(B) bytes;
  * feats_f32 = float32 [B][27][9][9] exactly as nnet.features returns; planes_u8 = same values as
  * uint8 [B][27][81]; legal_out uint8 [B][81] (Game.get_legal_moves, go.py:245-260);
- * libs_out uint8 [B][81] (Game._libs after the call). */
+ * libs_out uint8 [B][81] (Game._libs after the call; may alias libs_in for an in-place update). */
 size_t bk_feats_conv_bytes(int B);
 int bk_encode(const int8_t *boards, const int16_t *ko, const int16_t *last, const int16_t *turn,
               const uint8_t *libs_in, void *feats_conv, float *feats_f32, uint8_t *planes_u8,

@@ -50,3 +50,13 @@ if os.path.exists(rep):
                     f.write(f"| {base} | {r[i]} | {units[i]} |\n")
             f.write("\n")
     print(open(f"profiles/{tag}_{os.path.basename(rep).replace('.ncu-rep','')}_metrics.md").read()[:3000])
+
+    # per-launch DRAM traffic of the conv kernel for bench.py's roofline.traffic (captured at the bench's default batch)
+    import json
+    ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:] if "bk_forward_tc" in r[ik]]
+    if vals:
+        json.dump({"bk_forward_tc_kernel": {"batch": int(os.environ.get("BK_NCU_BATCH", "4096")), "dram_bytes_per_launch": sum(vals) / len(vals),
+                                            "launches": len(vals), "source": f"profiles/{tag}_{os.path.basename(rep).replace('.ncu-rep','')}_metrics.md"}},
+                  open("profiles/ncu_traffic.json", "w"), indent=1)
