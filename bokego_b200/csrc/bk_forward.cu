@@ -3,21 +3,26 @@
 // Replaces PolicyNet.forward (/root/reference/bokego/nnet.py:19-57), ValueNet.forward (nnet.py:59-113),
 // Conv2dUntiedBias.forward (nnet.py:175-180) and SOFT (nnet.py:16) in eval mode, BatchNorm folded.
 //
-// One persistent CTA per SM.  A work item is one trunk (policy or value) over up to 5 boards of one group:
+// Persistent CTA PAIRS (clusters of two, one CTA per SM).  A work item of one CTA is one trunk (policy or value)
+// over up to 5 boards of one group; the two CTAs of a pair work on two items of the SAME net in lock step and
+// share the weights through tcgen05 cta_group::2:
 //   * activations of the item (<= 5 x 100 padded rows x 128 ch, fp16) stay in shared memory for all 7 conv
-//     layers; each layer is an implicit GEMM  D[rows, 128 co] += A[rows + tap shift, ci] * W[tap]  issued as
-//     tcgen05.mma (cta_group::1, kind::f16, M=128, N=128, K=16) with fp32 accumulators for up to four 128-row
-//     tiles resident in TMEM (4 x 128 = 512 columns);
-//   * weights stream L2 -> shared memory in 8 KiB stages of two K steps (cp.async.bulk + mbarrier, a 48 KiB
-//     ring); every stage is used by all tiles of the pass before its slot is recycled;
+//     layers; each layer is an implicit GEMM  D[rows, 128 co] += A[rows + tap shift, ci] * W[tap]  issued by the
+//     pair's leader as tcgen05.mma.cta_group::2.kind::f16, M=256 (128 rows of each CTA), N=128, K=16, with fp32
+//     accumulators for up to four 128-row tiles per CTA resident in TMEM (4 x 128 = 512 columns);
+//     a single-CTA M=128 x N=128 MMA reads 8 KiB of operands per 64 tensor cycles, i.e. it is bound by the
+//     128 B/clk shared-memory port (measured 76 cycles); in the pair each CTA reads its own A rows and only
+//     HALF of B (the weights of 64 output channels), 6 KiB per MMA, and the MMA runs at its 64-cycle floor;
+//   * weights stream L2 -> shared memory in stages of two K steps (4 KiB per CTA, cp.async.bulk + mbarrier,
+//     a 12-slot ring); every stage is used by all tiles of the pass before its slot is recycled;
 //   * the folded bias enters through the tensor core as well: two extra K rows (bias split into fp16 hi + lo)
 //     multiplied by a constant all-ones operand, so the accumulators leave TMEM ready for ReLU;
-//   * 16 epilogue warps (one thread per GEMM row: TMEM lane quarter = warp % 4, tile = warp / 4) pull the
+//   * 16 epilogue warps per CTA (one thread per GEMM row: TMEM lane quarter = warp % 4, tile = warp / 4) pull the
 //     accumulators out of TMEM (tcgen05.ld), apply ReLU, round to fp16 and write the next layer's operand in
 //     place; after the last layer they compute the 1x1 head with the untied bias and finish with the 81-way
 //     softmax (policy) or the small dense tail + tanh (value).
-// Warp roles: warps 0-15 epilogue, warp 16 = bulk-copy producer (+ TMEM allocation), warp 17 = MMA issuer
-// (warp-uniform control flow, lane 0 issues).
+// Warp roles: warps 0-15 epilogue, warp 16 = bulk-copy producer (+ TMEM allocation), warp 17 = MMA issuer in the
+// leader CTA / barrier forwarder in the peer CTA (tells the leader when the peer's operands have landed).
 // Items that do not fill a whole round of the grid are split into smaller board ranges (fewer M tiles each)
 // so that the last round, and small batches, spread over more SMs.
 //
@@ -33,7 +38,7 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------------
-// shared-memory plan of the tcgen05 kernel
+// shared-memory plan of the tcgen05 kernel (identical in both CTAs of a pair)
 // ------------------------------------------------------------------------------------------------------
 constexpr int A_MARGIN = 12;                       // zero rows in front of GEMM row 0 (|tap shift| <= 11)
 constexpr int A_ROWS = A_MARGIN + 512;             // 524: the rows behind a chunk are the next chunk's margin
@@ -43,37 +48,35 @@ constexpr int F_MARGIN = 24;                       // |5x5 tap shift| <= 24
 constexpr int F_ROWS = F_MARGIN + BK_F_ROWS_G;     // 629
 constexpr int F_LBO = F_ROWS * 16;
 constexpr int F_BYTES = (BK_F_CHUNKS * F_LBO + F_MARGIN * 16 + 127) / 128 * 128;   // 40,704 (+ zero rows behind chunk 3)
-#ifndef BK_KSTEPS_PER_STAGE
-#define BK_KSTEPS_PER_STAGE 2
-#endif
-constexpr int KSTEP_BYTES = 4096;                  // B operand of one K=16 MMA: [2 k-chunks][128 co][8 k] fp16
-constexpr int KPS = BK_KSTEPS_PER_STAGE;           // K steps per pipeline stage
-constexpr int STAGE_BYTES = KPS * KSTEP_BYTES;
-constexpr int N_STAGES = 49152 / STAGE_BYTES;      // 48 KiB weight ring
-constexpr int L0_KSTEPS = 51;                      // 25 taps x 2 halves + the bias step
-constexpr int L_KSTEPS = 73;                       // 9 taps x 8 + the bias step
+constexpr int CTA_STAGE_BYTES = BK_STAGE_BYTES / 2;   // this CTA's N half of a stage: [2 k-steps][2 k-chunks][64 co][8 k]
+constexpr int CTA_KSTEP_BYTES = BK_KSTEP_BYTES / 2;
+constexpr int N_STAGES = 12;                       // 48 KiB weight ring
 constexpr int ONES_BYTES = 4096;                   // [2 k-chunks][128 rows][8]: 1.0 in k = 0, 1
 constexpr int OFF_A = 0;
 constexpr int OFF_F = OFF_A + A_BYTES;             // F's front margin doubles as the rows behind A's last chunk
 constexpr int OFF_W = OFF_F + F_BYTES;
-constexpr int OFF_ONES = OFF_W + N_STAGES * STAGE_BYTES;
-constexpr int OFF_BAR = OFF_ONES + ONES_BYTES;     // barriers (2 * N_STAGES + 4, 8 B each)
-constexpr int OFF_TMEM = OFF_BAR + 256;
+constexpr int OFF_ONES = OFF_W + N_STAGES * CTA_STAGE_BYTES;
+constexpr int OFF_BAR = OFF_ONES + ONES_BYTES;     // barriers, 8 B each
+constexpr int OFF_TMEM = OFF_BAR + 384;
 constexpr int OFF_LOGIT = OFF_TMEM + 16;           // float[5][81]: head output per square
-constexpr int SMEM_BYTES = OFF_LOGIT + 1664;       // 229,904
+constexpr int SMEM_BYTES = OFF_LOGIT + 1664;       // 230,032
 static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KiB");
 static_assert(OFF_W % 128 == 0 && OFF_ONES % 128 == 0, "operand alignment");
 
-enum { BAR_WFULL = 0, BAR_WEMPTY = N_STAGES, BAR_ACC = 2 * N_STAGES, BAR_ACT, BAR_FFULL, BAR_FEMPTY, N_BARS };
-static_assert(N_BARS * 8 <= 256, "barrier area");
+// WFULL: this CTA's half of a stage has landed.  PFULL (leader): the peer's half has landed.  WEMPTY: the pair's MMAs
+// that read the stage are complete.  ACC: accumulators of the pass complete.  ACT (leader): both CTAs' epilogues done.
+// FFULL / PFFULL / FEMPTY: the same for the feature planes of an item.
+enum { BAR_WFULL = 0, BAR_PFULL = N_STAGES, BAR_WEMPTY = 2 * N_STAGES, BAR_ACC = 3 * N_STAGES, BAR_ACT, BAR_FFULL, BAR_PFFULL,
+       BAR_FEMPTY, N_BARS };
+static_assert(N_BARS * 8 <= 384, "barrier area");
 
 constexpr int N_EPI_WARPS = 16;
 constexpr int WARP_PRODUCER = 16;
 constexpr int WARP_MMA = 17;
 constexpr int N_THREADS = 576;
 
-// instruction descriptor: D=f32 (bit 4), A=B=f16 (0), both K-major (0), N=128 (>>3 at bit 17), M=128 (>>4 at bit 24)
-constexpr uint32_t IDESC = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D=f32 (bit 4), A=B=f16 (0), both K-major (0), N=128 (>>3 at bit 17), M=256 (>>4 at bit 24)
+constexpr uint32_t IDESC = (1u << 4) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 // high word of every shared-memory matrix descriptor used here: stride between 8-row groups = 128 B, version 1
 constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
 
@@ -81,6 +84,23 @@ constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -89,6 +109,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on a barrier of another (or this) CTA of the cluster; `cbar` is a shared::cluster address from mapa()
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cbar)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cbar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
 {
@@ -99,7 +124,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
@@ -135,28 +160,34 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// TMEM of the pair: the same warp of both CTAs allocates / frees, both get the same column range
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols)
 {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
 {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accum, uint32_t idesc = IDESC)
+// D[tmem] (+)= A[smem] * B[smem] over the CTA pair: rows 0..127 from the leader's A, 128..255 from the peer's A at the
+// same shared-memory offset; output channels 0..63 from the leader's B half, 64..127 from the peer's
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accum)
 {
     const uint64_t adesc = ((uint64_t)DESC_HI << 32) | a_lo, bdesc = ((uint64_t)DESC_HI << 32) | b_lo;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accum)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar)
+// completion of all MMAs issued so far -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
 }
 // 32 lanes x 32 consecutive columns of 32-bit accumulators -> 32 registers per thread
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
@@ -204,40 +235,51 @@ struct FwdArgs {
     const uint8_t *blob[2];    // policy, value
     float *logits, *probs, *value;
     int B, G, n_nets, first_net;
-    int n_items;               // G * n_nets (group, net) pairs
-    int n_whole;               // the first n_whole pairs are one item each; the rest are split ...
-    int split;                 // ... into `split` board ranges each
-    int n_virtual;             // n_whole + (n_items - n_whole) * split
+    // schedule: per net the sub-items are [whole groups 0..g_whole-1] then [groups g_whole..G-1 split into `split`
+    // board ranges each]; a PAIR takes sub-items 2j (leader) and 2j+1 (peer) of one net; pair v = j * n_nets + net
+    int g_whole, split, n_sub, n_pairs;
     float *dump;               // diagnostic: raw accumulators [640][128] of pass `dump_pass` (first item of CTA 0)
     int dump_pass;
-    int diag_nostream;         // diagnostic: the producer signals stages without copying weights
+    int diag;                  // diagnostic bits: 1 = producer signals stages without copying, 2 = aligned A windows
     long long *prof;           // diagnostic: clock64 stamps of CTA 0, 4 per pass
     unsigned int *dbg;         // host-mapped words written before a bounded wait traps
 };
 
 struct Item { int g, net, lo, nb; };
 
-// virtual item index -> (group, net, first board, board count); false when the range is empty
-__device__ __forceinline__ bool decode_item(const FwdArgs &a, int v, Item &it)
+// sub-item u of a net -> (group, first board, board count); nb = 0 when out of range or the range is empty
+__device__ __forceinline__ void decode_sub(const FwdArgs &a, int u, Item &it)
 {
-    int pair = v, lo = 0, hi = BK_GROUP;
-    if (v >= a.n_whole) {
-        const int j = v - a.n_whole;
-        pair = a.n_whole + j / a.split;
-        const int piece = j - (j / a.split) * a.split;
+    it.g = 0; it.lo = 0; it.nb = 0;
+    if (u >= a.n_sub) return;
+    int lo = 0, hi = BK_GROUP;
+    if (u < a.g_whole) {
+        it.g = u;
+    } else {
+        const int t = u - a.g_whole;
+        it.g = a.g_whole + t / a.split;
+        const int piece = t - (t / a.split) * a.split;
         lo = piece * BK_GROUP / a.split;
         hi = (piece + 1) * BK_GROUP / a.split;
     }
-    it.g = pair / a.n_nets;
-    it.net = a.first_net + (pair - it.g * a.n_nets);
     const int in_group = min(BK_GROUP, a.B - BK_GROUP * it.g);
     it.lo = min(lo, in_group);
     it.nb = min(hi, in_group) - it.lo;
-    return it.nb > 0;
+}
+// pair v -> this CTA's item and the board count that fixes the pass structure of the pair; false = nothing to do
+__device__ __forceinline__ bool decode_pair(const FwdArgs &a, int v, int rank, Item &mine, int &pair_nb)
+{
+    const int j = v / a.n_nets;
+    Item other;
+    decode_sub(a, 2 * j + rank, mine);
+    decode_sub(a, 2 * j + (rank ^ 1), other);
+    mine.net = a.first_net + (v - j * a.n_nets);
+    pair_nb = max(mine.nb, other.nb);
+    return pair_nb > 0;
 }
 
 // A full item takes 8 passes (layer 0 needs five 128-row tiles but TMEM holds four), a smaller one 7.
-struct Pass { int layer, tile0, n_tiles, n_ksteps; bool l0_last; };
+struct Pass { int layer, tile0, n_tiles; bool l0_last; };
 __device__ __forceinline__ int n_passes(int nb) { return nb == BK_GROUP ? 8 : 7; }
 __device__ __forceinline__ Pass pass_info(int nb, int ps)
 {
@@ -254,9 +296,9 @@ __device__ __forceinline__ Pass pass_info(int nb, int ps)
         p.n_tiles = ps == 0 ? (121 * nb - 2 + 127) >> 7 : nt;   // tiles of the stride-11 raster (layer 0)
         p.l0_last = ps == 0;
     }
-    p.n_ksteps = p.layer == 0 ? L0_KSTEPS : L_KSTEPS;
     return p;
 }
+__device__ __forceinline__ int n_stages_of(int layer) { return (layer == 0 ? BK_L0_FULL_STAGES : BK_L_FULL_STAGES) + 1; }
 
 // layers 1..6: GEMM row r (0..511) -> is it a real square of boards 0..nb-1?  (in place: destination row = r)
 __device__ __forceinline__ bool act_row_valid(int r, int nb, int &board, int &sq)
@@ -365,14 +407,15 @@ __device__ __forceinline__ void finish_board(const float *logit, int net, const 
 // ------------------------------------------------------------------------------------------------------
 // the tcgen05 kernel
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdArgs args)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdArgs args)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
     const uint32_t s_base = smem_u32(smem);
     const uint32_t sA = s_base + OFF_A, sF = s_base + OFF_F, sW = s_base + OFF_W, sBar = s_base + OFF_BAR;
     float *logit = reinterpret_cast<float *>(smem + OFF_LOGIT);
-    const int grid = gridDim.x;
+    const int rank = (int)cluster_ctarank();           // 0 = leader (issues the pair's MMAs), 1 = peer
+    const int pair0 = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     if (threadIdx.x == 0 && args.dbg) g_dbg = args.dbg;
 
     // ---- one-time setup: zero the operand buffers (pad rows must read as 0), the ones operand, barriers, TMEM
@@ -386,29 +429,36 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdAr
         fence_proxy_async();
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < N_STAGES; ++s) { mbar_init(sBar + 8 * (BAR_WFULL + s), 1); mbar_init(sBar + 8 * (BAR_WEMPTY + s), 1); }
+        for (int s = 0; s < N_STAGES; ++s) {
+            mbar_init(sBar + 8 * (BAR_WFULL + s), 1);
+            mbar_init(sBar + 8 * (BAR_PFULL + s), 1);
+            mbar_init(sBar + 8 * (BAR_WEMPTY + s), 1);
+        }
         mbar_init(sBar + 8 * BAR_ACC, 1);
-        mbar_init(sBar + 8 * BAR_ACT, N_EPI_WARPS);
+        mbar_init(sBar + 8 * BAR_ACT, 2 * N_EPI_WARPS);
         mbar_init(sBar + 8 * BAR_FFULL, 1);
+        mbar_init(sBar + 8 * BAR_PFFULL, 1);
         mbar_init(sBar + 8 * BAR_FEMPTY, 1);
         fence_barrier_init();
     }
     if (warp == WARP_PRODUCER) tmem_alloc(s_base + OFF_TMEM, 512);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                                 // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t *>(smem + OFF_TMEM), 0);
 
     if (warp == WARP_PRODUCER) {
-        // =========================== bulk-copy producer ===========================
+        // =========================== bulk-copy producer (both CTAs: own planes, own N half of the weights) =========
         if (lane == 0) {
             uint32_t wit = 0;   // weight stage counter over the whole kernel
             auto load_feats = [&](const Item &it) {
                 // rows of boards lo..lo+nb-1; a partial range is followed by 22 zero rows (board 0's top padding)
                 const uint8_t *src = args.feats + (size_t)it.g * BK_F_GROUP_BYTES;
                 const uint32_t n = (uint32_t)(BK_F_ROWS_B * it.nb) * 16u;
-                const uint32_t tail = it.nb < BK_GROUP ? 22u * 16u : 0u;
+                const uint32_t tail = (it.nb > 0 && it.nb < BK_GROUP) ? 22u * 16u : 0u;
                 mbar_arrive_expect_tx(sBar + 8 * BAR_FFULL, BK_F_CHUNKS * (n + tail));
+                if (n == 0) return;                      // the partner has boards, this CTA does not
 #pragma unroll
                 for (int c = 0; c < BK_F_CHUNKS; ++c) {
                     const uint32_t dst = sF + c * F_LBO + F_MARGIN * 16;
@@ -416,64 +466,85 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdAr
                     if (tail) bulk_g2s(dst + n, src + (size_t)c * BK_F_ROWS_G * 16, tail, sBar + 8 * BAR_FFULL);
                 }
             };
-            auto stream = [&](const uint8_t *src, int n_ksteps) {   // one layer's K steps, KPS per stage
-                for (int q = 0; q < n_ksteps; q += KPS, ++wit) {
+            auto stream = [&](const uint8_t *layer, int n_stages) {   // this CTA's half of every stage of one layer
+                for (int s = 0; s < n_stages; ++s, ++wit) {
                     const uint32_t st = wit % N_STAGES, ph = (wit / N_STAGES) & 1u;
-                    const uint32_t bytes = (uint32_t)min(KPS, n_ksteps - q) * KSTEP_BYTES;
+                    const uint32_t bytes = s == n_stages - 1 ? BK_BIAS_STAGE_BYTES / 2 : CTA_STAGE_BYTES;
+                    const long long t_we = args.prof ? clock64() : 0;   // diagnostic: when the producer started waiting for the slot
                     mbar_wait(sBar + 8 * (BAR_WEMPTY + st), ph ^ 1u, 0x100u + wit);
-                    if ((args.diag_nostream & 1) && wit >= N_STAGES) {       // measurement only: skip the copy (wrong results)
+                    if ((args.diag & 1) && wit >= N_STAGES) {          // measurement only: skip the copy (wrong results)
                         mbar_arrive(sBar + 8 * (BAR_WFULL + st));
                         continue;
                     }
+                    if (args.prof && blockIdx.x == 1 && wit < 128) { args.prof[512 + wit] = t_we; args.prof[768 + wit] = clock64(); }
                     mbar_arrive_expect_tx(sBar + 8 * (BAR_WFULL + st), bytes);
-                    bulk_g2s(sW + st * STAGE_BYTES, src + (size_t)q * KSTEP_BYTES, bytes, sBar + 8 * (BAR_WFULL + st));
+                    bulk_g2s(sW + st * CTA_STAGE_BYTES, layer + (size_t)s * BK_STAGE_BYTES + (size_t)rank * bytes, bytes,
+                             sBar + 8 * (BAR_WFULL + st));
                 }
             };
             Item it, nx;
-            int n_done = 0;
-            if ((int)blockIdx.x < args.n_virtual && decode_item(args, blockIdx.x, it)) load_feats(it);
-            for (int v = blockIdx.x; v < args.n_virtual; v += grid) {
-                if (!decode_item(args, v, it)) continue;
+            int pair_nb, nx_nb, n_done = 0;
+            if (pair0 < args.n_pairs && decode_pair(args, pair0, rank, it, pair_nb)) load_feats(it);
+            for (int v = pair0; v < args.n_pairs; v += n_clusters) {
+                if (!decode_pair(args, v, rank, it, pair_nb)) continue;
                 const uint8_t *blob = args.blob[it.net];
-                stream(blob + BK_W_L0_OFF, L0_KSTEPS);
-                if (it.nb == BK_GROUP) stream(blob + BK_W_L0_OFF, L0_KSTEPS);   // layer 0, tile 4
-                stream(blob + BK_W_L_OFF(1), L_KSTEPS);
-                if (v + grid < args.n_virtual && decode_item(args, v + grid, nx)) {   // prefetch the next planes
+                stream(blob + BK_W_L0_OFF, n_stages_of(0));
+                if (pair_nb == BK_GROUP) stream(blob + BK_W_L0_OFF, n_stages_of(0));   // layer 0, tile 4
+                stream(blob + BK_W_L_OFF(1), n_stages_of(1));
+                if (v + n_clusters < args.n_pairs && decode_pair(args, v + n_clusters, rank, nx, nx_nb)) {   // prefetch planes
                     mbar_wait(sBar + 8 * BAR_FEMPTY, n_done & 1u, 0x200u);
                     load_feats(nx);
                 }
-                for (int l = 2; l <= 6; ++l) stream(blob + BK_W_L_OFF(l), L_KSTEPS);
+                for (int l = 2; l <= 6; ++l) stream(blob + BK_W_L_OFF(l), n_stages_of(l));
                 ++n_done;
             }
         }
+    } else if (warp == WARP_MMA && rank == 1) {
+        // =========================== peer: forward "my operands have landed" to the leader ===========================
+        uint32_t st = 0, ph = 0, n_done = 0, fwd_n = 0;
+        const uint32_t leader_bar = mapa(sBar, 0);
+        Item it;
+        int pair_nb;
+        for (int v = pair0; v < args.n_pairs; v += n_clusters) {
+            if (!decode_pair(args, v, rank, it, pair_nb)) continue;
+            mbar_wait(sBar + 8 * BAR_FFULL, n_done & 1u, 0x300u);
+            ++n_done;
+            if (lane == 0) mbar_arrive_cluster(leader_bar + 8 * BAR_PFFULL);
+            const int np = n_passes(pair_nb);
+            for (int ps = 0; ps < np; ++ps) {
+                const int ns = n_stages_of(pass_info(pair_nb, ps).layer);
+                for (int s = 0; s < ns; ++s) {
+                    mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x700u + st);
+                    if (lane == 0) mbar_arrive_cluster(leader_bar + 8 * (BAR_PFULL + st));
+                    if (args.prof && blockIdx.x == 1 && fwd_n < 128 && lane == 0) args.prof[640 + fwd_n] = clock64();
+                    ++fwd_n;
+                    if (++st == N_STAGES) { st = 0; ph ^= 1u; }
+                }
+            }
+        }
     } else if (warp == WARP_MMA) {
-        // =========================== MMA issuer (whole warp runs the loop, one elected lane issues) ===========
-        // The tensor pipe queues only a few MMAs, so the scalar work between two stages has to stay well below
-        // the ~190 cycles the queue covers: descriptors are formed with adds of compile-time offsets, and one
-        // elected lane issues all MMAs of a stage plus the commit that hands the stage back to the producer.
-        static_assert(KPS == 2, "the issue loop is written for stages of two K steps");
+        // =========================== leader: MMA issuer (whole warp runs the loop, one elected lane issues) ===========
+        // The tensor pipe queues only a few MMAs, so the scalar work between two stages has to stay small:
+        // descriptors are formed with adds of compile-time offsets, and one elected lane issues all MMAs of a stage
+        // plus the commit that hands the stage back to both producers.
         uint32_t st = 0, ph = 0, pass = 0, n_done = 0;   // weight ring slot / phase
         const uint32_t a_lo0 = desc_lo(sA + A_MARGIN * 16, A_LBO);
         const uint32_t f_lo0 = desc_lo(sF + F_MARGIN * 16, F_LBO);
         const uint32_t one_lo = desc_lo(s_base + OFF_ONES, 2048);
-        const uint32_t w_lo0 = desc_lo(sW, 2048);
+        const uint32_t w_lo0 = desc_lo(sW, 1024);          // B half: [2 k-chunks][64 co][8 k] per K step
         int n_tiles = 0;
-        // one stage: K steps with A windows a0 (and a1), B = the two 4 KiB halves of ring slot `st`
+        // one stage: K steps with A windows a0 (and a1), B = the two 2 KiB K steps of ring slot `st` in both CTAs
+        long long tw = 0, tp = 0, ti = 0;                  // diagnostic: cycles waiting for own / peer weights, issuing
+        const bool profiling = args.prof != nullptr && blockIdx.x == 0;
         auto stage = [&](uint32_t a0, uint32_t a1, bool two, uint32_t row_step, uint32_t accum0) {
+            long long c0 = 0, c1 = 0, c2 = 0;
+            if (profiling) c0 = clock64();
             mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x500u + st);
+            if (profiling) c1 = clock64();
+            mbar_wait(sBar + 8 * (BAR_PFULL + st), ph, 0x580u + st);
+            if (profiling) { c2 = clock64(); tw += c1 - c0; tp += c2 - c1; }
             tc_fence_after();
-            const uint32_t w_lo = w_lo0 + st * (STAGE_BYTES >> 4);
-            if (args.diag_nostream & 4) {   // measurement only: the same K steps as two N=256 MMAs (garbage results)
-                if (elect_one()) {
-                    const uint32_t id256 = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
-                    for (int t = 0; t < 2; ++t) umma_f16(tmem + (uint32_t)(t * 256), a0 + (uint32_t)t * row_step, w_lo, accum0, id256);
-                    if (two) for (int t = 0; t < 2; ++t) umma_f16(tmem + (uint32_t)(t * 256), a1 + (uint32_t)t * row_step, w_lo + 128u, 1u, id256);
-                    umma_commit(sBar + 8 * (BAR_WEMPTY + st));
-                }
-                __syncwarp();
-                if (++st == N_STAGES) { st = 0; ph ^= 1u; }
-                return;
-            }
+            const uint32_t w_lo = w_lo0 + st * (CTA_STAGE_BYTES >> 4);
             if (elect_one()) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
@@ -481,21 +552,24 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdAr
                 if (two) {
 #pragma unroll
                     for (int t = 0; t < 4; ++t)
-                        if (t < n_tiles) umma_f16(tmem + (uint32_t)(t * 128), a1 + (uint32_t)t * row_step, w_lo + (KSTEP_BYTES >> 4), 1u);
+                        if (t < n_tiles) umma_f16(tmem + (uint32_t)(t * 128), a1 + (uint32_t)t * row_step, w_lo + (CTA_KSTEP_BYTES >> 4), 1u);
                 }
-                umma_commit(sBar + 8 * (BAR_WEMPTY + st));   // stage consumed -> producer may refill
+                umma_commit_pair(sBar + 8 * (BAR_WEMPTY + st));   // stage consumed -> both producers may refill
             }
             __syncwarp();
+            if (profiling) ti += clock64() - c2;
             if (++st == N_STAGES) { st = 0; ph ^= 1u; }
         };
         Item it;
-        for (int v = blockIdx.x; v < args.n_virtual; v += grid) {
-            if (!decode_item(args, v, it)) continue;
+        int pair_nb;
+        for (int v = pair0; v < args.n_pairs; v += n_clusters) {
+            if (!decode_pair(args, v, rank, it, pair_nb)) continue;
             mbar_wait(sBar + 8 * BAR_FFULL, n_done & 1u, 0x300u);
+            mbar_wait(sBar + 8 * BAR_PFFULL, n_done & 1u, 0x380u);
             ++n_done;
-            const int np = n_passes(it.nb);
+            const int np = n_passes(pair_nb);
             for (int ps = 0; ps < np; ++ps, ++pass) {
-                const Pass pi = pass_info(it.nb, ps);
+                const Pass pi = pass_info(pair_nb, ps);
                 n_tiles = pi.n_tiles;
                 if (pass > 0) mbar_wait(sBar + 8 * BAR_ACT, (pass - 1) & 1u, 0x400u + pass);   // operands written, TMEM drained
                 tc_fence_after();
@@ -511,7 +585,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdAr
                     for (int tap = 0; tap < 9; ++tap) {                // K steps 8*tap .. 8*tap+7: channel chunks 2j, 2j+1
                         const int ti = tap / 3, tj = tap - 3 * ti;
                         uint32_t a = a_lo0 + (uint32_t)((ti - 1) * 10 + (tj - 1));
-                        if (args.diag_nostream & 2) a = a_lo0 - 4u;                     // measurement only: 128 B aligned windows
+                        if (args.diag & 2) a = a_lo0 - 4u;             // measurement only: 128 B aligned windows
 #pragma unroll
                         for (int part = 0; part < 4; ++part)
                             stage(a + (uint32_t)(4 * part) * (A_LBO >> 4), a + (uint32_t)(4 * part + 2) * (A_LBO >> 4), true, 128u,
@@ -520,27 +594,33 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdAr
                 }
                 stage(one_lo, 0u, false, 0u, 1u);                      // bias rows x the all-ones operand
                 if (elect_one()) {
-                    if (pi.l0_last) umma_commit(sBar + 8 * BAR_FEMPTY);   // feature planes no longer needed
-                    umma_commit(sBar + 8 * BAR_ACC);                      // accumulators of this pass complete
+                    if (pi.l0_last) umma_commit_pair(sBar + 8 * BAR_FEMPTY);   // feature planes no longer needed
+                    umma_commit_pair(sBar + 8 * BAR_ACC);                      // accumulators of this pass complete
                 }
                 __syncwarp();
-                if (args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) args.prof[pass * 4 + 1] = clock64();
+                if (args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) {
+                    args.prof[pass * 4 + 1] = clock64();
+                    args.prof[256 + pass * 4 + 0] = tw; args.prof[256 + pass * 4 + 1] = tp; args.prof[256 + pass * 4 + 2] = ti;
+                    tw = tp = ti = 0;
+                }
                 __syncwarp();
             }
         }
     } else {
-        // =========================== epilogue warps ===========================
+        // =========================== epilogue warps (both CTAs, each on its own rows) ===========================
         const int quad = warp & 3, wq = warp >> 2;
         const uint32_t t_lane = tmem + ((uint32_t)(32 * quad) << 16);
+        const uint32_t leader_act = mapa(sBar + 8 * BAR_ACT, 0);
         uint32_t pass = 0;
         bool first = true;
         Item it;
-        for (int v = blockIdx.x; v < args.n_virtual; v += grid) {
-            if (!decode_item(args, v, it)) continue;
+        int pair_nb;
+        for (int v = pair0; v < args.n_pairs; v += n_clusters) {
+            if (!decode_pair(args, v, rank, it, pair_nb)) continue;
             const uint8_t *blob = args.blob[it.net];
-            const int np = n_passes(it.nb);
+            const int np = n_passes(pair_nb);
             for (int ps = 0; ps < np; ++ps, ++pass) {
-                const Pass pi = pass_info(it.nb, ps);
+                const Pass pi = pass_info(pair_nb, ps);
                 mbar_wait(sBar + 8 * BAR_ACC, pass & 1u, 0x600u + pass);
                 tc_fence_after();
                 const bool prof = args.prof && blockIdx.x == 0 && pass < 64 && threadIdx.x == 0;
@@ -596,7 +676,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdAr
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(sBar + 8 * BAR_ACT);
+                if (lane == 0) mbar_arrive_cluster(leader_act);
                 if (prof) args.prof[pass * 4 + 3] = clock64();
                 if (pi.layer == 6) {
                     // logit[] holds nb boards x 81 head outputs; it is next written seven passes from now, and
@@ -614,9 +694,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdAr
         }
     }
 
-    // ---- teardown ----------------------------------------------------------------------------------------
+    // ---- teardown: nobody leaves while the partner may still signal its barriers or read its shared memory ------
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();
     if (warp == WARP_PRODUCER) { __syncwarp(); tmem_dealloc(tmem, 512); }
 }
 
@@ -665,7 +746,7 @@ __global__ void __launch_bounds__(128) bk_forward_simt_kernel(const FwdArgs args
             const int ti = tap / kw, tj = tap - kw * ti;
             for (int c = 0; c < nchunk; ++c) {
                 const int k = tap * nchunk * 8 + c * 8;
-                const uint4 wv = *reinterpret_cast<const uint4 *>(wl + (size_t)(k >> 6) * BK_STAGE_BYTES + ((k & 63) >> 3) * 2048 + co * 16);
+                const uint4 wv = *reinterpret_cast<const uint4 *>(wl + BK_W_OFF(k, co));
                 const __half2 *wh = reinterpret_cast<const __half2 *>(&wv);
                 const float2 w01 = __half22float2(wh[0]), w23 = __half22float2(wh[1]), w45 = __half22float2(wh[2]),
                              w67 = __half22float2(wh[3]);
@@ -746,40 +827,29 @@ extern "C" int bk_weights_pack(const float *w0, const float *w16, const float *b
     if (!w0 || !w16 || !bias || !head_w || !head_b || !blob_out) return -1;
     uint8_t *blob = static_cast<uint8_t *>(blob_out);
     memset(blob, 0, BK_W_BLOB_BYTES);
-    uint16_t *h0 = reinterpret_cast<uint16_t *>(blob + BK_W_L0_OFF);
+    uint8_t *l0 = blob + BK_W_L0_OFF;
+    auto put = [](uint8_t *at, uint16_t v) { memcpy(at, &v, 2); };
     for (int co = 0; co < 128; ++co)
         for (int ci = 0; ci < 27; ++ci)
-            for (int tap = 0; tap < 25; ++tap) {
-                const int k = tap * 32 + ci;
-                h0[(size_t)(k >> 6) * (BK_STAGE_BYTES / 2) + ((k & 63) >> 3) * 1024 + co * 8 + (k & 7)] =
-                    f2h(w0[(co * 27 + ci) * 25 + tap]);
-            }
-    // folded bias as two extra K rows (fp16 hi + lo) that meet the all-ones operand: layer 0 in the spare
-    // tap slot (K = 800, 801), layers 1..6 in a short 19th stage (K rows 0, 1 of k-chunk 0)
+            for (int tap = 0; tap < 25; ++tap) put(l0 + BK_W_OFF(tap * 32 + ci, co), f2h(w0[(co * 27 + ci) * 25 + tap]));
+    // folded bias as two extra K rows (fp16 hi + lo) that meet the all-ones operand, in the short stage behind each layer
     for (int co = 0; co < 128; ++co) {
-        const float b = bias[co];
-        const uint16_t hi = f2h(b), lo = f2h(b - h2f(hi));
-        const int k = 800;
-        h0[(size_t)(k >> 6) * (BK_STAGE_BYTES / 2) + ((k & 63) >> 3) * 1024 + co * 8 + 0] = hi;
-        h0[(size_t)(k >> 6) * (BK_STAGE_BYTES / 2) + ((k & 63) >> 3) * 1024 + co * 8 + 1] = lo;
+        const uint16_t hi = f2h(bias[co]);
+        put(l0 + BK_W_BIAS_ROW_OFF(BK_L0_FULL_STAGES, 0, co), hi);
+        put(l0 + BK_W_BIAS_ROW_OFF(BK_L0_FULL_STAGES, 1, co), f2h(bias[co] - h2f(hi)));
     }
     for (int l = 1; l <= 6; ++l) {
-        uint16_t *hl = reinterpret_cast<uint16_t *>(blob + BK_W_L_OFF(l));
-        uint16_t *hb = hl + (size_t)BK_L_STAGES * (BK_STAGE_BYTES / 2);
+        uint8_t *ll = blob + BK_W_L_OFF(l);
+        const float *wl = w16 + (size_t)(l - 1) * 128 * 128 * 9;
         for (int co = 0; co < 128; ++co) {
             const float b = bias[l * 128 + co];
-            const uint16_t hi = f2h(b), lo = f2h(b - h2f(hi));
-            hb[co * 8 + 0] = hi;
-            hb[co * 8 + 1] = lo;
-        }
-        const float *wl = w16 + (size_t)(l - 1) * 128 * 128 * 9;
-        for (int co = 0; co < 128; ++co)
+            const uint16_t hi = f2h(b);
+            put(ll + BK_W_BIAS_ROW_OFF(BK_L_FULL_STAGES, 0, co), hi);
+            put(ll + BK_W_BIAS_ROW_OFF(BK_L_FULL_STAGES, 1, co), f2h(b - h2f(hi)));
             for (int ci = 0; ci < 128; ++ci)
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int k = tap * 128 + ci;
-                    hl[(size_t)(k >> 6) * (BK_STAGE_BYTES / 2) + ((k & 63) >> 3) * 1024 + co * 8 + (k & 7)] =
-                        f2h(wl[((size_t)co * 128 + ci) * 9 + tap]);
-                }
+                for (int tap = 0; tap < 9; ++tap)
+                    put(ll + BK_W_OFF(tap * 128 + ci, co), f2h(wl[((size_t)co * 128 + ci) * 9 + tap]));
+        }
     }
     memcpy(blob + BK_W_BIAS_OFF, bias, 7 * 128 * 4);
     memcpy(blob + BK_W_HEADW_OFF, head_w, 128 * 4);
@@ -840,10 +910,9 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
     a.B = B; a.G = (B + BK_GROUP - 1) / BK_GROUP;
     a.n_nets = (do_p ? 1 : 0) + (do_v ? 1 : 0);
     a.first_net = do_p ? 0 : 1;
-    a.n_items = a.G * a.n_nets;
-    a.n_whole = a.n_items; a.split = 1; a.n_virtual = a.n_items;
+    a.g_whole = a.G; a.split = 1; a.n_sub = a.G; a.n_pairs = 0;
     a.dump = dump; a.dump_pass = dump_pass; a.prof = prof;
-    a.diag_nostream = prof ? ((flags & 0x200) ? 1 : 0) | ((flags & 0x400) ? 2 : 0) | ((flags & 0x800) ? 4 : 0) : 0;
+    a.diag = prof ? ((flags & 0x200) ? 1 : 0) | ((flags & 0x400) ? 2 : 0) : 0;
     if (!g_dbg_host) {
         if (cudaHostAlloc((void **)&g_dbg_host, 64, cudaHostAllocMapped) != cudaSuccess) g_dbg_host = nullptr;
         else memset(g_dbg_host, 0, 64);
@@ -868,16 +937,21 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
             e = cudaFuncSetAttribute(bk_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
             if (e != cudaSuccess) { n_sm = 0; return -3; }
         }
-        // whole rounds of the grid take one (group, net) pair per CTA; the pairs of the last, partial round are
-        // split into board ranges so that it spreads over the idle SMs (fewer M tiles per CTA)
-        a.n_whole = (a.n_items / n_sm) * n_sm;
-        const int rest = a.n_items - a.n_whole;
-        if (rest > 0 && !(flags & BK_FWD_NOSPLIT)) {
+        // Schedule (see FwdArgs): CTA pairs take two groups of one net at a time.  The pairs of whole groups fill
+        // complete rounds of the n_sm / 2 clusters; the groups left over for the last, partial round are split into
+        // board ranges so that it spreads over the idle SMs (fewer M tiles per CTA).
+        const int n_clusters = n_sm / 2;
+        const int whole_pairs = a.n_nets * (a.G / 2);
+        const int rounds = whole_pairs / n_clusters;
+        a.g_whole = (flags & BK_FWD_NOSPLIT) ? a.G : 2 * (rounds * n_clusters / a.n_nets);
+        const int rest = (a.G - a.g_whole) * a.n_nets;          // whole-group items left for the last round
+        if (rest > 0) {
             a.split = n_sm / rest < BK_GROUP ? n_sm / rest : BK_GROUP;
             if (a.split < 1) a.split = 1;
         }
-        a.n_virtual = a.n_whole + rest * a.split;
-        const int grid = a.n_virtual < n_sm ? a.n_virtual : n_sm;
+        a.n_sub = a.g_whole + (a.G - a.g_whole) * a.split;
+        a.n_pairs = a.n_nets * ((a.n_sub + 1) / 2);
+        const int grid = 2 * (a.n_pairs < n_clusters ? a.n_pairs : n_clusters);
         bk_forward_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, stream>>>(a);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -3;

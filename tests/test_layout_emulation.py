@@ -11,9 +11,8 @@ from oracle import nets as onets
 
 GROUP, F_ROWS_B, F_ROWS_G = 5, 121, 605
 A_MARGIN, A_ROWS, F_MARGIN, F_ROWS = 12, 536, 24, 653   # emulation buffers (the kernel overlaps the margins)
-L_BYTES = 18 * 16384 + 4096          # 18 K-slabs + the short bias stage
-STAGE_H = 8192                      # halfs per 16 KiB stage
-L0_STAGES, L_STAGES = 13, 18
+L0_FULL, L_FULL = 25, 36             # full 8 KiB stages (two K steps) per layer; a 4 KiB bias stage follows
+L0_BYTES, L_BYTES = L0_FULL * 8192 + 4096, L_FULL * 8192 + 4096
 
 
 def _fold(sd):
@@ -41,16 +40,25 @@ def _pack(sd):
     return blob, bias, hw, hb
 
 
-def _stage(blob, byte_off, s):
-    """one 16 KiB K-slab -> float32 [64 k][128 co]"""
-    h = blob[byte_off + s * 16384: byte_off + (s + 1) * 16384].view(np.float16).astype(np.float32)
-    return h.reshape(8, 128, 8).transpose(0, 2, 1).reshape(64, 128)      # [kchunk][co][k8] -> [k][co]
+def _kstep(blob, layer_off, q):
+    """B operand of K step q of a layer as the CTA pair sees it -> float32 [16 k][128 co]:
+    stage q/2 = [2 N-halves][2 k-steps][2 k-chunks][64 co][8 k]; each CTA reads its half with k-chunk stride 1024 B"""
+    out = np.zeros((16, 128), np.float32)
+    for h in range(2):
+        off = layer_off + (q >> 1) * 8192 + h * 4096 + (q & 1) * 2048
+        half = blob[off: off + 2048].view(np.float16).astype(np.float32).reshape(2, 64, 8)   # [k-chunk][co][k8]
+        out[:, 64 * h: 64 * h + 64] = half.transpose(0, 2, 1).reshape(16, 64)
+    return out
 
 
-def _bias_stage(blob, byte_off):
-    """the 4 KiB bias stage behind a layer's 18 slabs -> float32 [16 k][128 co]"""
-    h = blob[byte_off + 18 * 16384: byte_off + 18 * 16384 + 4096].view(np.float16).astype(np.float32)
-    return h.reshape(2, 128, 8).transpose(0, 2, 1).reshape(16, 128)
+def _bias_step(blob, layer_off, n_full):
+    """the 4 KiB bias stage behind a layer's full stages -> float32 [16 k][128 co]"""
+    out = np.zeros((16, 128), np.float32)
+    for h in range(2):
+        off = layer_off + n_full * 8192 + h * 2048
+        half = blob[off: off + 2048].view(np.float16).astype(np.float32).reshape(2, 64, 8)
+        out[:, 64 * h: 64 * h + 64] = half.transpose(0, 2, 1).reshape(16, 64)
+    return out
 
 
 ONES = np.zeros(16, np.float32)
@@ -68,21 +76,17 @@ def _emulate(planes_u8, blob, bias, hw, hb):
     A = np.zeros((16, A_ROWS, 8), np.float32)
     # ---- layer 0: two passes (tiles 0..3, tile 4), 13 stages of two 5x5 taps ----
     D = np.zeros((640, 128), np.float32)
-    for s in range(L0_STAGES):
-        W = _stage(blob, 0, s)
-        for kk in range(4):
-            tap = 2 * s + (kk >> 1)
-            if tap >= 25:
-                if kk == 2:                                      # K rows 800, 801: bias hi + lo times the ones operand
-                    D += np.tile(ONES, (640, 1)) @ W[kk * 16:(kk + 1) * 16]
-                continue
-            off = (tap // 5 - 2) * 11 + (tap % 5 - 2)
-            c0 = (kk & 1) * 2
-            rows = F_MARGIN + np.arange(640) + off
-            ok = rows < F_ROWS                                   # rows past the buffer feed invalid outputs only
-            a = np.zeros((640, 16), np.float32)
-            a[ok] = np.concatenate([F[c0, rows[ok]], F[c0 + 1, rows[ok]]], axis=1)
-            D += a @ W[kk * 16:(kk + 1) * 16]
+    for q in range(50):                                          # K step q: tap q/2, channel chunks 0,1 / 2,3
+        W = _kstep(blob, 0, q)
+        tap = q >> 1
+        off = (tap // 5 - 2) * 11 + (tap % 5 - 2)
+        c0 = (q & 1) * 2
+        rows = F_MARGIN + np.arange(640) + off
+        ok = rows < F_ROWS                                       # rows past the buffer feed invalid outputs only
+        a = np.zeros((640, 16), np.float32)
+        a[ok] = np.concatenate([F[c0, rows[ok]], F[c0 + 1, rows[ok]]], axis=1)
+        D += a @ W
+    D += np.tile(ONES, (640, 1)) @ _bias_step(blob, 0, L0_FULL)  # bias hi + lo times the ones operand
     for r0 in range(640):
         board, rem = divmod(r0, F_ROWS_B)
         if board >= GROUP or rem < 22:
@@ -95,18 +99,17 @@ def _emulate(planes_u8, blob, bias, hw, hb):
         A[:, A_MARGIN + dest, :] = o.reshape(16, 8)
     # ---- layers 1..6 ----
     for layer in range(1, 7):
-        off_b = L0_STAGES * 16384 + (layer - 1) * L_BYTES
+        off_b = L0_BYTES + (layer - 1) * L_BYTES
         D = np.zeros((512, 128), np.float32)
-        for s in range(L_STAGES):
-            W = _stage(blob, off_b, s)
-            tap = s >> 1
+        for q in range(72):                                      # K step q: tap q/8, channel chunks 2*(q%8), +1
+            W = _kstep(blob, off_b, q)
+            tap = q >> 3
             off = (tap // 3 - 1) * 10 + (tap % 3 - 1)
             rows = A_MARGIN + np.arange(512) + off
-            for kk in range(4):
-                c0 = (s & 1) * 8 + kk * 2
-                a = np.concatenate([A[c0, rows], A[c0 + 1, rows]], axis=1)
-                D += a @ W[kk * 16:(kk + 1) * 16]
-        D += np.tile(ONES, (512, 1)) @ _bias_stage(blob, off_b)
+            c0 = (q & 7) * 2
+            a = np.concatenate([A[c0, rows], A[c0 + 1, rows]], axis=1)
+            D += a @ W
+        D += np.tile(ONES, (512, 1)) @ _bias_step(blob, off_b, L_FULL)
         logits = np.zeros((GROUP, 81), np.float32)
         for r in range(512):
             board, rem = divmod(r, 100)
@@ -144,16 +147,15 @@ def test_partial_group_is_isolated(positions, nets_golden, sd17):
 def test_blob_size_and_value_tail(sd_value):
     from bokego_b200 import _lib
     L = _lib.lib()
-    assert L.bk_weights_blob_bytes() == 2032896 and L.bk_feats_conv_bytes(4096) == 820 * 38720
+    assert L.bk_weights_blob_bytes() == 2028800 and L.bk_feats_conv_bytes(4096) == 820 * 38720
     assert L.bk_feats_conv_bytes(1) == 38720 and L.bk_feats_conv_bytes(0) == 0
 
 
 def test_bias_rows_reproduce_fp32_bias(sd17):
     """the fp16 hi + lo split of the folded bias (added by the tensor core) carries ~22 bits"""
     blob, bias, _, _ = _pack(sd17)
-    got0 = _stage(blob, 0, 12)[32:34].sum(0)                     # layer 0: K = 800, 801
-    assert np.abs(got0 - bias[0]).max() <= 2e-6 * max(1.0, np.abs(bias[0]).max())
-    for layer in range(1, 7):
-        b = _bias_stage(blob, L0_STAGES * 16384 + (layer - 1) * L_BYTES)
+    for layer in range(7):
+        off, n_full = (0, L0_FULL) if layer == 0 else (L0_BYTES + (layer - 1) * L_BYTES, L_FULL)
+        b = _bias_step(blob, off, n_full)
         assert np.abs(b[:2].sum(0) - bias[layer]).max() <= 2e-6 * max(1.0, np.abs(bias[layer]).max())
         assert not b[2:].any()

@@ -34,7 +34,7 @@ def main():
     logits = torch.zeros(B, 81, device=dev)
     probs = torch.zeros(B, 81, device=dev)
     value = torch.zeros(B, device=dev)
-    prof = torch.zeros(64 * 4, dtype=torch.int64, device=dev)
+    prof = torch.zeros(1024, dtype=torch.int64, device=dev)
     flags = (1 if a.nets == "policy" else 3) | a.flags
     for rep in range(3):
         prof.zero_()
@@ -46,15 +46,21 @@ def main():
         ev1.record()
         torch.cuda.synchronize()
     print("rc", rc, "kernel ms", ev0.elapsed_time(ev1))
-    p = prof.cpu().numpy().reshape(64, 4)
+    pall = prof.cpu().numpy()
+    p, w = pall[:256].reshape(64, 4), pall[256:512].reshape(64, 4)
+    we, full, iss = pall[512:640], pall[640:768], pall[768:896]
+    if iss[0]:
+        print('peer CTA, first stages: [wait-slot start, copy issue, landed+forwarded] relative; copy latency')
+        for i in range(0, 100, 1):
+            print(f'  stage {i:3d}  wait_start {we[i]-iss[0]:8d}  issue {iss[i]-iss[0]:8d}  fwd {full[i]-iss[0]:8d}  latency {full[i]-iss[i]:6d}')
     used = [i for i in range(64) if p[i, 0] != 0]
     t0 = p[used[0], 0]
-    print("pass  issue_start  issue_len  mma_phase(start->acc)  epilogue  gap_to_next_start")
+    print("pass  issue_start  issue_len  mma_phase(start->acc)  epilogue  gap_to_next_start | wait_own_w  wait_peer_w  issue")
     mma_tot = epi_tot = gap_tot = 0
     for k, i in enumerate(used):
         s, e, acc, act = p[i]
         nxt = p[used[k + 1], 0] if k + 1 < len(used) else act
-        print(f"{i:4d} {s - t0:12d} {e - s:10d} {acc - s:12d} {act - acc:16d} {nxt - act:10d}")
+        print(f"{i:4d} {s - t0:12d} {e - s:10d} {acc - s:12d} {act - acc:16d} {nxt - act:10d} | {w[i,0]:9d} {w[i,1]:9d} {w[i,2]:9d}")
         mma_tot += acc - s; epi_tot += act - acc; gap_tot += nxt - act
     tot = p[used[-1], 3] - t0
     print(f"passes {len(used)}  total {tot}  mma {mma_tot} ({100 * mma_tot / tot:.1f}%)  epilogue {epi_tot} "
