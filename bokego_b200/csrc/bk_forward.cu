@@ -28,6 +28,7 @@
 //
 // A plain CUDA-core kernel over the same packed operands (BK_FWD_SIMT) exists to validate the packing and
 // the tensor-core path against each other on the GPU; it is not a fallback and is never selected implicitly.
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -63,12 +64,18 @@ constexpr int SMEM_BYTES = OFF_LOGIT + 1664;       // 230,032
 static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KiB");
 static_assert(OFF_W % 128 == 0 && OFF_ONES % 128 == 0, "operand alignment");
 
-// WFULL: this CTA's half of a stage has landed.  PFULL (leader): the peer's half has landed.  WEMPTY: the pair's MMAs
-// that read the stage are complete.  ACC: accumulators of the pass complete.  ACT (leader): both CTAs' epilogues done.
-// FFULL / PFFULL / FEMPTY: the same for the feature planes of an item.
-enum { BAR_WFULL = 0, BAR_PFULL = N_STAGES, BAR_WEMPTY = 2 * N_STAGES, BAR_ACC = 3 * N_STAGES, BAR_ACT, BAR_FFULL, BAR_PFFULL,
-       BAR_FEMPTY, N_BARS };
+// WFULL (leader): both CTAs' halves of a stage have landed -- each CTA's tensor-map copy (cta_group::2) reports its
+// bytes to the LEADER's barrier.  WEMPTY: the pair's MMAs that read the stage are complete.  ACC: accumulators of the
+// pass complete.  ACT (leader): both CTAs' epilogues done.  FFULL / PFFULL (leader) / FEMPTY: the same for the
+// feature planes of an item (the peer forwards its FFULL to the leader's PFFULL, once per item).
+enum { BAR_WFULL = 0, BAR_WEMPTY = N_STAGES, BAR_ACC = 2 * N_STAGES, BAR_ACT, BAR_FFULL, BAR_PFFULL, BAR_FEMPTY, N_BARS };
 static_assert(N_BARS * 8 <= 384, "barrier area");
+
+// the conv weights of a blob seen as a 2-D tensor of 512-byte rows (256 fp16); one CTA's half of a stage = 8 rows
+constexpr int TM_ROW_BYTES = 512;
+constexpr int TM_BOX_ROWS = CTA_STAGE_BYTES / TM_ROW_BYTES;     // 8
+constexpr int TM_ROWS = BK_W_BIAS_OFF / TM_ROW_BYTES;           // 3912
+static_assert(BK_W_BIAS_OFF % TM_ROW_BYTES == 0 && BK_L0_BYTES % TM_ROW_BYTES == 0 && BK_L_BYTES % TM_ROW_BYTES == 0, "row grid");
 
 constexpr int N_EPI_WARPS = 16;
 constexpr int WARP_PRODUCER = 16;
@@ -115,6 +122,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cbar)
 {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cbar) : "memory");
 }
+// The epilogue's hand-over to the leader.  What the leader's MMAs read next is this CTA's OWN shared memory, through this
+// SM's tensor core; the stores were made visible to that (async) proxy by fence.proxy.async before this arrive, so only the
+// signal crosses the SM boundary and a cluster-scope release (which costs ~1,000 cycles here) is not needed.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cbar)
+{
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cbar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -153,6 +167,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+// 8 rows x 512 B of the weight tensor -> this CTA's shared memory; the byte count is reported to `cbar`, a barrier
+// that may live in the other CTA of the pair (shared::cluster address)
+__device__ __forceinline__ void tma_rows_g2s(uint32_t dst, const CUtensorMap *tm, int row, uint32_t cbar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row), "r"(cbar)
+        : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -407,7 +430,8 @@ __device__ __forceinline__ void finish_board(const float *logit, int net, const 
 // ------------------------------------------------------------------------------------------------------
 // the tcgen05 kernel
 // ------------------------------------------------------------------------------------------------------
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) bk_forward_tc_kernel(const FwdArgs args)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1)
+bk_forward_tc_kernel(const FwdArgs args, const __grid_constant__ CUtensorMap tm_policy, const __grid_constant__ CUtensorMap tm_value)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
@@ -431,7 +455,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) bk_for
     if (threadIdx.x == 0) {
         for (int s = 0; s < N_STAGES; ++s) {
             mbar_init(sBar + 8 * (BAR_WFULL + s), 1);
-            mbar_init(sBar + 8 * (BAR_PFULL + s), 1);
             mbar_init(sBar + 8 * (BAR_WEMPTY + s), 1);
         }
         mbar_init(sBar + 8 * BAR_ACC, 1);
@@ -466,20 +489,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) bk_for
                     if (tail) bulk_g2s(dst + n, src + (size_t)c * BK_F_ROWS_G * 16, tail, sBar + 8 * BAR_FFULL);
                 }
             };
-            auto stream = [&](const uint8_t *layer, int n_stages) {   // this CTA's half of every stage of one layer
+            const uint32_t leader_wfull = mapa(sBar + 8 * BAR_WFULL, 0);
+            auto stream = [&](const CUtensorMap *tm, int layer_off, int n_stages) {   // this CTA's half of every stage of a layer
                 for (int s = 0; s < n_stages; ++s, ++wit) {
                     const uint32_t st = wit % N_STAGES, ph = (wit / N_STAGES) & 1u;
-                    const uint32_t bytes = s == n_stages - 1 ? BK_BIAS_STAGE_BYTES / 2 : CTA_STAGE_BYTES;
-                    const long long t_we = args.prof ? clock64() : 0;   // diagnostic: when the producer started waiting for the slot
+                    // the short bias stage is [2 halves][2 KiB]; its copy still moves a whole 8-row box (the extra rows are unused)
+                    const int row = layer_off / TM_ROW_BYTES + s * (BK_STAGE_BYTES / TM_ROW_BYTES) +
+                                    rank * (s == n_stages - 1 ? TM_BOX_ROWS / 2 : TM_BOX_ROWS);
                     mbar_wait(sBar + 8 * (BAR_WEMPTY + st), ph ^ 1u, 0x100u + wit);
-                    if ((args.diag & 1) && wit >= N_STAGES) {          // measurement only: skip the copy (wrong results)
-                        mbar_arrive(sBar + 8 * (BAR_WFULL + st));
+                    if ((args.diag & 1) && wit >= N_STAGES) {          // measurement only: skip the copies (wrong results)
+                        if (rank == 0) mbar_arrive(sBar + 8 * (BAR_WFULL + st));
                         continue;
                     }
-                    if (args.prof && blockIdx.x == 1 && wit < 128) { args.prof[512 + wit] = t_we; args.prof[768 + wit] = clock64(); }
-                    mbar_arrive_expect_tx(sBar + 8 * (BAR_WFULL + st), bytes);
-                    bulk_g2s(sW + st * CTA_STAGE_BYTES, layer + (size_t)s * BK_STAGE_BYTES + (size_t)rank * bytes, bytes,
-                             sBar + 8 * (BAR_WFULL + st));
+                    if (rank == 0) mbar_arrive_expect_tx(sBar + 8 * (BAR_WFULL + st), 2 * CTA_STAGE_BYTES);   // both halves
+                    tma_rows_g2s(sW + st * CTA_STAGE_BYTES, tm, row, leader_wfull + 8 * st);
                 }
             };
             Item it, nx;
@@ -487,21 +510,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) bk_for
             if (pair0 < args.n_pairs && decode_pair(args, pair0, rank, it, pair_nb)) load_feats(it);
             for (int v = pair0; v < args.n_pairs; v += n_clusters) {
                 if (!decode_pair(args, v, rank, it, pair_nb)) continue;
-                const uint8_t *blob = args.blob[it.net];
-                stream(blob + BK_W_L0_OFF, n_stages_of(0));
-                if (pair_nb == BK_GROUP) stream(blob + BK_W_L0_OFF, n_stages_of(0));   // layer 0, tile 4
-                stream(blob + BK_W_L_OFF(1), n_stages_of(1));
+                const CUtensorMap *tm = it.net == 0 ? &tm_policy : &tm_value;
+                stream(tm, BK_W_L0_OFF, n_stages_of(0));
+                if (pair_nb == BK_GROUP) stream(tm, BK_W_L0_OFF, n_stages_of(0));   // layer 0, tile 4
+                stream(tm, BK_W_L_OFF(1), n_stages_of(1));
                 if (v + n_clusters < args.n_pairs && decode_pair(args, v + n_clusters, rank, nx, nx_nb)) {   // prefetch planes
                     mbar_wait(sBar + 8 * BAR_FEMPTY, n_done & 1u, 0x200u);
                     load_feats(nx);
                 }
-                for (int l = 2; l <= 6; ++l) stream(blob + BK_W_L_OFF(l), n_stages_of(l));
+                for (int l = 2; l <= 6; ++l) stream(tm, BK_W_L_OFF(l), n_stages_of(l));
                 ++n_done;
             }
         }
     } else if (warp == WARP_MMA && rank == 1) {
-        // =========================== peer: forward "my operands have landed" to the leader ===========================
-        uint32_t st = 0, ph = 0, n_done = 0, fwd_n = 0;
+        // =========================== peer: tell the leader when this CTA's feature planes have landed ===============
+        uint32_t n_done = 0;
         const uint32_t leader_bar = mapa(sBar, 0);
         Item it;
         int pair_nb;
@@ -510,17 +533,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) bk_for
             mbar_wait(sBar + 8 * BAR_FFULL, n_done & 1u, 0x300u);
             ++n_done;
             if (lane == 0) mbar_arrive_cluster(leader_bar + 8 * BAR_PFFULL);
-            const int np = n_passes(pair_nb);
-            for (int ps = 0; ps < np; ++ps) {
-                const int ns = n_stages_of(pass_info(pair_nb, ps).layer);
-                for (int s = 0; s < ns; ++s) {
-                    mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x700u + st);
-                    if (lane == 0) mbar_arrive_cluster(leader_bar + 8 * (BAR_PFULL + st));
-                    if (args.prof && blockIdx.x == 1 && fwd_n < 128 && lane == 0) args.prof[640 + fwd_n] = clock64();
-                    ++fwd_n;
-                    if (++st == N_STAGES) { st = 0; ph ^= 1u; }
-                }
-            }
         }
     } else if (warp == WARP_MMA) {
         // =========================== leader: MMA issuer (whole warp runs the loop, one elected lane issues) ===========
@@ -540,9 +552,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) bk_for
             long long c0 = 0, c1 = 0, c2 = 0;
             if (profiling) c0 = clock64();
             mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x500u + st);
-            if (profiling) c1 = clock64();
-            mbar_wait(sBar + 8 * (BAR_PFULL + st), ph, 0x580u + st);
-            if (profiling) { c2 = clock64(); tw += c1 - c0; tp += c2 - c1; }
+            if (profiling) { c1 = c2 = clock64(); tw += c1 - c0; tp += 0; }
             tc_fence_after();
             const uint32_t w_lo = w_lo0 + st * (CTA_STAGE_BYTES >> 4);
             if (elect_one()) {
@@ -676,7 +686,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) bk_for
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_act);
+                if (lane == 0) mbar_arrive_cluster_relaxed(leader_act);
                 if (prof) args.prof[pass * 4 + 3] = clock64();
                 if (pi.layer == 6) {
                     // logit[] holds nb boards x 81 head outputs; it is next written seven passes from now, and
@@ -869,6 +879,31 @@ extern "C" int bk_weights_pack(const float *w0, const float *w16, const float *b
 
 static unsigned int *g_dbg_host = nullptr;   // pinned, device-visible; survives a trapped kernel
 
+// Tensor map over the conv weights of one blob: rows of 512 bytes, boxes of 8 rows (one CTA's half of a stage).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_weight_map(const void *blob, CUtensorMap *out)
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -3;
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    memset(out, 0, sizeof(*out));
+    if (!blob) return 0;
+    const cuuint64_t dims[2] = {TM_ROW_BYTES / 2, (cuuint64_t)TM_ROWS};
+    const cuuint64_t strides[1] = {TM_ROW_BYTES};
+    const cuuint32_t box[2] = {TM_ROW_BYTES / 2, (cuuint32_t)TM_BOX_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(blob), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+
 extern "C" int bk_debug_words(unsigned int *out8)
 {
     for (int i = 0; i < 8; ++i) out8[i] = g_dbg_host ? g_dbg_host[i] : 0u;
@@ -952,7 +987,16 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
         a.n_sub = a.g_whole + (a.G - a.g_whole) * a.split;
         a.n_pairs = a.n_nets * ((a.n_sub + 1) / 2);
         const int grid = 2 * (a.n_pairs < n_clusters ? a.n_pairs : n_clusters);
-        bk_forward_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, stream>>>(a);
+        static const void *cached_blob[2] = {nullptr, nullptr};   // the maps depend on the blob addresses only
+        static CUtensorMap cached_map[2];
+        for (int i = 0; i < 2; ++i) {
+            if (cached_blob[i] != a.blob[i] || !a.blob[i]) {
+                const int rc = make_weight_map(a.blob[i], &cached_map[i]);
+                if (rc != 0) return rc;
+                cached_blob[i] = a.blob[i];
+            }
+        }
+        bk_forward_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, stream>>>(a, cached_map[0], cached_map[1]);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
