@@ -308,10 +308,10 @@ __device__ __forceinline__ Pass pass_info(int nb, int ps)
 {
     Pass p;
     const int nt = (100 * nb - 1 + 127) >> 7;           // tiles of the stride-10 raster (layers 1..6)
-    if (nb == BK_GROUP) {
+    if (nb == BK_GROUP) {                               // layer 0: tiles 0..2, then tiles 3..4 (3 + 2 balances the two passes)
         p.layer = ps < 2 ? 0 : ps - 1;
-        p.tile0 = ps == 1 ? 4 : 0;
-        p.n_tiles = ps == 0 ? 4 : (ps == 1 ? 1 : nt);
+        p.tile0 = ps == 1 ? 3 : 0;
+        p.n_tiles = ps == 0 ? 3 : (ps == 1 ? 2 : nt);
         p.l0_last = ps == 1;
     } else {
         p.layer = ps;
@@ -512,7 +512,7 @@ bk_forward_tc_kernel(const FwdArgs args, const __grid_constant__ CUtensorMap tm_
                 if (!decode_pair(args, v, rank, it, pair_nb)) continue;
                 const CUtensorMap *tm = it.net == 0 ? &tm_policy : &tm_value;
                 stream(tm, BK_W_L0_OFF, n_stages_of(0));
-                if (pair_nb == BK_GROUP) stream(tm, BK_W_L0_OFF, n_stages_of(0));   // layer 0, tile 4
+                if (pair_nb == BK_GROUP) stream(tm, BK_W_L0_OFF, n_stages_of(0));   // layer 0, second pass (tiles 3, 4)
                 stream(tm, BK_W_L_OFF(1), n_stages_of(1));
                 if (v + n_clusters < args.n_pairs && decode_pair(args, v + n_clusters, rank, nx, nx_nb)) {   // prefetch planes
                     mbar_wait(sBar + 8 * BAR_FEMPTY, n_done & 1u, 0x200u);
@@ -636,21 +636,9 @@ bk_forward_tc_kernel(const FwdArgs args, const __grid_constant__ CUtensorMap tm_
                 const bool prof = args.prof && blockIdx.x == 0 && pass < 64 && threadIdx.x == 0;
                 if (prof) args.prof[pass * 4 + 2] = clock64();
                 const bool dump = args.dump && blockIdx.x == 0 && first && ps == args.dump_pass;
-                if (pi.tile0 == 4) {
-                    // second layer-0 pass: one tile, the 16 warps split it by row quarter x column quarter
-                    const int r0 = 512 + 32 * quad + lane;
-                    const int dest = l0_dest_row(r0, it.nb);
-                    uint32_t v0[32];
-                    tmem_ld32(t_lane + (uint32_t)(wq * 32), v0);
-                    tc_wait_ld();
-                    if (dump) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) args.dump[(size_t)r0 * 128 + wq * 32 + i] = __uint_as_float(v0[i]);
-                    }
-                    if (dest >= 0) store_act32(smem, v0, wq * 4, dest);
-                } else if (wq < pi.n_tiles) {
-                    // one thread per GEMM row: all 128 output channels of row r
-                    const int r = 128 * wq + 32 * quad + lane;
+                if (wq < pi.n_tiles) {
+                    // one thread per GEMM row: all 128 output channels of row r (accumulator slot wq holds tile tile0 + wq)
+                    const int r = 128 * (pi.tile0 + wq) + 32 * quad + lane;
                     int dest, board = 0, sq = 0;
                     if (pi.layer == 0) dest = l0_dest_row(r, it.nb);
                     else dest = act_row_valid(r, it.nb, board, sq) ? r : -1;
