@@ -197,6 +197,29 @@ def playout_step(pos, probs, mode, max_turn, seed=0, game0=0, q_inj=None, moves_
     return moves_out
 
 
+def make_moves(pos, parent_idx, moves):
+    """Go_MCTS.make_move for a batch (mcts.py:340-346): child c = position parent_idx[c] of `pos` with moves[c] played.
+    parent_idx int32 [C], moves int16 [C] (device tensors).  Returns (Positions of the C children, status uint8 [C]);
+    the children carry the liberty cache exactly as deepcopy + play_move does."""
+    L = _lib.lib()
+    dev = pos.device
+    C_ = parent_idx.shape[0]
+    _want(parent_idx, torch.int32, (C_,), "parent_idx", dev)
+    _want(moves, torch.int16, (C_,), "moves", dev)
+    child = Positions(torch.empty(C_, 81, dtype=torch.int8, device=dev), torch.empty(C_, dtype=torch.int16, device=dev),
+                      torch.empty(C_, dtype=torch.int16, device=dev), torch.empty(C_, dtype=torch.int16, device=dev),
+                      torch.empty(C_, 81, dtype=torch.uint8, device=dev))
+    status = torch.empty(C_, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.bk_make_moves(_lib.ptr(pos.boards), _lib.ptr(pos.ko), _lib.ptr(pos.last), _lib.ptr(pos.turn), _lib.ptr(pos.libs),
+                             _lib.ptr(parent_idx), _lib.ptr(moves), _lib.ptr(child.boards), _lib.ptr(child.ko),
+                             _lib.ptr(child.last), _lib.ptr(child.turn), _lib.ptr(child.libs), _lib.ptr(status), C_,
+                             _lib.stream_ptr(dev))
+    _lib.check(rc, "bk_make_moves")
+    _lib.count_launch()
+    return child, status
+
+
 def score_batch(boards, komi=5.5, out=None):
     """Game.score() and the +-1 reward for a batch: returns (score float32 [B], reward int8 [B])."""
     L = _lib.lib()

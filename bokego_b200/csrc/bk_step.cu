@@ -191,6 +191,53 @@ bk_score_kernel(const int8_t *__restrict__ boards, float komi, float *__restrict
     }
 }
 
+// Go_MCTS.make_move (/root/reference/bokego/mcts.py:340-346) for a batch of children: child c is a copy of parent
+// parent_idx[c] with moves[c] played by Game.play_move (go.py:123-182; -1 = play_pass go.py:109-121).  One warp per child.
+// The carried liberty cache is refreshed on the PARENT position before the move, as go.py:160 does, and handed to the child
+// (deepcopy carries `_libs`, mcts.py:281-307); a parent without a cache (libs == nullptr) hands down exact liberties of the
+// parent position, which is what the first get_liberties() call of a fresh Game computes.
+// status: 0 ok, 1 ko, 2 not_empty, 3 suicide -- the reference raises IllegalMove there; the child is then the unchanged parent.
+__global__ void __launch_bounds__(128)
+bk_make_moves_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ ko_arr, const int16_t *__restrict__ last_arr,
+                     const int16_t *__restrict__ turn_arr, const uint8_t *__restrict__ libs, const int32_t *__restrict__ parent_idx,
+                     const int16_t *__restrict__ moves, int8_t *__restrict__ boards_out, int16_t *__restrict__ ko_out,
+                     int16_t *__restrict__ last_out, int16_t *__restrict__ turn_out, uint8_t *__restrict__ libs_out,
+                     uint8_t *__restrict__ status_out, int C)
+{
+    const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= C) return;
+    const int par = parent_idx[c];
+    const int mv = moves[c];
+    int ko = ko_arr[par], last = last_arr[par], turn = turn_arr[par];
+    BB black, white;
+    load_boards(boards + (size_t)par * BK_NSQ, lane, black, white);
+    if (libs_out) {
+        const uint8_t *lb = libs ? libs + (size_t)par * BK_NSQ : nullptr;
+        const bool stale = lb && mv >= 0 && last >= 0 && lb[last] == 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int p = lane + 32 * k;
+            if (p < BK_NSQ) {
+                int v;
+                if (!lb) v = bb_exact_lib_of(black, white, p);
+                else v = mv >= 0 ? bb_lazy_lib_of(black, white, last, stale, p, (int)lb[p]) : (int)lb[p];
+                libs_out[(size_t)c * BK_NSQ + p] = (uint8_t)v;
+            }
+        }
+    }
+    const int st = bb_play(black, white, ko, last, turn, mv);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int p = lane + 32 * k;
+        if (p < BK_NSQ) boards_out[(size_t)c * BK_NSQ + p] = bb_test(black, p) ? 1 : (bb_test(white, p) ? -1 : 0);
+    }
+    if (lane == 0) {
+        ko_out[c] = (int16_t)ko; last_out[c] = (int16_t)last; turn_out[c] = (int16_t)turn;
+        if (status_out) status_out[c] = (uint8_t)st;
+    }
+}
+
 __global__ void bk_exp_draws_kernel(uint64_t seed, uint32_t game0, uint32_t move, uint32_t tr, float *__restrict__ q, int B)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,6 +255,18 @@ extern "C" int bk_playout_step(int8_t *boards, int16_t *ko, int16_t *last, int16
     if (B <= 0) return 0;
     bk_step_kernel<<<(B + 3) / 4, 128, 0, stream>>>(boards, ko, last, turn, libs, done, probs, q_inj, q_vecs, seed, game0,
                                                     mode, max_turn, moves_out, B);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+extern "C" int bk_make_moves(const int8_t *boards, const int16_t *ko, const int16_t *last, const int16_t *turn, const uint8_t *libs,
+                             const int32_t *parent_idx, const int16_t *moves, int8_t *boards_out, int16_t *ko_out,
+                             int16_t *last_out, int16_t *turn_out, uint8_t *libs_out, uint8_t *status_out, int C,
+                             cudaStream_t stream)
+{
+    if (C <= 0) return 0;
+    if (!boards || !ko || !last || !turn || !parent_idx || !moves || !boards_out || !ko_out || !last_out || !turn_out) return -1;
+    bk_make_moves_kernel<<<(C + 3) / 4, 128, 0, stream>>>(boards, ko, last, turn, libs, parent_idx, moves, boards_out, ko_out,
+                                                          last_out, turn_out, libs_out, status_out, C);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

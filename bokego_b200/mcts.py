@@ -1,0 +1,252 @@
+"""Batched tree search over the B200 hot path (BASELINE configs[2]: "MCTS genmove with batched leaf
+evaluation, virtual loss").
+
+Same search rule as the reference's `MCTS` in its default `no_sim` mode (/root/reference/bokego/mcts.py:15-255):
+  * PUCT selection (mcts.py:219-234): child score = -V[c]/N[c] + c_puct * P_parent[move] * sqrt(max(1, sum_c N[c])) / (1 + N[c]);
+  * a leaf is expanded (all legal moves, never PASS, mcts.py:309-317) only once it has been visited more than `expand_thresh`
+    times (mcts.py:172-183); the root is expanded immediately (mcts.py:153-157);
+  * the leaf is scored by the value net, terminal or not (mcts.py:133-151), and the value alternates sign on the way up
+    (mcts.py:208-217); `choose` takes the most visited child and re-roots (mcts.py:110-131).
+What differs is the machinery: the tree is a set of flat arrays indexed by node id (no per-node Python objects, no dict
+caches), positions of all nodes live in one device-resident pool, children are made by one `bk_make_moves` launch per
+expansion, and leaves are evaluated in batches: `leaf_batch` descents are made under a virtual loss before one encoder +
+one policy/value launch scores every new leaf.  With `leaf_batch=1` the visit counts are those of the sequential rule.
+
+Ties in the arg-max go to the lowest move index (the reference iterates a Python set, i.e. its tie-break is arbitrary).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, go
+from .batched import NONE, PASS, Positions, features_batch, make_moves, policy_value_batch
+
+MAX_TURNS = 80   # mcts.py:13
+
+
+def fake_nets(boards, turn):
+    """Deterministic stand-in for the two nets, a function of the position only (test hook: tests/golden/make_golden_mcts.py
+    drives the REFERENCE search with the same function, so the tree statistics can be compared exactly).
+    boards int8 [n,81], turn int16 [n] -> (probs float32 [n,81], value float32 [n])"""
+    import zlib
+    probs = np.zeros((len(boards), 81), np.float32)
+    val = np.zeros(len(boards), np.float32)
+    for i in range(len(boards)):
+        rng = np.random.RandomState(zlib.crc32(np.ascontiguousarray(boards[i], np.int8).tobytes() + bytes([int(turn[i]) & 0xFF])))
+        lg = (rng.standard_normal(81) * 1.5).astype(np.float32)
+        e = np.exp(lg - lg.max())
+        probs[i] = (e / e.sum()).astype(np.float32)
+        val[i] = np.float32(np.tanh(rng.standard_normal()))
+    return probs, val
+
+
+class MCTS:
+    """root: a bokego_b200.go.Game (or None for the empty board).  policy_net / value_net: PackedNet (or the nnet mirror's
+    PolicyNet / ValueNet, whose packed blobs are used).  kwargs as in the reference: expand_thresh (100),
+    exploration_weight (4.0); additionally leaf_batch (descents per evaluation batch, default 1), device, and `nets_override`
+    (test hook: a callable (boards int8 [n,81], turn int16 [n]) -> (probs, value) replacing the two nets; the encoder still
+    supplies legal moves and the liberty cache)."""
+
+    def __init__(self, root=None, policy_net=None, value_net=None, **kwargs):
+        self.device = _lib.require_device(kwargs.get("device", "cuda"))
+        self.expand_thresh = kwargs.get("expand_thresh", 100)
+        self.exploration_weight = kwargs.get("exploration_weight", 4.0)
+        self.leaf_batch = max(1, int(kwargs.get("leaf_batch", 1)))
+        self.nets_override = kwargs.get("nets_override")
+        self.policy = self.value = None
+        if self.nets_override is None:
+            if policy_net is None:
+                raise TypeError("Missing required keywork argument: 'policy_net'")
+            if value_net is None:
+                raise TypeError("Keyword argument 'value_net' is required for no simulation mode")
+            pk = lambda n: n._packed(self.device) if hasattr(n, "_packed") else n
+            self.policy, self.value = pk(policy_net), pk(value_net)
+        self.n_evals = 0        # positions sent through the nets
+        self.n_eval_batches = 0
+        self.set_root(root)
+
+    # ---- storage ---------------------------------------------------------------------------------------------------
+    def _alloc(self, cap):
+        dev = self.device
+        self.cap = cap
+        self.pool = Positions(torch.zeros(cap, 81, dtype=torch.int8, device=dev), torch.full((cap,), -1, dtype=torch.int16, device=dev),
+                              torch.full((cap,), NONE, dtype=torch.int16, device=dev), torch.zeros(cap, dtype=torch.int16, device=dev),
+                              torch.zeros(cap, 81, dtype=torch.uint8, device=dev))
+        self.parent = np.full(cap, -1, np.int32)
+        self.move = np.full(cap, NONE, np.int16)        # the move that led to the node
+        self.N = np.zeros(cap, np.int64)
+        self.V = np.zeros(cap, np.float64)
+        self.child0 = np.full(cap, -1, np.int32)        # first child id, children are contiguous
+        self.nchild = np.full(cap, -1, np.int32)        # -1 = not expanded
+        self.val = np.full(cap, np.nan, np.float64)     # value net output (mover's perspective), nan = not evaluated
+        self.turn = np.zeros(cap, np.int16)
+        self.last = np.full(cap, NONE, np.int16)
+        self.prior = np.zeros((cap, 81), np.float32)    # policy probabilities of the node's position
+        self.legal = np.zeros((cap, 81), np.uint8)
+        self.n = 0
+
+    def _grow(self, need):
+        if self.n + need <= self.cap:
+            return
+        cap = max(self.cap * 2, self.n + need)
+        old, n = self.pool, self.n
+        keep = {k: getattr(self, k) for k in ("parent", "move", "N", "V", "child0", "nchild", "val", "turn", "last", "prior", "legal")}
+        self._alloc(cap)
+        self.n = n
+        for k, v in keep.items():
+            getattr(self, k)[: len(v)] = v
+        for a, b in ((self.pool.boards, old.boards), (self.pool.ko, old.ko), (self.pool.last, old.last), (self.pool.turn, old.turn),
+                     (self.pool.libs, old.libs)):
+            a[: b.shape[0]] = b
+
+    def set_root(self, root=None):
+        """Start a new tree at `root` (a go.Game, or None = empty board): evaluate it and expand it (mcts.py:153-157)."""
+        self._alloc(4096)
+        if root is None:
+            root = go.Game()
+        lut = {go.BLACK: 1, go.WHITE: -1, go.EMPTY: 0}
+        bd = torch.tensor([lut[c] for c in root.board], dtype=torch.int8)
+        self.pool.boards[0] = bd.to(self.device)
+        self.pool.ko[0] = -1 if root.ko is None else int(root.ko)
+        last = PASS if root.last_move == go.PASS else (NONE if not isinstance(root.last_move, int) else int(root.last_move))
+        self.pool.last[0] = last
+        self.pool.turn[0] = int(root.turn)
+        self.turn[0], self.last[0] = int(root.turn), last
+        self._root_fresh = root._libs is None
+        if root._libs is not None:
+            self.pool.libs[0] = torch.frombuffer(bytearray(root._libs), dtype=torch.uint8).to(self.device)
+        self.n = 1
+        self.root = 0
+        self._evaluate([0])
+        self._expand(0)
+
+    # ---- evaluation and expansion -------------------------------------------------------------------------------------
+    def _evaluate(self, ids):
+        """value, priors, legal moves and the refreshed liberty cache for the nodes `ids` (one encoder + one forward launch)"""
+        ids = [i for i in dict.fromkeys(ids) if np.isnan(self.val[i])]
+        if not ids:
+            return
+        idx = torch.as_tensor(ids, dtype=torch.long, device=self.device)
+        fresh = ids == [0] and getattr(self, "_root_fresh", False) and self.parent[0] < 0
+        sub = Positions(self.pool.boards[idx].contiguous(), self.pool.ko[idx].contiguous(), self.pool.last[idx].contiguous(),
+                        self.pool.turn[idx].contiguous(), None if fresh else self.pool.libs[idx].contiguous())
+        if self.nets_override is None:
+            out = features_batch(sub, want=("conv", "legal", "libs"))
+            _, probs, val = policy_value_batch(out["conv"], sub.B, self.policy, self.value, want_logits=False)
+            probs, val = probs.cpu().numpy(), val.double().cpu().numpy()
+        else:
+            out = features_batch(sub, want=("legal", "libs"))
+            probs, val = self.nets_override(sub.boards.cpu().numpy(), sub.turn.cpu().numpy())
+            # what the reference's search sees: Categorical renormalises the probabilities in float32 (nnet.py:274)
+            probs = torch.distributions.Categorical(probs=torch.from_numpy(np.asarray(probs, np.float32))).probs.numpy()
+        self.pool.libs[idx] = out["libs"]
+        self.prior[ids] = probs
+        self.val[ids] = np.asarray(val, np.float64)
+        self.legal[ids] = out["legal"].cpu().numpy()
+        self.n_evals += len(ids)
+        self.n_eval_batches += 1
+
+    def _terminal(self, i):
+        return self.turn[i] > MAX_TURNS or self.last[i] == PASS      # mcts.py:362-364
+
+    def _expand(self, i):
+        if self.nchild[i] >= 0:
+            return
+        if self._terminal(i):
+            self.nchild[i] = 0
+            return
+        mv = np.flatnonzero(self.legal[i]).astype(np.int16)
+        c = len(mv)
+        self.nchild[i] = c
+        if c == 0:
+            return
+        self._grow(c)
+        lo = self.n
+        par = torch.full((c,), i, dtype=torch.int32, device=self.device)
+        child, status = make_moves(self.pool, par, torch.from_numpy(mv).to(self.device))
+        sl = slice(lo, lo + c)
+        self.pool.boards[sl], self.pool.ko[sl], self.pool.last[sl] = child.boards, child.ko, child.last
+        self.pool.turn[sl], self.pool.libs[sl] = child.turn, child.libs
+        self.child0[i] = lo
+        self.parent[sl], self.move[sl] = i, mv
+        self.turn[sl], self.last[sl] = self.turn[i] + 1, mv
+        self.n += c
+
+    # ---- search -----------------------------------------------------------------------------------------------------------
+    def _select(self, i):
+        lo, c = self.child0[i], self.nchild[i]
+        n = self.N[lo: lo + c]
+        total = max(1, int(n.sum()))
+        avg = np.divide(self.V[lo: lo + c], n, out=np.zeros(c), where=n > 0)
+        p = self.prior[i][self.move[lo: lo + c]].astype(np.float64)
+        score = -avg + self.exploration_weight * p * math.sqrt(total) / (1.0 + n)
+        return lo + int(np.argmax(score))
+
+    def _descend(self):
+        """path from the root to a leaf (mcts.py:172-183); a leaf visited more than expand_thresh times gets its children"""
+        path = [self.root]
+        i = self.root
+        while True:
+            if self.nchild[i] <= 0:
+                if self.nchild[i] < 0 and self.N[i] > self.expand_thresh and not np.isnan(self.val[i]):
+                    self._expand(i)
+                return path
+            i = self._select(i)
+            path.append(i)
+
+    def rollout(self, n=1):
+        """n rollouts; leaf_batch descents share one evaluation batch (virtual loss keeps them apart)"""
+        done = 0
+        while done < n:
+            k = min(self.leaf_batch, n - done)
+            paths = []
+            for _ in range(k):
+                path = self._descend()
+                paths.append(path)
+                if k > 1:
+                    for j in path:                      # virtual loss: as if the descent had been lost for whoever chose it
+                        self.N[j] += 1
+                        self.V[j] += 1.0
+            if k > 1:
+                for path in paths:
+                    for j in path:
+                        self.N[j] -= 1
+                        self.V[j] -= 1.0
+            self._evaluate([p[-1] for p in paths])
+            for path in paths:
+                v = self.val[path[-1]]
+                for j in reversed(path):                # mcts.py:208-217
+                    self.N[j] += 1
+                    self.V[j] += v
+                    v = -v
+            done += k
+
+    def root_visits(self):
+        """visit counts of the root's children as an 81-vector indexed by move"""
+        out = np.zeros(81, np.int64)
+        lo, c = self.child0[self.root], max(0, self.nchild[self.root])
+        out[self.move[lo: lo + c]] = self.N[lo: lo + c]
+        return out
+
+    def best_move(self):
+        lo, c = self.child0[self.root], max(0, self.nchild[self.root])
+        if c == 0:
+            return PASS
+        return int(self.move[lo + int(np.argmax(self.N[lo: lo + c]))])
+
+    def choose(self):
+        """most visited child of the root becomes the new root (mcts.py:110-131); returns its move"""
+        lo, c = self.child0[self.root], max(0, self.nchild[self.root])
+        if c == 0:
+            return PASS
+        best = lo + int(np.argmax(self.N[lo: lo + c]))
+        self.root = best
+        self._evaluate([best])
+        self._expand(best)
+        return int(self.move[best])
+
+    def winrate(self, node=None):
+        """(V/N + 1) / 2 from the perspective of the player to move at the node (mcts.py:159-170)"""
+        i = self.root if node is None else node
+        return (self.V[i] / self.N[i] + 1) / 2 if self.N[i] > 0 else 0

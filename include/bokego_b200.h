@@ -87,6 +87,14 @@ int bk_forward(const void *feats_conv, const void *blob_policy, const void *blob
 int bk_playout_step(int8_t *boards, int16_t *ko, int16_t *last, int16_t *turn, uint8_t *libs,
                     uint8_t *done, const float *probs, const float *q_inj, int q_vecs, uint64_t seed,
                     uint32_t game0, int mode, int max_turn, int16_t *moves_out, int B, void *stream);
+/* Go_MCTS.make_move (bokego/mcts.py:340-346) for C children: child c = copy of parent parent_idx[c] (an index into the
+ * parent arrays) with moves[c] played by Game.play_move (go.py:123-182; -1 = play_pass go.py:109-121).  The lazy liberty
+ * cache is refreshed on the parent position before the move (go.py:160) and handed to the child; libs == NULL means the
+ * parents are fresh Games (exact liberties).  libs_out / status_out may be NULL.  status: 0 ok, 1 ko, 2 not_empty,
+ * 3 suicide (the reference raises IllegalMove; the child is then the unchanged parent). */
+int bk_make_moves(const int8_t *boards, const int16_t *ko, const int16_t *last, const int16_t *turn, const uint8_t *libs,
+                  const int32_t *parent_idx, const int16_t *moves, int8_t *boards_out, int16_t *ko_out, int16_t *last_out,
+                  int16_t *turn_out, uint8_t *libs_out, uint8_t *status_out, int C, void *stream);
 /* Game.score (go.py:202-218) minus komi, and Go_MCTS.reward's +-1 (mcts.py:330-338) */
 int bk_score(const int8_t *boards, float komi, float *score_out, int8_t *reward_out, int B, void *stream);
 /* the counter-based Exp(1) stream itself: q float32 [B][81] for (seed, game0 + b, move, try) */
