@@ -431,7 +431,7 @@ __device__ __forceinline__ void finish_board(const float *logit, int net, const 
 // the tcgen05 kernel
 // ------------------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1)
-bk_forward_tc_kernel(const FwdArgs args, const __grid_constant__ CUtensorMap tm_policy, const __grid_constant__ CUtensorMap tm_value)
+bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant__ CUtensorMap tm_policy, const __grid_constant__ CUtensorMap tm_value)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
