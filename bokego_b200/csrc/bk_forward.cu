@@ -13,8 +13,8 @@
 //     a single-CTA M=128 x N=128 MMA reads 8 KiB of operands per 64 tensor cycles, i.e. it is bound by the
 //     128 B/clk shared-memory port (measured 76 cycles); in the pair each CTA reads its own A rows and only
 //     HALF of B (the weights of 64 output channels), 6 KiB per MMA, and the MMA runs at its 64-cycle floor;
-//   * weights stream L2 -> shared memory in stages of two K steps (4 KiB per CTA, cp.async.bulk + mbarrier,
-//     a 12-slot ring); every stage is used by all tiles of the pass before its slot is recycled;
+//   * weights stream L2 -> shared memory in stages of four K steps (8 KiB per CTA, tensor-map TMA + mbarrier,
+//     a 6-slot ring); every stage is used by all tiles of the pass before its slot is recycled;
 //   * the folded bias enters through the tensor core as well: two extra K rows (bias split into fp16 hi + lo)
 //     multiplied by a constant all-ones operand, so the accumulators leave TMEM ready for ReLU;
 //   * 16 epilogue warps per CTA (one thread per GEMM row: TMEM lane quarter = warp % 4, tile = warp / 4) pull the
@@ -49,32 +49,38 @@ constexpr int F_MARGIN = 24;                       // |5x5 tap shift| <= 24
 constexpr int F_ROWS = F_MARGIN + BK_F_ROWS_G;     // 629
 constexpr int F_LBO = F_ROWS * 16;
 constexpr int F_BYTES = (BK_F_CHUNKS * F_LBO + F_MARGIN * 16 + 127) / 128 * 128;   // 40,704 (+ zero rows behind chunk 3)
-constexpr int CTA_STAGE_BYTES = BK_STAGE_BYTES / 2;   // this CTA's N half of a stage: [2 k-steps][2 k-chunks][64 co][8 k]
+constexpr int CTA_STAGE_BYTES = BK_STAGE_BYTES / 2;   // this CTA's N half of a stage: [4 k-steps][2 k-chunks][64 co][8 k]
 constexpr int CTA_KSTEP_BYTES = BK_KSTEP_BYTES / 2;
-constexpr int N_STAGES = 12;                       // 48 KiB weight ring
+constexpr int CTA_BIAS_BYTES = BK_BIAS_BYTES / 2;  // this CTA's half of a layer's bias rows
+constexpr int N_STAGES = 6;                        // 48 KiB weight ring
 constexpr int ONES_BYTES = 4096;                   // [2 k-chunks][128 rows][8]: 1.0 in k = 0, 1
 constexpr int OFF_A = 0;
 constexpr int OFF_F = OFF_A + A_BYTES;             // F's front margin doubles as the rows behind A's last chunk
 constexpr int OFF_W = OFF_F + F_BYTES;
-constexpr int OFF_ONES = OFF_W + N_STAGES * CTA_STAGE_BYTES;
+constexpr int OFF_BIASW = OFF_W + N_STAGES * CTA_STAGE_BYTES;
+constexpr int OFF_ONES = OFF_BIASW + CTA_BIAS_BYTES;
 constexpr int OFF_BAR = OFF_ONES + ONES_BYTES;     // barriers, 8 B each
-constexpr int OFF_TMEM = OFF_BAR + 384;
+constexpr int OFF_TMEM = OFF_BAR + 192;
 constexpr int OFF_LOGIT = OFF_TMEM + 16;           // float[5][81]: head output per square
-constexpr int SMEM_BYTES = OFF_LOGIT + 1664;       // 230,032
+constexpr int SMEM_BYTES = OFF_LOGIT + 1664;       // 232,016
 static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KiB");
-static_assert(OFF_W % 128 == 0 && OFF_ONES % 128 == 0, "operand alignment");
+static_assert(OFF_W % 128 == 0 && OFF_ONES % 128 == 0 && OFF_BIASW % 128 == 0, "operand alignment");
 
 // WFULL (leader): both CTAs' halves of a stage have landed -- each CTA's tensor-map copy (cta_group::2) reports its
-// bytes to the LEADER's barrier.  WEMPTY: the pair's MMAs that read the stage are complete.  ACC: accumulators of the
-// pass complete.  ACT (leader): both CTAs' epilogues done.  FFULL / PFFULL (leader) / FEMPTY: the same for the
-// feature planes of an item (the peer forwards its FFULL to the leader's PFFULL, once per item).
-enum { BAR_WFULL = 0, BAR_WEMPTY = N_STAGES, BAR_ACC = 2 * N_STAGES, BAR_ACT, BAR_FFULL, BAR_PFFULL, BAR_FEMPTY, N_BARS };
-static_assert(N_BARS * 8 <= 384, "barrier area");
+// bytes to the LEADER's barrier.  WEMPTY: the pair's MMAs that read the stage are complete.  BFULL / BEMPTY: the same for
+// the layer's bias rows (single slot).  ACC: accumulators of the pass complete.  ACT (leader): both CTAs' epilogues done.
+// FFULL / PFFULL (leader) / FEMPTY: the same for the feature planes of an item (the peer forwards its FFULL to the
+// leader's PFFULL, once per item).
+enum { BAR_WFULL = 0, BAR_WEMPTY = N_STAGES, BAR_BFULL = 2 * N_STAGES, BAR_BEMPTY, BAR_ACC, BAR_ACT, BAR_FFULL, BAR_PFFULL,
+       BAR_FEMPTY, N_BARS };
+static_assert(N_BARS * 8 <= 192, "barrier area");
 
-// the conv weights of a blob seen as a 2-D tensor of 512-byte rows (256 fp16); one CTA's half of a stage = 8 rows
+// the conv weights of a blob seen as a 2-D tensor of 512-byte rows (256 fp16): one CTA's half of a stage = 16 rows,
+// its half of the bias rows = 4 rows (a second tensor map with a smaller box)
 constexpr int TM_ROW_BYTES = 512;
-constexpr int TM_BOX_ROWS = CTA_STAGE_BYTES / TM_ROW_BYTES;     // 8
-constexpr int TM_ROWS = BK_W_BIAS_OFF / TM_ROW_BYTES;           // 3912
+constexpr int TM_BOX_ROWS = CTA_STAGE_BYTES / TM_ROW_BYTES;     // 16
+constexpr int TM_BIAS_BOX_ROWS = CTA_BIAS_BYTES / TM_ROW_BYTES; // 4
+constexpr int TM_ROWS = BK_W_BIAS_OFF / TM_ROW_BYTES;           // 3928
 static_assert(BK_W_BIAS_OFF % TM_ROW_BYTES == 0 && BK_L0_BYTES % TM_ROW_BYTES == 0 && BK_L_BYTES % TM_ROW_BYTES == 0, "row grid");
 
 constexpr int N_EPI_WARPS = 16;
@@ -321,7 +327,7 @@ __device__ __forceinline__ Pass pass_info(int nb, int ps)
     }
     return p;
 }
-__device__ __forceinline__ int n_stages_of(int layer) { return (layer == 0 ? BK_L0_FULL_STAGES : BK_L_FULL_STAGES) + 1; }
+__device__ __forceinline__ int n_stages_of(int layer) { return layer == 0 ? BK_L0_STAGES : BK_L_STAGES; }
 
 // layers 1..6: GEMM row r (0..511) -> is it a real square of boards 0..nb-1?  (in place: destination row = r)
 __device__ __forceinline__ bool act_row_valid(int r, int nb, int &board, int &sq)
@@ -431,7 +437,9 @@ __device__ __forceinline__ void finish_board(const float *logit, int net, const 
 // the tcgen05 kernel
 // ------------------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1)
-bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant__ CUtensorMap tm_policy, const __grid_constant__ CUtensorMap tm_value)
+bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant__ CUtensorMap tm_policy,
+                     const __grid_constant__ CUtensorMap tm_value, const __grid_constant__ CUtensorMap tb_policy,
+                     const __grid_constant__ CUtensorMap tb_value)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
@@ -457,6 +465,8 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
             mbar_init(sBar + 8 * (BAR_WFULL + s), 1);
             mbar_init(sBar + 8 * (BAR_WEMPTY + s), 1);
         }
+        mbar_init(sBar + 8 * BAR_BFULL, 1);
+        mbar_init(sBar + 8 * BAR_BEMPTY, 1);
         mbar_init(sBar + 8 * BAR_ACC, 1);
         mbar_init(sBar + 8 * BAR_ACT, 2 * N_EPI_WARPS);
         mbar_init(sBar + 8 * BAR_FFULL, 1);
@@ -489,20 +499,29 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     if (tail) bulk_g2s(dst + n, src + (size_t)c * BK_F_ROWS_G * 16, tail, sBar + 8 * BAR_FFULL);
                 }
             };
-            const uint32_t leader_wfull = mapa(sBar + 8 * BAR_WFULL, 0);
-            auto stream = [&](const CUtensorMap *tm, int layer_off, int n_stages) {   // this CTA's half of every stage of a layer
+            const uint32_t leader_wfull = mapa(sBar + 8 * BAR_WFULL, 0), leader_bfull = mapa(sBar + 8 * BAR_BFULL, 0);
+            uint32_t n_bias = 0;    // bias loads so far (one per pass)
+            // this CTA's half of every stage of one pass over a layer, and of the layer's bias rows.  The bias slot is
+            // refilled a few stages into the pass: by then the previous pass has handed it back, so the wait is free and
+            // the first stages of the pass are prefetched while the previous pass is still running.
+            auto stream = [&](const CUtensorMap *tm, const CUtensorMap *tb, int layer_off, int n_stages) {
                 for (int s = 0; s < n_stages; ++s, ++wit) {
                     const uint32_t st = wit % N_STAGES, ph = (wit / N_STAGES) & 1u;
-                    // the short bias stage is [2 halves][2 KiB]; its copy still moves a whole 8-row box (the extra rows are unused)
-                    const int row = layer_off / TM_ROW_BYTES + s * (BK_STAGE_BYTES / TM_ROW_BYTES) +
-                                    rank * (s == n_stages - 1 ? TM_BOX_ROWS / 2 : TM_BOX_ROWS);
+                    const int row = layer_off / TM_ROW_BYTES + s * (BK_STAGE_BYTES / TM_ROW_BYTES) + rank * TM_BOX_ROWS;
                     mbar_wait(sBar + 8 * (BAR_WEMPTY + st), ph ^ 1u, 0x100u + wit);
                     if ((args.diag & 1) && wit >= N_STAGES) {          // measurement only: skip the copies (wrong results)
                         if (rank == 0) mbar_arrive(sBar + 8 * (BAR_WFULL + st));
-                        continue;
+                    } else {
+                        if (rank == 0) mbar_arrive_expect_tx(sBar + 8 * (BAR_WFULL + st), 2 * CTA_STAGE_BYTES);   // both halves
+                        tma_rows_g2s(sW + st * CTA_STAGE_BYTES, tm, row, leader_wfull + 8 * st);
                     }
-                    if (rank == 0) mbar_arrive_expect_tx(sBar + 8 * (BAR_WFULL + st), 2 * CTA_STAGE_BYTES);   // both halves
-                    tma_rows_g2s(sW + st * CTA_STAGE_BYTES, tm, row, leader_wfull + 8 * st);
+                    if (s == N_STAGES - 1) {
+                        mbar_wait(sBar + 8 * BAR_BEMPTY, (n_bias & 1u) ^ 1u, 0x180u);
+                        if (rank == 0) mbar_arrive_expect_tx(sBar + 8 * BAR_BFULL, 2 * CTA_BIAS_BYTES);
+                        tma_rows_g2s(s_base + OFF_BIASW, tb, (layer_off + n_stages * BK_STAGE_BYTES) / TM_ROW_BYTES + rank * TM_BIAS_BOX_ROWS,
+                                     leader_bfull);
+                        ++n_bias;
+                    }
                 }
             };
             Item it, nx;
@@ -511,14 +530,15 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
             for (int v = pair0; v < args.n_pairs; v += n_clusters) {
                 if (!decode_pair(args, v, rank, it, pair_nb)) continue;
                 const CUtensorMap *tm = it.net == 0 ? &tm_policy : &tm_value;
-                stream(tm, BK_W_L0_OFF, n_stages_of(0));
-                if (pair_nb == BK_GROUP) stream(tm, BK_W_L0_OFF, n_stages_of(0));   // layer 0, second pass (tiles 3, 4)
-                stream(tm, BK_W_L_OFF(1), n_stages_of(1));
+                const CUtensorMap *tb = it.net == 0 ? &tb_policy : &tb_value;
+                stream(tm, tb, BK_W_L0_OFF, n_stages_of(0));
+                if (pair_nb == BK_GROUP) stream(tm, tb, BK_W_L0_OFF, n_stages_of(0));   // layer 0, second pass (tiles 3, 4)
+                stream(tm, tb, BK_W_L_OFF(1), n_stages_of(1));
                 if (v + n_clusters < args.n_pairs && decode_pair(args, v + n_clusters, rank, nx, nx_nb)) {   // prefetch planes
                     mbar_wait(sBar + 8 * BAR_FEMPTY, n_done & 1u, 0x200u);
                     load_feats(nx);
                 }
-                for (int l = 2; l <= 6; ++l) stream(tm, BK_W_L_OFF(l), n_stages_of(l));
+                for (int l = 2; l <= 6; ++l) stream(tm, tb, BK_W_L_OFF(l), n_stages_of(l));
                 ++n_done;
             }
         }
@@ -544,30 +564,34 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         const uint32_t f_lo0 = desc_lo(sF + F_MARGIN * 16, F_LBO);
         const uint32_t one_lo = desc_lo(s_base + OFF_ONES, 2048);
         const uint32_t w_lo0 = desc_lo(sW, 1024);          // B half: [2 k-chunks][64 co][8 k] per K step
+        const uint32_t b_lo0 = desc_lo(s_base + OFF_BIASW, 1024);
         int n_tiles = 0;
-        // one stage: K steps with A windows a0 (and a1), B = the two 2 KiB K steps of ring slot `st` in both CTAs
-        long long tw = 0, tp = 0, ti = 0;                  // diagnostic: cycles waiting for own / peer weights, issuing
+        // one stage: up to four K steps with A windows a[0..nk-1], B = the 2 KiB K steps of ring slot `st` in both CTAs
+        long long tw = 0, tp = 0, ti = 0;                  // diagnostic: cycles waiting for weights / bias rows, issuing
         const bool profiling = args.prof != nullptr && blockIdx.x == 0;
-        auto stage = [&](uint32_t a0, uint32_t a1, bool two, uint32_t row_step, uint32_t accum0) {
-            long long c0 = 0, c1 = 0, c2 = 0;
+        auto stage = [&](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int nk, uint32_t accum0) {
+            long long c0 = 0, c1 = 0;
             if (profiling) c0 = clock64();
             mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x500u + st);
-            if (profiling) { c1 = c2 = clock64(); tw += c1 - c0; tp += 0; }
+            if (profiling) { c1 = clock64(); tw += c1 - c0; }
             tc_fence_after();
             const uint32_t w_lo = w_lo0 + st * (CTA_STAGE_BYTES >> 4);
             if (elect_one()) {
+                const uint32_t aw[4] = {a0, a1, a2, a3};
 #pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    if (t < n_tiles) umma_f16(tmem + (uint32_t)(t * 128), a0 + (uint32_t)t * row_step, w_lo, accum0);
-                if (two) {
+                for (int j = 0; j < 4; ++j) {
+                    if (j < nk) {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        if (t < n_tiles) umma_f16(tmem + (uint32_t)(t * 128), a1 + (uint32_t)t * row_step, w_lo + (CTA_KSTEP_BYTES >> 4), 1u);
+                        for (int t = 0; t < 4; ++t)
+                            if (t < n_tiles)
+                                umma_f16(tmem + (uint32_t)(t * 128), aw[j] + (uint32_t)t * 128u, w_lo + (uint32_t)j * (CTA_KSTEP_BYTES >> 4),
+                                         j == 0 ? accum0 : 1u);
+                    }
                 }
                 umma_commit_pair(sBar + 8 * (BAR_WEMPTY + st));   // stage consumed -> both producers may refill
             }
             __syncwarp();
-            if (profiling) ti += clock64() - c2;
+            if (profiling) ti += clock64() - c1;
             if (++st == N_STAGES) { st = 0; ph ^= 1u; }
         };
         Item it;
@@ -585,24 +609,41 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                 tc_fence_after();
                 if (args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) args.prof[pass * 4 + 0] = clock64();
                 if (pi.layer == 0) {
+                    // stage s = taps 2s, 2s+1; a tap is two K steps (channel chunks 0,1 / 2,3); the last stage holds tap 24 only
                     const uint32_t fb = f_lo0 + (uint32_t)(128 * pi.tile0);
-                    for (int tap = 0; tap < 25; ++tap) {               // K steps 2*tap, 2*tap+1: channel chunks 0,1 / 2,3
-                        const int ti = tap / 5, tj = tap - 5 * ti;
-                        const uint32_t a = fb + (uint32_t)((ti - 2) * 11 + (tj - 2));
-                        stage(a, a + 2u * (F_LBO >> 4), true, 128u, tap != 0);
+                    for (int s2 = 0; s2 < BK_L0_STAGES; ++s2) {
+                        const int t0 = 2 * s2, t1 = 2 * s2 + 1;
+                        const uint32_t a = fb + (uint32_t)((t0 / 5 - 2) * 11 + (t0 % 5 - 2));
+                        const uint32_t c = fb + (uint32_t)((t1 / 5 - 2) * 11 + (t1 % 5 - 2));
+                        stage(a, a + 2u * (F_LBO >> 4), c, c + 2u * (F_LBO >> 4), t1 < 25 ? 4 : 2, s2 != 0);
                     }
                 } else {
-                    for (int tap = 0; tap < 9; ++tap) {                // K steps 8*tap .. 8*tap+7: channel chunks 2j, 2j+1
+                    // stage s = half a tap: K steps with channel chunks (8*part + 2j, +1), j = 0..3
+                    for (int tap = 0; tap < 9; ++tap) {
                         const int ti = tap / 3, tj = tap - 3 * ti;
                         uint32_t a = a_lo0 + (uint32_t)((ti - 1) * 10 + (tj - 1));
                         if (args.diag & 2) a = a_lo0 - 4u;             // measurement only: 128 B aligned windows
 #pragma unroll
-                        for (int part = 0; part < 4; ++part)
-                            stage(a + (uint32_t)(4 * part) * (A_LBO >> 4), a + (uint32_t)(4 * part + 2) * (A_LBO >> 4), true, 128u,
-                                  (tap | part) != 0);
+                        for (int part = 0; part < 2; ++part) {
+                            const uint32_t b = a + (uint32_t)(8 * part) * (A_LBO >> 4);
+                            stage(b, b + 2u * (A_LBO >> 4), b + 4u * (A_LBO >> 4), b + 6u * (A_LBO >> 4), 4, (tap | part) != 0);
+                        }
                     }
                 }
-                stage(one_lo, 0u, false, 0u, 1u);                      // bias rows x the all-ones operand
+                {   // bias rows x the all-ones operand (one K step; every row of the ones operand is the same)
+                    long long c0 = 0;
+                    if (profiling) c0 = clock64();
+                    mbar_wait(sBar + 8 * BAR_BFULL, pass & 1u, 0x5C0u);
+                    if (profiling) tp += clock64() - c0;
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (t < n_tiles) umma_f16(tmem + (uint32_t)(t * 128), one_lo, b_lo0, 1u);
+                        umma_commit_pair(sBar + 8 * BAR_BEMPTY);
+                    }
+                    __syncwarp();
+                }
                 if (elect_one()) {
                     if (pi.l0_last) umma_commit_pair(sBar + 8 * BAR_FEMPTY);   // feature planes no longer needed
                     umma_commit_pair(sBar + 8 * BAR_ACC);                      // accumulators of this pass complete
@@ -830,11 +871,11 @@ extern "C" int bk_weights_pack(const float *w0, const float *w16, const float *b
     for (int co = 0; co < 128; ++co)
         for (int ci = 0; ci < 27; ++ci)
             for (int tap = 0; tap < 25; ++tap) put(l0 + BK_W_OFF(tap * 32 + ci, co), f2h(w0[(co * 27 + ci) * 25 + tap]));
-    // folded bias as two extra K rows (fp16 hi + lo) that meet the all-ones operand, in the short stage behind each layer
+    // folded bias as two extra K rows (fp16 hi + lo) that meet the all-ones operand, behind the stages of each layer
     for (int co = 0; co < 128; ++co) {
         const uint16_t hi = f2h(bias[co]);
-        put(l0 + BK_W_BIAS_ROW_OFF(BK_L0_FULL_STAGES, 0, co), hi);
-        put(l0 + BK_W_BIAS_ROW_OFF(BK_L0_FULL_STAGES, 1, co), f2h(bias[co] - h2f(hi)));
+        put(l0 + BK_W_BIAS_ROW_OFF(BK_L0_STAGES, 0, co), hi);
+        put(l0 + BK_W_BIAS_ROW_OFF(BK_L0_STAGES, 1, co), f2h(bias[co] - h2f(hi)));
     }
     for (int l = 1; l <= 6; ++l) {
         uint8_t *ll = blob + BK_W_L_OFF(l);
@@ -842,8 +883,8 @@ extern "C" int bk_weights_pack(const float *w0, const float *w16, const float *b
         for (int co = 0; co < 128; ++co) {
             const float b = bias[l * 128 + co];
             const uint16_t hi = f2h(b);
-            put(ll + BK_W_BIAS_ROW_OFF(BK_L_FULL_STAGES, 0, co), hi);
-            put(ll + BK_W_BIAS_ROW_OFF(BK_L_FULL_STAGES, 1, co), f2h(b - h2f(hi)));
+            put(ll + BK_W_BIAS_ROW_OFF(BK_L_STAGES, 0, co), hi);
+            put(ll + BK_W_BIAS_ROW_OFF(BK_L_STAGES, 1, co), f2h(b - h2f(hi)));
             for (int ci = 0; ci < 128; ++ci)
                 for (int tap = 0; tap < 9; ++tap)
                     put(ll + BK_W_OFF(tap * 128 + ci, co), f2h(wl[((size_t)co * 128 + ci) * 9 + tap]));
@@ -871,7 +912,7 @@ static unsigned int *g_dbg_host = nullptr;   // pinned, device-visible; survives
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_weight_map(const void *blob, CUtensorMap *out)
+static int make_weight_map(const void *blob, int box_rows, CUtensorMap *out)
 {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -884,7 +925,7 @@ static int make_weight_map(const void *blob, CUtensorMap *out)
     if (!blob) return 0;
     const cuuint64_t dims[2] = {TM_ROW_BYTES / 2, (cuuint64_t)TM_ROWS};
     const cuuint64_t strides[1] = {TM_ROW_BYTES};
-    const cuuint32_t box[2] = {TM_ROW_BYTES / 2, (cuuint32_t)TM_BOX_ROWS};
+    const cuuint32_t box[2] = {TM_ROW_BYTES / 2, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(blob), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -976,15 +1017,17 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
         a.n_pairs = a.n_nets * ((a.n_sub + 1) / 2);
         const int grid = 2 * (a.n_pairs < n_clusters ? a.n_pairs : n_clusters);
         static const void *cached_blob[2] = {nullptr, nullptr};   // the maps depend on the blob addresses only
-        static CUtensorMap cached_map[2];
+        static CUtensorMap cached_map[2], cached_bias_map[2];
         for (int i = 0; i < 2; ++i) {
             if (cached_blob[i] != a.blob[i] || !a.blob[i]) {
-                const int rc = make_weight_map(a.blob[i], &cached_map[i]);
+                int rc = make_weight_map(a.blob[i], TM_BOX_ROWS, &cached_map[i]);
+                if (rc == 0) rc = make_weight_map(a.blob[i], TM_BIAS_BOX_ROWS, &cached_bias_map[i]);
                 if (rc != 0) return rc;
                 cached_blob[i] = a.blob[i];
             }
         }
-        bk_forward_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, stream>>>(a, cached_map[0], cached_map[1]);
+        bk_forward_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, stream>>>(a, cached_map[0], cached_map[1], cached_bias_map[0],
+                                                                     cached_bias_map[1]);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

@@ -17,11 +17,11 @@
  *
  * Weight blob (per net), bytes.  The conv kernel runs on CTA pairs (tcgen05 cta_group::2): the two CTAs share
  * the B operand, each holding the weights of 64 of the 128 output channels ("N half" h = co / 64).
- *     stage   = two K steps (32 K values) = 8 KiB: [2 N-halves][2 k-steps][2 k-chunks][64 co][8 k] fp16,
- *               so the 4 KiB a CTA needs of a stage are contiguous
- *     layer 0 : 25 stages, K = tap*32 + ci (25 taps, ci padded 27->32), then a 4 KiB bias stage
- *     layer l : 36 stages, K = tap*128 + ci (l = 1..6),                 then a 4 KiB bias stage
- *     bias stage = [2 N-halves][2 k-chunks][64 co][8 k]: k = 0, 1 hold the folded bias as fp16 hi + lo; they are
+ *     stage   = four K steps (64 K values) = 16 KiB: [2 N-halves][4 k-steps][2 k-chunks][64 co][8 k] fp16,
+ *               so the 8 KiB a CTA needs of a stage are contiguous
+ *     layer 0 : 13 stages, K = tap*32 + ci (25 taps, ci padded 27->32; the last stage is half empty), then 4 KiB of bias rows
+ *     layer l : 18 stages, K = tap*128 + ci (l = 1..6),                                               then 4 KiB of bias rows
+ *     bias rows = [2 N-halves][2 k-chunks][64 co][8 k]: k = 0, 1 hold the folded bias as fp16 hi + lo; they are
  *               multiplied by an all-ones A operand, so the bias is added by the tensor core
  *     then fp32: bias[7][128] (BatchNorm folded; read by the validation kernel), head_w[128], head_b[96] (81 used),
  *     value tail: {bn_scale, bn_shift, lin2_b, 0}, W1T[81][64] (BN1d folded, transposed), b1[64], w2[64]
@@ -36,20 +36,20 @@
 #define BK_F_GROUP_BYTES (BK_F_CHUNKS * BK_F_ROWS_G * 16)
 
 #define BK_KSTEP_BYTES 4096
-#define BK_STAGE_BYTES 8192
-#define BK_BIAS_STAGE_BYTES 4096
-#define BK_L0_FULL_STAGES 25
-#define BK_L_FULL_STAGES 36
-#define BK_L0_BYTES (BK_L0_FULL_STAGES * BK_STAGE_BYTES + BK_BIAS_STAGE_BYTES) /* 208,896 */
-#define BK_L_BYTES (BK_L_FULL_STAGES * BK_STAGE_BYTES + BK_BIAS_STAGE_BYTES)   /* 299,008 */
+#define BK_STAGE_BYTES 16384
+#define BK_BIAS_BYTES 4096
+#define BK_L0_STAGES 13
+#define BK_L_STAGES 18
+#define BK_L0_BYTES (BK_L0_STAGES * BK_STAGE_BYTES + BK_BIAS_BYTES) /* 217,088 */
+#define BK_L_BYTES (BK_L_STAGES * BK_STAGE_BYTES + BK_BIAS_BYTES)   /* 299,008 */
 #define BK_W_L0_OFF 0
 #define BK_W_L_OFF(l) (BK_L0_BYTES + ((l) - 1) * BK_L_BYTES)
-#define BK_W_BIAS_OFF (BK_L0_BYTES + 6 * BK_L_BYTES) /* 2,002,944 */
-/* byte offset inside a layer of weight (K index k, output channel co); n_full = full stages of the layer */
-#define BK_W_OFF(k, co) ((size_t)((k) >> 5) * BK_STAGE_BYTES + ((co) >> 6) * 4096 + (((k) >> 4) & 1) * 2048 + \
+#define BK_W_BIAS_OFF (BK_L0_BYTES + 6 * BK_L_BYTES) /* 2,011,136 */
+/* byte offset inside a layer of weight (K index k, output channel co) */
+#define BK_W_OFF(k, co) ((size_t)((k) >> 6) * BK_STAGE_BYTES + ((co) >> 6) * 8192 + (((k) >> 4) & 3) * 2048 + \
                          (((k) >> 3) & 1) * 1024 + ((co) & 63) * 16 + ((k) & 7) * 2)
-/* byte offset inside a layer of bias row k (0 = hi, 1 = lo) of output channel co */
-#define BK_W_BIAS_ROW_OFF(n_full, k, co) ((size_t)(n_full) * BK_STAGE_BYTES + ((co) >> 6) * 2048 + ((co) & 63) * 16 + (k) * 2)
+/* byte offset inside a layer of bias row k (0 = hi, 1 = lo) of output channel co; n_stages = stages of the layer */
+#define BK_W_BIAS_ROW_OFF(n_stages, k, co) ((size_t)(n_stages) * BK_STAGE_BYTES + ((co) >> 6) * 2048 + ((co) & 63) * 16 + (k) * 2)
 #define BK_W_HEADW_OFF (BK_W_BIAS_OFF + 7 * 128 * 4)
 #define BK_W_HEADB_OFF (BK_W_HEADW_OFF + 128 * 4)
 #define BK_W_VT_OFF (BK_W_HEADB_OFF + 96 * 4)

@@ -11,8 +11,8 @@ from oracle import nets as onets
 
 GROUP, F_ROWS_B, F_ROWS_G = 5, 121, 605
 A_MARGIN, A_ROWS, F_MARGIN, F_ROWS = 12, 536, 24, 653   # emulation buffers (the kernel overlaps the margins)
-L0_FULL, L_FULL = 25, 36             # full 8 KiB stages (two K steps) per layer; a 4 KiB bias stage follows
-L0_BYTES, L_BYTES = L0_FULL * 8192 + 4096, L_FULL * 8192 + 4096
+L0_FULL, L_FULL = 13, 18             # 16 KiB stages (four K steps) per layer; 4 KiB of bias rows follow
+L0_BYTES, L_BYTES = L0_FULL * 16384 + 4096, L_FULL * 16384 + 4096
 
 
 def _fold(sd):
@@ -42,20 +42,20 @@ def _pack(sd):
 
 def _kstep(blob, layer_off, q):
     """B operand of K step q of a layer as the CTA pair sees it -> float32 [16 k][128 co]:
-    stage q/2 = [2 N-halves][2 k-steps][2 k-chunks][64 co][8 k]; each CTA reads its half with k-chunk stride 1024 B"""
+    stage q/4 = [2 N-halves][4 k-steps][2 k-chunks][64 co][8 k]; each CTA reads its half with k-chunk stride 1024 B"""
     out = np.zeros((16, 128), np.float32)
     for h in range(2):
-        off = layer_off + (q >> 1) * 8192 + h * 4096 + (q & 1) * 2048
+        off = layer_off + (q >> 2) * 16384 + h * 8192 + (q & 3) * 2048
         half = blob[off: off + 2048].view(np.float16).astype(np.float32).reshape(2, 64, 8)   # [k-chunk][co][k8]
         out[:, 64 * h: 64 * h + 64] = half.transpose(0, 2, 1).reshape(16, 64)
     return out
 
 
 def _bias_step(blob, layer_off, n_full):
-    """the 4 KiB bias stage behind a layer's full stages -> float32 [16 k][128 co]"""
+    """the 4 KiB of bias rows behind a layer's stages -> float32 [16 k][128 co]"""
     out = np.zeros((16, 128), np.float32)
     for h in range(2):
-        off = layer_off + n_full * 8192 + h * 2048
+        off = layer_off + n_full * 16384 + h * 2048
         half = blob[off: off + 2048].view(np.float16).astype(np.float32).reshape(2, 64, 8)
         out[:, 64 * h: 64 * h + 64] = half.transpose(0, 2, 1).reshape(16, 64)
     return out
@@ -147,7 +147,7 @@ def test_partial_group_is_isolated(positions, nets_golden, sd17):
 def test_blob_size_and_value_tail(sd_value):
     from bokego_b200 import _lib
     L = _lib.lib()
-    assert L.bk_weights_blob_bytes() == 2028800 and L.bk_feats_conv_bytes(4096) == 820 * 38720
+    assert L.bk_weights_blob_bytes() == 2036992 and L.bk_feats_conv_bytes(4096) == 820 * 38720
     assert L.bk_feats_conv_bytes(1) == 38720 and L.bk_feats_conv_bytes(0) == 0
 
 
