@@ -1,11 +1,11 @@
-// bk_encode.cu -- kernel (a): batched board -> 27 feature planes, one warp per 9x9 board.
+// bk_encode.cu -- kernel (a): batched board -> 27 feature planes, three warps (one thread per square) per 9x9 board.
 //
 // Replaces nnet.features (/root/reference/bokego/nnet.py:182-262) and the go.py routines it calls
 // (get_legal_moves go.py:245-260, get_liberties go.py:220-243, get_caps go.py:404-418).
 // Integer only; bit-exact against the reference in both liberty-cache modes.
 //
-// Work split: the board's two colour sets are built with warp ballots into 81-bit bit-boards that
-// every lane keeps in registers; lane l then owns squares l, l+32, l+64 and evaluates each of them
+// Work split: one block of three warps per board; the board's two colour sets are built with warp ballots into
+// 81-bit bit-boards that every thread keeps in registers; thread t then owns square t and evaluates it
 // on its own (group flood fill by iterated dilation, capture / liberty counts by popcount).  No
 // shared memory, no atomics.  Outputs are optional (null pointer = skip):
 //   feats_conv  fp16 operand layout of the conv kernel: [group of 5 boards][4 channel chunks]
@@ -32,15 +32,16 @@ __device__ __forceinline__ uint32_t half_bits(int n)   // fp16 bit pattern of a 
 
 __device__ __forceinline__ uint32_t pack2(int lo, int hi) { return half_bits(lo) | (half_bits(hi) << 16); }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(96)
 bk_encode_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ ko_arr,
                  const int16_t *__restrict__ last_arr, const int16_t *__restrict__ turn_arr,
                  const uint8_t *__restrict__ libs_in, uint4 *__restrict__ feats_conv,
                  float *__restrict__ feats_f32, uint8_t *__restrict__ planes_u8,
                  uint8_t *__restrict__ legal_out, uint8_t *__restrict__ libs_out, int B, int slots)
 {
-    const int slot = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
+    // one block of three warps per board: warp w owns squares 32w .. 32w+31 (one square per thread)
+    const int slot = (int)blockIdx.x;
+    const int lane = threadIdx.x & 31, wsq = threadIdx.x >> 5;
     if (slot >= slots) return;
 
     uint4 *conv_base = nullptr;
@@ -49,7 +50,7 @@ bk_encode_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ 
         conv_base = feats_conv + (size_t)g * (BK_F_CHUNKS * BK_F_ROWS_G) + bi * BK_F_ROWS_B;
         // zero rows/columns of this board's block (and the whole block for a slot past the batch)
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int r = lane; r < BK_F_ROWS_B; r += 32) {
+        for (int r = threadIdx.x; r < BK_F_ROWS_B; r += 96) {
             const bool pad = r < 22 || ((r - 22) % 11) >= 9 || slot >= B;
             if (pad) {
 #pragma unroll
@@ -81,13 +82,12 @@ bk_encode_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ 
     const BB own = blk ? black : white, opp = blk ? white : black;
     const bool carried = libs_in != nullptr;
     const bool stale = carried && last >= 0 && libs_in[(size_t)b * BK_NSQ + last] == 0;
-    __syncwarp();   // every lane has read libs_in[last]: libs_out may alias libs_in (each lane rewrites only its own squares)
+    __syncthreads();   // every thread has read libs_in[last]: libs_out may alias libs_in (each thread rewrites only its own square)
 
     // ---- per-square evaluation --------------------------------------------------------------------
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int p = lane + 32 * k;
-        if (p >= BK_NSQ) break;
+    {
+        const int p = lane + 32 * wsq;
+        if (p >= BK_NSQ) return;
         const bool mine = bb_test(own, p), theirs = bb_test(opp, p);
         int lib;
         if (carried) lib = bb_lazy_lib_of(black, white, last, stale, p, (int)libs_in[(size_t)b * BK_NSQ + p]);
@@ -193,9 +193,7 @@ extern "C" int bk_encode(const int8_t *boards, const int16_t *ko, const int16_t 
     if (B <= 0) return 0;
     if (!boards || !ko || !last || !turn) return -1;
     const int slots = feats_conv ? ((B + BK_GROUP - 1) / BK_GROUP) * BK_GROUP : B;
-    const int warps_per_block = 4;
-    const int grid = (slots + warps_per_block - 1) / warps_per_block;
-    bk_encode_kernel<<<grid, warps_per_block * 32, 0, stream>>>(boards, ko, last, turn, libs_in, (uint4 *)feats_conv,
+    bk_encode_kernel<<<slots, 96, 0, stream>>>(boards, ko, last, turn, libs_in, (uint4 *)feats_conv,
                                                                  feats_f32, planes_u8, legal_out, libs_out, B, slots);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
