@@ -185,6 +185,26 @@ def cpu_rate(sample, sd17, sdv, seed=1, repeats=1):
     return sample / float(np.mean(ts)), cores, ts
 
 
+def cpu_selfplay_rate(n_games, sd17, sd19, seed=1):
+    """CPU arm of the self-play line: the same 72-move games (policy_17 vs policy_19) through the oracle port --
+    C feature encoder + fp32 torch CPU policy forward + C stepping -- all games of the sample in lock step on all cores"""
+    from oracle import cpu as ocpu
+    from oracle import nets as onets
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    nets = [{k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()} for sd in (sd17, sd19)]
+    bd = np.zeros((n_games, 81), np.int8); ko = np.full(n_games, -1, np.int16); last = np.full(n_games, -2, np.int16)
+    turn = np.zeros(n_games, np.int16); done = np.zeros(n_games, np.uint8); libs = None
+    t0 = time.perf_counter()
+    for k in range(72):
+        f, _, libs = ocpu.features_batch(bd, ko, last, turn, libs)
+        probs = onets.policy_probs(nets[k % 2], onets.planes_to_float(f)).numpy()
+        ocpu.step_batch(bd, ko, last, turn, libs, done, probs, 1, 70, seed=seed, game0=0)
+    ocpu.score_batch(bd)
+    dt = time.perf_counter() - t0
+    return n_games / dt, cores, dt
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -336,6 +356,10 @@ def run_ours(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu:
             rate, cores, ts = cpu_rate(args.cpu_sample, sd17, sdv)
+            if "selfplay" in extra:
+                sp_rate, sp_cores, sp_dt = cpu_selfplay_rate(args.cpu_selfplay_games, sd17, sd19)
+                extra["selfplay"]["cpu_baseline"] = {"value": sp_rate, "unit": "games/s", "cores": sp_cores, "kind": "port",
+                                                     "sample": f"{args.cpu_selfplay_games} games x 72 moves in lock step ({sp_dt:.1f} s)"}
             line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_sample} positions, 1 pass ({ts[0]:.1f} s); C feature oracle (OpenMP) + fp32 torch CPU forward, {cores} threads"}
         line.update(extra)
@@ -356,6 +380,7 @@ def main():
     ap.add_argument("--no-playouts", action="store_true", help="skip the self-play / simulate secondary measurements")
     ap.add_argument("--selfplay-games", type=int, default=4096)
     ap.add_argument("--simulate-boards", type=int, default=65536)
+    ap.add_argument("--cpu-selfplay-games", type=int, default=256)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

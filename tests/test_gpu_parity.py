@@ -205,6 +205,27 @@ def test_forward_full_batch_properties(bk, dev, sd17, sd_value):
     assert float((v.cpu()[sub] - wv).abs().max()) <= TOL_VALUE
 
 
+@pytest.mark.parametrize("n", [148, 370, 739, 740, 741, 1480, 3705, 16384])
+def test_forward_schedule_boundaries(bk, dev, sd17, sd_value, n):
+    """batch sizes around whole rounds of the 74 CTA pairs (74 pairs x 2 groups x 5 boards = 740 boards per net and round) and
+    the BASELINE maximum: the tensor-core kernel, whose work split depends on the batch size, against the CUDA-core kernel,
+    whose work split does not; plus bit-exact agreement of every row with the same position evaluated in a batch of 123"""
+    bd, ko, last, turn = _legal_positions(bk, dev, 123, 7)
+    idx = np.arange(n) % 123
+    pos = _pos(bk, dev, bd[idx], ko[idx], last[idx], turn[idx])
+    conv = bk.features_batch(pos, want=("conv",))["conv"]
+    pol, val = bk.PackedNet(sd17, dev), bk.PackedNet(sd_value, dev)
+    l_t, p_t, v_t = bk.policy_value_batch(conv, n, pol, val)
+    l_s, p_s, v_s = bk.policy_value_batch(conv, n, pol, val, simt=True)
+    torch.cuda.synchronize()
+    assert float((l_t - l_s).abs().max()) < TOL_LOGIT and float((v_t - v_s).abs().max()) < TOL_VALUE
+    assert float((p_t.sum(1) - 1).abs().max()) < 1e-5
+    small = _pos(bk, dev, bd, ko, last, turn)
+    l_0, _, v_0 = bk.policy_value_batch(bk.features_batch(small, want=("conv",))["conv"], 123, pol, val)
+    it = torch.from_numpy(idx).to(dev)
+    assert torch.equal(l_t, l_0[it]) and torch.equal(v_t, v_0[it])
+
+
 def test_exp_stream_bit_identical(bk, dev):
     for seed, g0, mv, tr in ((0, 0, 0, 0), (12345678901234, 77, 13, 5), (2**63 + 5, 4000, 80, 81)):
         q = bk.exp_draws(seed, g0, mv, tr, 6, dev).cpu().numpy()

@@ -29,7 +29,7 @@ def folded(sd):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pass", dest="ps", type=int, default=0)
-    ap.add_argument("--swap", type=int, default=0)
+    ap.add_argument("--swap", type=int, default=0)   # kept for old command lines; ignored
     ap.add_argument("--boards", type=int, default=10)
     a = ap.parse_args()
     g = os.path.join(ROOT, "tests", "golden")
@@ -58,18 +58,18 @@ def main():
     d = dump.cpu().double()
     ws, bs = folded(sd)
     x = torch.from_numpy(P["feats"][src[:5]]).double().reshape(-1, 27, 9, 9)
-    acc = F.conv2d(x, ws[0], None, padding=2)                       # layer-0 accumulators, group 0
+    acc = F.conv2d(x, ws[0], None, padding=2) + bs[0][None, :, None, None]   # layer-0 accumulators incl. the bias rows, group 0
     if a.ps in (0, 1):
         exp = torch.full((640, 128), float("nan"), dtype=torch.float64)
         for b in range(x.shape[0]):
             for p in range(81):
                 exp[121 * b + 22 + 11 * (p // 9) + p % 9] = acc[b, :, p // 9, p % 9]
-        rows = range(0, 512) if a.ps == 0 else range(512, 640)
+        rows = range(0, 384) if a.ps == 0 else range(384, 640)      # layer 0 runs as tiles 0..2, then tiles 3..4
     else:
         h = acc
         for l in range(1, a.ps):                                   # pass ps (>=2) is layer ps-1
-            h = F.relu(h + bs[l - 1][None, :, None, None]).float().half().double()
-            h = F.conv2d(h, ws[l], None, padding=1)
+            h = F.relu(h).float().half().double()
+            h = F.conv2d(h, ws[l], None, padding=1) + bs[l][None, :, None, None]
         exp = torch.full((640, 128), float("nan"), dtype=torch.float64)
         for b in range(x.shape[0]):
             for p in range(81):
