@@ -226,6 +226,27 @@ def test_forward_schedule_boundaries(bk, dev, sd17, sd_value, n):
     assert torch.equal(l_t, l_0[it]) and torch.equal(v_t, v_0[it])
 
 
+@pytest.mark.parametrize("n", [16, 745, 4096])
+def test_forward_is_repeatable_under_cold_and_warm_l2(bk, dev, sd17, n):
+    """protocol stress: back-to-back launches, every other one with the L2 flushed (weights and planes then come from HBM,
+    which shifts every producer / MMA / epilogue hand-over), must give bit-identical results (n = 745 ends in a CTA pair
+    whose second CTA has no boards; 4096 mixes whole items and split ones)"""
+    bd, ko, last, turn = _legal_positions(bk, dev, 123, 11)
+    idx = np.arange(n) % 123
+    pos = _pos(bk, dev, bd[idx], ko[idx], last[idx], turn[idx])
+    conv = bk.features_batch(pos, want=("conv",))["conv"]
+    pol = bk.PackedNet(sd17, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ref_l, _, ref_v = bk.policy_value_batch(conv, n, pol, pol)
+    for it in range(120):
+        if it % 2 == 0:
+            flush.zero_()
+        l, _, v = bk.policy_value_batch(conv, n, pol, pol)
+        assert torch.equal(l, ref_l) and torch.equal(v, ref_v), it
+        l1, _, _ = bk.policy_value_batch(conv, n, pol, None)
+        assert torch.equal(l1, ref_l), it
+
+
 def test_exp_stream_bit_identical(bk, dev):
     for seed, g0, mv, tr in ((0, 0, 0, 0), (12345678901234, 77, 13, 5), (2**63 + 5, 4000, 80, 81)):
         q = bk.exp_draws(seed, g0, mv, tr, 6, dev).cpu().numpy()
