@@ -42,6 +42,17 @@ class PlayoutResult:
         return torch.cat([head, self.moves], dim=1).contiguous()
 
 
+def record_to_sgf(record, out_path, **kwargs):
+    """One game record (a row of PlayoutResult.records(): n_moves, reward, 2*score, moves...) -> an SGF file written by
+    go.write_sgf (the reference's record format, /root/reference/bokego/go.py:538-582; read back by go.get_moves).
+    Moves after the end of the game (BK_MOVE_* codes below PASS) are dropped; the result is B+/W+ from the reward."""
+    from . import go
+    rec = [int(v) for v in record]
+    moves = [m for m in rec[3:] if m >= go.PASS]
+    kwargs.setdefault("result", ("B+" if rec[1] > 0 else "W+") + str(abs(rec[2]) / 2))
+    return go.write_sgf(moves, out_path, **kwargs)
+
+
 def n_steps_for(mode, max_turn, first_turn=0):
     """number of move steps after which every board of the batch is finished"""
     last = max_turn + (1 if mode == MODE_MCTS else 2)

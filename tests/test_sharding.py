@@ -66,3 +66,20 @@ def test_two_rank_gather_equals_single_rank(tmp_path):
 def test_gather_is_identity_for_one_rank():
     t = torch.arange(12, dtype=torch.int16).reshape(4, 3)
     assert gather_records(t, 4, 0, 1) is t
+
+
+def test_record_round_trips_through_sgf(tmp_path):
+    """a game record written with the reference's SGF layout reads back move for move"""
+    from bokego_b200 import go
+    from bokego_b200.playout import record_to_sgf
+    rec = _oracle_games(3, 4, seed=99, steps=20)[0]
+    path = str(tmp_path / "g.sgf")
+    sgf = record_to_sgf(rec, path, B="policy_17", W="policy_19")
+    moves = [int(m) for m in rec[3:] if m >= -1]
+    assert go.get_moves(path) == moves and len(moves) == 20
+    assert "PB[policy_17]PW[policy_19]" in sgf and ("RE[B+" in sgf or "RE[W+" in sgf)
+    g = go.Game(sgf=path)                       # like the reference, Game(sgf=...) loads the move list ...
+    assert g.moves == moves and len(g) == 20
+    for m in g.moves:                           # ... and the moves replay legally
+        g.play_move(m)
+    assert g.turn == 20
