@@ -340,3 +340,82 @@ BK_HD float bk_exp_draw(uint64_t seed, uint32_t game, uint32_t move, uint32_t tr
     bk_philox(seed, game, move, tr, (uint32_t)(i >> 2), r);
     return bk_exp_from_bits(r[i & 3]);
 }
+
+// ---- group table of one board (shared memory of a block of 96 threads, thread t = square t) -----------------------
+// Every stone floods its own group once; the group's lowest square is its id and publishes the group's stones and
+// liberties.  "What if the side to move puts a stone on the empty square s" (bb_candidate) then needs no flood at all:
+// the <= 4 neighbouring groups are looked up.  Device only.
+#if defined(__CUDACC__)
+struct BKGroups {
+    uint32_t stones[BK_NSQ][3];
+    uint32_t libs[BK_NSQ][3];
+    uint8_t root[BK_NSQ];
+};
+
+// call with all threads of the block (p = square of this thread, p >= 81 for the idle ones), then __syncthreads()
+__device__ __forceinline__ void bk_groups_build(BKGroups &g, BB black, BB white, int p)
+{
+    if (p >= BK_NSQ) return;
+    const bool pb = bb_test(black, p), pw = bb_test(white, p);
+    if (!pb && !pw) return;
+    BB all; all.w[0] = BK_M27; all.w[1] = BK_M27; all.w[2] = BK_M27;
+    const BB empty = bb_andn(bb_andn(all, black), white);
+    const BB grp = bb_flood(bb_bit(p), pb ? black : white);
+    const int r = bb_first(grp);
+    g.root[p] = (uint8_t)r;
+    if (r == p) {
+        const BB l = bb_libs(grp, empty);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { g.stones[p][k] = grp.w[k]; g.libs[p][k] = l.w[k]; }
+    }
+}
+__device__ __forceinline__ BB bk_group_stones(const BKGroups &g, int q)
+{
+    const int r = g.root[q];
+    BB b; b.w[0] = g.stones[r][0]; b.w[1] = g.stones[r][1]; b.w[2] = g.stones[r][2];
+    return b;
+}
+__device__ __forceinline__ BB bk_group_libs(const BKGroups &g, int q)
+{
+    const int r = g.root[q];
+    BB b; b.w[0] = g.libs[r][0]; b.w[1] = g.libs[r][1]; b.w[2] = g.libs[r][2];
+    return b;
+}
+// bb_candidate(own, opp, s, ...) from the table; `dead` receives the captured stones
+__device__ __forceinline__ Cand bk_groups_candidate(const BKGroups &g, BB own, BB opp, int s, BB *dead_out)
+{
+    BB all; all.w[0] = BK_M27; all.w[1] = BK_M27; all.w[2] = BK_M27;
+    const BB sb = bb_bit(s);
+    const BB empty_after = bb_andn(bb_andn(bb_andn(all, own), opp), sb);
+    BB dead = bb_zero(), merged = sb;
+    Cand c; c.caps = 0; c.single_cap = -1;
+    int nb[4];
+    const int nn = bb_nbr_list(s, nb);
+    for (int k = 0; k < nn; ++k) {
+        const int q = nb[k];
+        const bool qo = bb_test(opp, q), qm = bb_test(own, q);
+        if (!qo && !qm) continue;
+        const BB grp = bk_group_stones(g, q);
+        if (qm) { merged = bb_or(merged, grp); continue; }
+        if (!bb_any(bb_and(bk_group_libs(g, q), empty_after))) {          // its only liberty was s
+            const int n = bb_count(grp);
+            if (c.caps == 0 && n == 1) c.single_cap = q;
+            c.caps += n;
+            dead = bb_or(dead, grp);
+        }
+    }
+    if (c.caps != 1) c.single_cap = -1;
+    c.libs_after = bb_count(bb_libs(merged, bb_or(empty_after, dead)));
+    if (dead_out) *dead_out = dead;
+    return c;
+}
+// the lazy liberty cache for the stone / empty square p (bb_lazy_lib_of) from the table
+__device__ __forceinline__ int bk_groups_lazy_lib(const BKGroups &g, BB black, BB white, int last, bool last_stale, int p, int carried)
+{
+    if (!last_stale) return carried;
+    if (!bb_test(black, p) && !bb_test(white, p)) return carried;
+    const BB seeds = bb_or(bb_neighbours(bb_bit(last)), bb_bit(last));
+    if (!bb_any(bb_and(bk_group_stones(g, p), seeds))) return carried;
+    return bb_count(bk_group_libs(g, p));
+}
+#endif

@@ -88,23 +88,11 @@ bk_encode_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ 
     // ---- group table of the board (shared by the block): every stone floods its own group once; the group's lowest
     //      square is its id and publishes the group's stones and liberties.  Empty squares then evaluate "what if a stone
     //      is put here" from their <= 4 neighbouring groups by look-up instead of flooding up to five groups each. --------
-    __shared__ uint32_t g_stones[BK_NSQ][3], g_libs[BK_NSQ][3];
-    __shared__ uint8_t g_root[BK_NSQ];
+    __shared__ BKGroups grp;
     const int p = lane + 32 * wsq;
     const bool active = p < BK_NSQ;
     const bool mine = active && bb_test(own, p), theirs = active && bb_test(opp, p);
-    BB all; all.w[0] = BK_M27; all.w[1] = BK_M27; all.w[2] = BK_M27;
-    const BB empty = bb_andn(bb_andn(all, own), opp);
-    if (mine || theirs) {
-        const BB g = bb_flood(bb_bit(p), mine ? own : opp);
-        const int r = bb_first(g);
-        g_root[p] = (uint8_t)r;
-        if (r == p) {
-            const BB l = bb_libs(g, empty);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { g_stones[p][k] = g.w[k]; g_libs[p][k] = l.w[k]; }
-        }
-    }
+    bk_groups_build(grp, black, white, p);
     __syncthreads();   // the table is complete; also: every thread has read libs_in[last], so libs_out may alias libs_in
     if (!active) return;
 
@@ -112,52 +100,17 @@ bk_encode_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ 
     {
         int lib = 0;
         if (mine || theirs) {
-            const int r = g_root[p];
-            BB g, l;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { g.w[k] = g_stones[r][k]; l.w[k] = g_libs[r][k]; }
-            if (!carried) {
-                lib = bb_count(l);                                           // fresh Game: exact liberties
-            } else {
-                lib = (int)libs_in[(size_t)b * BK_NSQ + p];                  // lazy cache (go.py:220-243)
-                if (stale) {
-                    const BB seeds = bb_or(bb_neighbours(bb_bit(last)), bb_bit(last));
-                    if (bb_any(bb_and(g, seeds))) lib = bb_count(l);
-                }
-            }
+            if (!carried) lib = bb_count(bk_group_libs(grp, p));            // fresh Game: exact liberties
+            else lib = bk_groups_lazy_lib(grp, black, white, last, stale, p, (int)libs_in[(size_t)b * BK_NSQ + p]);
         } else if (carried) {
-            lib = (int)libs_in[(size_t)b * BK_NSQ + p];                      // stale values persist on empty squares
+            lib = (int)libs_in[(size_t)b * BK_NSQ + p];                      // stale values persist on empty squares (go.py:220-243)
         }
         int la = 0, cp = 0;
         bool lg = false;
         if (!mine && !theirs) {
             // the move "own stone on p" (nnet.py:241-247, go.py:404-418): a dead opponent group is counted once per
             // neighbour of p that belongs to it; liberties of the merged own group after the removal
-            const BB pb = bb_bit(p);
-            const BB empty_after = bb_andn(empty, pb);
-            BB dead = bb_zero(), merged = pb;
-            Cand c; c.caps = 0; c.single_cap = -1;
-            int nb[4];
-            const int nn = bb_nbr_list(p, nb);
-            for (int k = 0; k < nn; ++k) {
-                const int q = nb[k];
-                const bool qo = bb_test(opp, q), qm = bb_test(own, q);
-                if (!qo && !qm) continue;
-                const int r = g_root[q];
-                BB g;
-                g.w[0] = g_stones[r][0]; g.w[1] = g_stones[r][1]; g.w[2] = g_stones[r][2];
-                if (qm) { merged = bb_or(merged, g); continue; }
-                BB l;
-                l.w[0] = g_libs[r][0]; l.w[1] = g_libs[r][1]; l.w[2] = g_libs[r][2];
-                if (!bb_any(bb_and(l, empty_after))) {                       // its only liberty was p
-                    const int n = bb_count(g);
-                    if (c.caps == 0 && n == 1) c.single_cap = q;
-                    c.caps += n;
-                    dead = bb_or(dead, g);
-                }
-            }
-            if (c.caps != 1) c.single_cap = -1;
-            c.libs_after = bb_count(bb_libs(merged, bb_or(empty_after, dead)));
+            const Cand c = bk_groups_candidate(grp, own, opp, p, nullptr);
             lg = bb_listed_legal(own, opp, ko, p, c);
             if (lg) { la = c.libs_after; cp = c.caps; }
         }

@@ -1,6 +1,6 @@
 // bk_step.cu -- kernel (c): batched playout stepping, scoring, and the shared random stream.
 //
-//   bk_step_kernel   one warp per board: pick a move from the policy's probabilities and play it.
+//   bk_step_kernel   three warps per board (thread = square): pick a move from the policy's probabilities and play it.
 //       mode 0 (mcts flavour)      Go_MCTS.get_move + make_move + is_game_over
 //                                  (/root/reference/bokego/mcts.py:340-364): exponential-race sample,
 //                                  reject illegal moves and own-eye fills by zeroing their probability and
@@ -52,17 +52,38 @@ __device__ __forceinline__ void warp_argmax(float &v, int &i)
     }
 }
 
-__global__ void __launch_bounds__(128)
+// block-wide (max value, lowest index): warp shuffles, then the three warps' candidates through shared memory
+__device__ __forceinline__ void block_argmax(float &v, int &i, float *sv, int *si, int wsq, int lane)
+{
+    warp_argmax(v, i);
+    __syncthreads();                       // the previous round's readers are done with sv / si
+    if (lane == 0) { sv[wsq] = v; si[wsq] = i; }
+    __syncthreads();
+    v = sv[0]; i = si[0];
+#pragma unroll
+    for (int w = 1; w < 3; ++w)
+        if (sv[w] > v || (sv[w] == v && si[w] < i)) { v = sv[w]; i = si[w]; }
+}
+
+// One block of three warps per board, thread t = square t (as in bk_encode_kernel); the group table answers every
+// "what if a stone is put here" question by look-up.
+__global__ void __launch_bounds__(96)
 bk_step_kernel(int8_t *__restrict__ boards, int16_t *__restrict__ ko_arr, int16_t *__restrict__ last_arr,
                int16_t *__restrict__ turn_arr, uint8_t *__restrict__ libs, uint8_t *__restrict__ done,
                const float *__restrict__ probs, const float *__restrict__ q_inj, int q_vecs, uint64_t seed,
                uint32_t game0, int mode, int max_turn, int16_t *__restrict__ moves_out, int B)
 {
-    const int b = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
+    __shared__ BKGroups grp;
+    __shared__ float s_v[3];
+    __shared__ int s_i[3];
+    __shared__ uint8_t s_ok[BK_NSQ + 15];
+    const int b = (int)blockIdx.x;
+    const int lane = threadIdx.x & 31, wsq = threadIdx.x >> 5;
+    const int p = threadIdx.x;                       // this thread's square (81..95 idle)
+    const bool active = p < BK_NSQ;
     if (b >= B) return;
     if (done[b]) {
-        if (lane == 0 && moves_out) moves_out[b] = -3;
+        if (threadIdx.x == 0 && moves_out) moves_out[b] = -3;
         return;
     }
     int8_t *bd = boards + (size_t)b * BK_NSQ;
@@ -72,103 +93,106 @@ bk_step_kernel(int8_t *__restrict__ boards, int16_t *__restrict__ ko_arr, int16_
     const bool blk = (turn & 1) == 0;
     const BB own = blk ? black : white, opp = blk ? white : black;
     const int me = blk ? 1 : -1;
+    bk_groups_build(grp, black, white, p);
+    const bool stale = libs && last >= 0 && libs[(size_t)b * BK_NSQ + last] == 0;
+    __syncthreads();
 
-    // per-square probability and accept mask (bit k = square lane + 32k)
-    float pr[3];
-    uint32_t ok_mask = 0u;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int p = lane + 32 * k;
-        pr[k] = 0.0f;
-        if (p < BK_NSQ) {
-            pr[k] = probs[(size_t)b * BK_NSQ + p];
-            bool ok = bb_is_legal_quirk(own, opp, ko, p);
+    // probability and accept flag of this thread's square: Game.is_legal (go.py:184-200, early exit kept) and, in the
+    // mcts flavour, not an own eye (mcts.py:354)
+    float pr = 0.0f;
+    bool ok = false;
+    if (active) {
+        pr = probs[(size_t)b * BK_NSQ + p];
+        if (!bb_test(own, p) && !bb_test(opp, p)) {
+            int nb[4];
+            const int n = bb_nbr_list(p, nb);
+            const BB occ = bb_or(own, opp);
+            int empties = 0;
+            bool early = false;
+            for (int k = 0; k < n; ++k) {
+                if (empties > 1) { early = true; break; }
+                if (!bb_test(occ, nb[k])) ++empties;
+            }
+            ok = early || (p != ko && bk_groups_candidate(grp, own, opp, p, nullptr).libs_after > 0);
             if (mode == 0 && ok) ok = bb_possible_eye(black, white, p) != me;
-            if (ok) ok_mask |= 1u << k;
         }
+        s_ok[p] = ok;
     }
+    __syncthreads();
 
     int mv = BK_NONE;
     int t = 0;
     for (;;) {
         if (t > 0) {
-            const bool mass = pr[0] > 0.0f || pr[1] > 0.0f || pr[2] > 0.0f;
-            if (!__any_sync(0xffffffffu, mass)) { mv = BK_PASS; break; }
+            if (!__syncthreads_or(pr > 0.0f)) { mv = BK_PASS; break; }
             if (q_inj && t >= q_vecs) { mv = -4; break; }
         }
         float bv = -1.0f;
         int bi = 0x7fffffff;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int p = lane + 32 * k;
-            if (p < BK_NSQ) {
-                const float q = q_inj ? q_inj[((size_t)b * q_vecs + t) * BK_NSQ + p]
-                                      : bk_exp_draw(seed, game0 + (uint32_t)b, (uint32_t)turn, (uint32_t)t, p);
-                const float v = __fdiv_rn(pr[k], q);
-                if (v > bv) { bv = v; bi = p; }
-            }
+        if (active) {
+            const float q = q_inj ? q_inj[((size_t)b * q_vecs + t) * BK_NSQ + p]
+                                  : bk_exp_draw(seed, game0 + (uint32_t)b, (uint32_t)turn, (uint32_t)t, p);
+            bv = __fdiv_rn(pr, q);
+            bi = p;
         }
-        warp_argmax(bv, bi);
+        block_argmax(bv, bi, s_v, s_i, wsq, lane);
         ++t;
-        const int owner = bi & 31, slot = bi >> 5;
-        const bool accept = (__shfl_sync(0xffffffffu, ok_mask, owner) >> slot) & 1u;
+        const bool accept = s_ok[bi] != 0;
         if (mode == 1) {
             if (accept) { mv = bi; break; }
             // highest-probability legal move, lowest index on ties
-            float fv = -1.0f;
-            int fi = 0x7fffffff;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int p = lane + 32 * k;
-                if (p < BK_NSQ && ((ok_mask >> k) & 1u) && pr[k] > fv) { fv = pr[k]; fi = p; }
-            }
-            warp_argmax(fv, fi);
+            float fv = (active && ok) ? pr : -1.0f;
+            int fi = (active && ok) ? p : 0x7fffffff;
+            block_argmax(fv, fi, s_v, s_i, wsq, lane);
             mv = fi == 0x7fffffff ? BK_NONE : fi;
             break;
         }
         if (accept) { mv = bi; break; }
         if (t - 1 >= BK_NSQ) { mv = BK_PASS; break; }   // tries >= 81 (mcts.py:354)
-        if (lane == owner) {
-            if (slot == 0) pr[0] = 0.0f; else if (slot == 1) pr[1] = 0.0f; else pr[2] = 0.0f;
-        }
+        if (p == bi) pr = 0.0f;
     }
 
-    if (lane == 0 && moves_out) moves_out[b] = (int16_t)mv;
+    if (threadIdx.x == 0 && moves_out) moves_out[b] = (int16_t)mv;
     if (mv == BK_NONE || mv == -4) {
-        if (lane == 0) done[b] = 1;
+        if (threadIdx.x == 0) done[b] = 1;
         return;
     }
 
     // lazy liberty cache on the position BEFORE the move (go.py:160); a PASS does not touch it
-    if (libs && mv >= 0) {
+    if (libs && mv >= 0 && active) {
         uint8_t *lb = libs + (size_t)b * BK_NSQ;
-        const bool stale = last >= 0 && lb[last] == 0;
-        __syncwarp();
-        int nl[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int p = lane + 32 * k;
-            nl[k] = p < BK_NSQ ? bb_lazy_lib_of(black, white, last, stale, p, (int)lb[p]) : 0;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int p = lane + 32 * k;
-            if (p < BK_NSQ) lb[p] = (uint8_t)nl[k];
-        }
+        lb[p] = (uint8_t)bk_groups_lazy_lib(grp, black, white, last, stale, p, (int)lb[p]);   // `stale` was read before the barrier
     }
 
-    const int st = bb_play(black, white, ko, last, turn, mv);
+    // Game.play_move (go.py:123-182) from the table: every thread derives the same outcome
+    int st = 0;
+    if (mv == BK_PASS) {
+        turn += 1; ko = -1; last = BK_PASS;
+    } else if (mv == ko) {
+        st = 1;
+    } else if (bb_test(black, mv) || bb_test(white, mv)) {
+        st = 2;
+    } else {
+        const int pk = bb_possible_ko(black, white, mv);
+        BB dead;
+        const Cand c = bk_groups_candidate(grp, own, opp, mv, &dead);
+        if (c.libs_after == 0) {
+            st = 3;
+        } else {
+            ko = (c.caps == 1 && pk == (blk ? -1 : 1)) ? c.single_cap : -1;
+            const BB own2 = bb_or(own, bb_bit(mv)), opp2 = bb_andn(opp, dead);
+            black = blk ? own2 : opp2;
+            white = blk ? opp2 : own2;
+            last = mv;
+            turn += 1;
+        }
+    }
     if (st != 0) {   // cannot happen for a position reached by legal play; flag instead of corrupting state
-        if (lane == 0) { done[b] = 1; if (moves_out) moves_out[b] = (int16_t)(-10 - st); }
+        if (threadIdx.x == 0) { done[b] = 1; if (moves_out) moves_out[b] = (int16_t)(-10 - st); }
         return;
     }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int p = lane + 32 * k;
-        if (p < BK_NSQ) bd[p] = bb_test(black, p) ? 1 : (bb_test(white, p) ? -1 : 0);
-    }
-    if (lane == 0) {
+    if (active) bd[p] = bb_test(black, p) ? 1 : (bb_test(white, p) ? -1 : 0);
+    if (threadIdx.x == 0) {
         ko_arr[b] = (int16_t)ko; last_arr[b] = (int16_t)last; turn_arr[b] = (int16_t)turn;
         const bool over = mode == 0 ? (turn > max_turn || last == BK_PASS) : (turn > max_turn + 1);
         if (over) done[b] = 1;
@@ -253,7 +277,7 @@ extern "C" int bk_playout_step(int8_t *boards, int16_t *ko, int16_t *last, int16
                               int max_turn, int16_t *moves_out, int B, cudaStream_t stream)
 {
     if (B <= 0) return 0;
-    bk_step_kernel<<<(B + 3) / 4, 128, 0, stream>>>(boards, ko, last, turn, libs, done, probs, q_inj, q_vecs, seed, game0,
+    bk_step_kernel<<<B, 96, 0, stream>>>(boards, ko, last, turn, libs, done, probs, q_inj, q_vecs, seed, game0,
                                                     mode, max_turn, moves_out, B);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
