@@ -68,12 +68,11 @@ static_assert(OFF_W % 128 == 0 && OFF_ONES % 128 == 0 && OFF_BIASW % 128 == 0, "
 
 // WFULL (leader): both CTAs' halves of a stage have landed -- each CTA's tensor-map copy (cta_group::2) reports its
 // bytes to the LEADER's barrier.  WEMPTY: the pair's MMAs that read the stage are complete.  BFULL / BEMPTY: the same for
-// the layer's bias rows (single slot).  ACC[t]: accumulator tile t of the pass complete (the last stages of a pass are
-// issued tile by tile, so the epilogue of the first tiles overlaps the MMAs of the last).  ACT (leader): both CTAs' epilogues done.
+// the layer's bias rows (single slot).  ACC: accumulators of the pass complete.  ACT (leader): both CTAs' epilogues done.
 // FFULL / PFFULL (leader) / FEMPTY: the same for the feature planes of an item (the peer forwards its FFULL to the
 // leader's PFFULL, once per item).
-enum { BAR_WFULL = 0, BAR_WEMPTY = N_STAGES, BAR_BFULL = 2 * N_STAGES, BAR_BEMPTY, BAR_ACC, BAR_ACT = BAR_ACC + 4, BAR_FFULL,
-       BAR_PFFULL, BAR_FEMPTY, N_BARS };
+enum { BAR_WFULL = 0, BAR_WEMPTY = N_STAGES, BAR_BFULL = 2 * N_STAGES, BAR_BEMPTY, BAR_ACC, BAR_ACT, BAR_FFULL, BAR_PFFULL,
+       BAR_FEMPTY, N_BARS };
 static_assert(N_BARS * 8 <= 192, "barrier area");
 
 // the conv weights of a blob seen as a 2-D tensor of 512-byte rows (256 fp16): one CTA's half of a stage = 16 rows,
@@ -468,7 +467,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         }
         mbar_init(sBar + 8 * BAR_BFULL, 1);
         mbar_init(sBar + 8 * BAR_BEMPTY, 1);
-        for (int t = 0; t < 4; ++t) mbar_init(sBar + 8 * (BAR_ACC + t), 1);
+        mbar_init(sBar + 8 * BAR_ACC, 1);
         mbar_init(sBar + 8 * BAR_ACT, 2 * N_EPI_WARPS);
         mbar_init(sBar + 8 * BAR_FFULL, 1);
         mbar_init(sBar + 8 * BAR_PFFULL, 1);
@@ -567,42 +566,33 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         const uint32_t w_lo0 = desc_lo(sW, 1024);          // B half: [2 k-chunks][64 co][8 k] per K step
         const uint32_t b_lo0 = desc_lo(s_base + OFF_BIASW, 1024);
         int n_tiles = 0;
+        // one stage: up to four K steps with A windows a[0..nk-1], B = the 2 KiB K steps of ring slot `st` in both CTAs
         long long tw = 0, tp = 0, ti = 0;                  // diagnostic: cycles waiting for weights / bias rows, issuing
         const bool profiling = args.prof != nullptr && blockIdx.x == 0;
-        constexpr int TAIL = 3;                            // stages at the end of a pass that are issued tile by tile
-        // A windows (descriptor words of tile 0) of the up to four K steps of stage s of a pass
-        auto windows = [&](const Pass &pi, int s, uint32_t (&a)[4], int &nk) {
-            if (pi.layer == 0) {       // stage s = taps 2s, 2s+1; a tap is two K steps (channel chunks 0,1 / 2,3); stage 12 holds tap 24 only
-                const uint32_t fb = f_lo0 + (uint32_t)(128 * pi.tile0);
-                const int t0 = 2 * s, t1 = 2 * s + 1;
-                a[0] = fb + (uint32_t)((t0 / 5 - 2) * 11 + (t0 % 5 - 2));
-                a[1] = a[0] + 2u * (F_LBO >> 4);
-                a[2] = fb + (uint32_t)((t1 / 5 - 2) * 11 + (t1 % 5 - 2));
-                a[3] = a[2] + 2u * (F_LBO >> 4);
-                nk = t1 < 25 ? 4 : 2;
-            } else {                   // stage s = half a tap: K steps with channel chunks (8*part + 2j, +1), j = 0..3
-                const int tap = s >> 1, part = s & 1;
-                const int ti = tap / 3, tj = tap - 3 * ti;
-                uint32_t b = a_lo0 + (uint32_t)((ti - 1) * 10 + (tj - 1)) + (uint32_t)(8 * part) * (A_LBO >> 4);
-                if (args.diag & 2) b = a_lo0 - 4u + (uint32_t)(8 * part) * (A_LBO >> 4);   // measurement only: 128 B aligned windows
+        auto stage = [&](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int nk, uint32_t accum0) {
+            long long c0 = 0, c1 = 0;
+            if (profiling) c0 = clock64();
+            mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x500u + st);
+            if (profiling) { c1 = clock64(); tw += c1 - c0; }
+            tc_fence_after();
+            const uint32_t w_lo = w_lo0 + st * (CTA_STAGE_BYTES >> 4);
+            if (elect_one()) {
+                const uint32_t aw[4] = {a0, a1, a2, a3};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) a[j] = b + (uint32_t)(2 * j) * (A_LBO >> 4);
-                nk = 4;
-            }
-        };
-        // the K steps of one stage for tiles [t_lo, t_hi): B = the 2 KiB K steps of ring slot `slot` in both CTAs
-        auto issue = [&](const uint32_t (&a)[4], int nk, uint32_t slot, int t_lo, int t_hi, uint32_t accum0) {
-            const uint32_t w_lo = w_lo0 + slot * (CTA_STAGE_BYTES >> 4);
+                for (int j = 0; j < 4; ++j) {
+                    if (j < nk) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j < nk) {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        if (t >= t_lo && t < t_hi)
-                            umma_f16(tmem + (uint32_t)(t * 128), a[j] + (uint32_t)t * 128u, w_lo + (uint32_t)j * (CTA_KSTEP_BYTES >> 4),
-                                     j == 0 ? accum0 : 1u);
+                        for (int t = 0; t < 4; ++t)
+                            if (t < n_tiles)
+                                umma_f16(tmem + (uint32_t)(t * 128), aw[j] + (uint32_t)t * 128u, w_lo + (uint32_t)j * (CTA_KSTEP_BYTES >> 4),
+                                         j == 0 ? accum0 : 1u);
+                    }
                 }
+                umma_commit_pair(sBar + 8 * (BAR_WEMPTY + st));   // stage consumed -> both producers may refill
             }
+            __syncwarp();
+            if (profiling) ti += clock64() - c1;
+            if (++st == N_STAGES) { st = 0; ph ^= 1u; }
         };
         Item it;
         int pair_nb;
@@ -615,63 +605,50 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
             for (int ps = 0; ps < np; ++ps, ++pass) {
                 const Pass pi = pass_info(pair_nb, ps);
                 n_tiles = pi.n_tiles;
-                const int S = n_stages_of(pi.layer);
                 if (pass > 0) mbar_wait(sBar + 8 * BAR_ACT, (pass - 1) & 1u, 0x400u + pass);   // operands written, TMEM drained
                 tc_fence_after();
                 if (args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) args.prof[pass * 4 + 0] = clock64();
-                // ---- all but the last TAIL stages: stage by stage, every tile uses the stage before its slot is recycled
-                for (int s2 = 0; s2 < S - TAIL; ++s2) {
-                    long long c0 = 0, c1 = 0;
-                    if (profiling) c0 = clock64();
-                    mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x500u + st);
-                    if (profiling) { c1 = clock64(); tw += c1 - c0; }
-                    tc_fence_after();
-                    uint32_t a[4];
-                    int nk;
-                    windows(pi, s2, a, nk);
-                    if (elect_one()) {
-                        issue(a, nk, st, 0, n_tiles, s2 != 0);
-                        umma_commit_pair(sBar + 8 * (BAR_WEMPTY + st));   // stage consumed -> both producers may refill
+                if (pi.layer == 0) {
+                    // stage s = taps 2s, 2s+1; a tap is two K steps (channel chunks 0,1 / 2,3); the last stage holds tap 24 only
+                    const uint32_t fb = f_lo0 + (uint32_t)(128 * pi.tile0);
+                    for (int s2 = 0; s2 < BK_L0_STAGES; ++s2) {
+                        const int t0 = 2 * s2, t1 = 2 * s2 + 1;
+                        const uint32_t a = fb + (uint32_t)((t0 / 5 - 2) * 11 + (t0 % 5 - 2));
+                        const uint32_t c = fb + (uint32_t)((t1 / 5 - 2) * 11 + (t1 % 5 - 2));
+                        stage(a, a + 2u * (F_LBO >> 4), c, c + 2u * (F_LBO >> 4), t1 < 25 ? 4 : 2, s2 != 0);
                     }
-                    __syncwarp();
-                    if (profiling) ti += clock64() - c1;
-                    if (++st == N_STAGES) { st = 0; ph ^= 1u; }
-                }
-                // ---- the last TAIL stages and the bias rows: tile by tile, so that tile t is complete (ACC[t]) while the
-                //      tiles behind it are still running and its epilogue overlaps their MMAs
-                {
-                    long long c0 = 0, c1 = 0;
-                    if (profiling) c0 = clock64();
-                    uint32_t slot[TAIL], a[TAIL][4];
-                    int nk[TAIL];
+                } else {
+                    // stage s = half a tap: K steps with channel chunks (8*part + 2j, +1), j = 0..3
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ti = tap / 3, tj = tap - 3 * ti;
+                        uint32_t a = a_lo0 + (uint32_t)((ti - 1) * 10 + (tj - 1));
+                        if (args.diag & 2) a = a_lo0 - 4u;             // measurement only: 128 B aligned windows
 #pragma unroll
-                    for (int r = 0; r < TAIL; ++r) {
-                        slot[r] = st;
-                        mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x540u + st);
-                        if (++st == N_STAGES) { st = 0; ph ^= 1u; }
-                        windows(pi, S - TAIL + r, a[r], nk[r]);
-                    }
-                    mbar_wait(sBar + 8 * BAR_BFULL, pass & 1u, 0x5C0u);
-                    if (profiling) { c1 = clock64(); tp += c1 - c0; }
-                    tc_fence_after();
-                    if (elect_one()) {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            if (t < n_tiles) {
-#pragma unroll
-                                for (int r = 0; r < TAIL; ++r) issue(a[r], nk[r], slot[r], t, t + 1, 1u);
-                                umma_f16(tmem + (uint32_t)(t * 128), one_lo, b_lo0, 1u);   // bias rows x the all-ones operand
-                            }
-                            umma_commit_pair(sBar + 8 * (BAR_ACC + t));   // (tiles the pass does not have complete with the last real one)
+                        for (int part = 0; part < 2; ++part) {
+                            const uint32_t b = a + (uint32_t)(8 * part) * (A_LBO >> 4);
+                            stage(b, b + 2u * (A_LBO >> 4), b + 4u * (A_LBO >> 4), b + 6u * (A_LBO >> 4), 4, (tap | part) != 0);
                         }
+                    }
+                }
+                {   // bias rows x the all-ones operand (one K step; every row of the ones operand is the same)
+                    long long c0 = 0;
+                    if (profiling) c0 = clock64();
+                    mbar_wait(sBar + 8 * BAR_BFULL, pass & 1u, 0x5C0u);
+                    if (profiling) tp += clock64() - c0;
+                    tc_fence_after();
+                    if (elect_one()) {
 #pragma unroll
-                        for (int r = 0; r < TAIL; ++r) umma_commit_pair(sBar + 8 * (BAR_WEMPTY + slot[r]));
+                        for (int t = 0; t < 4; ++t)
+                            if (t < n_tiles) umma_f16(tmem + (uint32_t)(t * 128), one_lo, b_lo0, 1u);
                         umma_commit_pair(sBar + 8 * BAR_BEMPTY);
-                        if (pi.l0_last) umma_commit_pair(sBar + 8 * BAR_FEMPTY);   // feature planes no longer needed
                     }
                     __syncwarp();
-                    if (profiling) ti += clock64() - c1;
                 }
+                if (elect_one()) {
+                    if (pi.l0_last) umma_commit_pair(sBar + 8 * BAR_FEMPTY);   // feature planes no longer needed
+                    umma_commit_pair(sBar + 8 * BAR_ACC);                      // accumulators of this pass complete
+                }
+                __syncwarp();
                 if (args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) {
                     args.prof[pass * 4 + 1] = clock64();
                     args.prof[256 + pass * 4 + 0] = tw; args.prof[256 + pass * 4 + 1] = tp; args.prof[256 + pass * 4 + 2] = ti;
@@ -695,12 +672,9 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
             const int np = n_passes(pair_nb);
             for (int ps = 0; ps < np; ++ps, ++pass) {
                 const Pass pi = pass_info(pair_nb, ps);
-                // tile wq may be rewritten (in place) once the tile behind it is complete as well: that tile's MMAs read the
-                // first rows of tile wq's successor window, i.e. the last 11 rows of tile wq
-                const int wait_tile = wq < pi.n_tiles ? min(wq + 1, pi.n_tiles - 1) : 3;
-                mbar_wait(sBar + 8 * (BAR_ACC + wait_tile), pass & 1u, 0x600u + pass);
+                mbar_wait(sBar + 8 * BAR_ACC, pass & 1u, 0x600u + pass);
                 tc_fence_after();
-                const bool prof = args.prof && blockIdx.x == 0 && pass < 64 && threadIdx.x == 32 * 12;   // last tile's group
+                const bool prof = args.prof && blockIdx.x == 0 && pass < 64 && threadIdx.x == 0;
                 if (prof) args.prof[pass * 4 + 2] = clock64();
                 const bool dump = args.dump && blockIdx.x == 0 && first && ps == args.dump_pass;
                 if (wq < pi.n_tiles) {
@@ -741,7 +715,10 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster_relaxed(leader_act);
+                if (lane == 0) {
+                    __threadfence_block();     // the warp's stores are performed before the (relaxed) arrive can be observed
+                    mbar_arrive_cluster_relaxed(leader_act);
+                }
                 if (prof) args.prof[pass * 4 + 3] = clock64();
                 if (pi.layer == 6) {
                     // logit[] holds nb boards x 81 head outputs; it is next written seven passes from now, and
