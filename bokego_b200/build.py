@@ -29,7 +29,7 @@ def build(force=False, verbose=False):
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         subprocess.check_call(cmd)
         objs.append(o)
-    subprocess.check_call([NVCC, "-shared", "-o", SO] + objs + ["-lcudart"])
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs + ["-lcudart"])
     return SO
 
 
