@@ -144,7 +144,8 @@ class PackedNet:
         self.device = dev
 
 
-def policy_value_batch(feats_conv, B, policy=None, value=None, want_logits=True, simt=False, _extra_flags=0, probs_out=None):
+def policy_value_batch(feats_conv, B, policy=None, value=None, want_logits=True, simt=False, _extra_flags=0, probs_out=None,
+                       value_out=None):
     """PolicyNet / ValueNet forward for B positions (kernel b).
 
     feats_conv: the "conv" output of features_batch.  policy / value: PackedNet or None.
@@ -162,7 +163,11 @@ def policy_value_batch(feats_conv, B, policy=None, value=None, want_logits=True,
         if probs_out is not None:
             _want(probs_out, torch.float32, (B, 81), "probs_out", dev)
         probs = probs_out if probs_out is not None else torch.empty(B, 81, dtype=torch.float32, device=dev)
-    val = torch.empty(B, dtype=torch.float32, device=dev) if value is not None else None
+    val = None
+    if value is not None:
+        if value_out is not None:
+            _want(value_out, torch.float32, (B,), "value_out", dev)
+        val = value_out if value_out is not None else torch.empty(B, dtype=torch.float32, device=dev)
     flags = (FLAG_POLICY if policy is not None else 0) | (FLAG_VALUE if value is not None else 0) | \
             (FLAG_SIMT if simt else 0) | _extra_flags
     with torch.cuda.device(dev):
@@ -172,6 +177,81 @@ def policy_value_batch(feats_conv, B, policy=None, value=None, want_logits=True,
     _lib.check(rc, "bk_forward")
     _lib.count_launch()
     return logits, probs, val
+
+
+class HostEvaluator:
+    """Policy + value evaluation of positions that live in HOST memory (what a search running on the CPU calls): one packed
+    pinned staging buffer each way, so a call is one host-to-device copy (boards, ko, last, turn), the encoder, the conv
+    kernel, and one device-to-host copy (probabilities, values).  Fill `h_boards / h_ko / h_last / h_turn` (views of the
+    pinned input buffer), call `run()` (stream-ordered, does not synchronise), read `h_probs / h_value` after a
+    synchronisation.  With `depth` > 1 the staging buffers are rotated, so the copies of one call overlap the kernels of
+    the next (`run()` then returns the slot index whose outputs it will fill)."""
+
+    def __init__(self, B, policy, value, device, depth=1):
+        dev = _lib.require_device(device)
+        L = _lib.lib()
+        self.B, self.policy, self.value, self.device, self.depth = B, policy, value, dev, depth
+        nb = (B * 81 + 7) // 8 * 8                            # boards, padded so that the int16 arrays behind them are aligned
+        n_in, n_out = nb + 3 * 2 * B, 4 * (B * 81 + B)
+        self.slots = []
+        for _ in range(depth):
+            h_in = torch.empty(n_in, dtype=torch.uint8).pin_memory()
+            d_in = torch.empty(n_in, dtype=torch.uint8, device=dev)
+            h_out = torch.empty(B * 81 + B, dtype=torch.float32).pin_memory()
+            d_out = torch.empty(B * 81 + B, dtype=torch.float32, device=dev)
+            meta = lambda t, k: t[nb + 2 * B * k: nb + 2 * B * (k + 1)].view(torch.int16)
+            views = lambda t: (t[: B * 81].view(torch.int8).view(B, 81), meta(t, 0), meta(t, 1), meta(t, 2))
+            hb, hk, hl, ht = views(h_in)
+            db, dk, dl, dt = views(d_in)
+            self.slots.append({"h_in": h_in, "d_in": d_in, "h_out": h_out, "d_out": d_out,
+                               "h": (hb, hk, hl, ht), "pos": Positions(db, dk, dl, dt),
+                               "d_probs": d_out[: B * 81].view(B, 81), "d_value": d_out[B * 81:],
+                               "h_probs": h_out[: B * 81].view(B, 81), "h_value": h_out[B * 81:],
+                               "conv": torch.empty(L.bk_feats_conv_bytes(B), dtype=torch.uint8, device=dev),
+                               "in_done": torch.cuda.Event(), "out_done": torch.cuda.Event(), "computed": torch.cuda.Event()})
+        self.k = 0
+        self.copy_in = torch.cuda.Stream(device=dev) if depth > 1 else None
+        self.copy_out = torch.cuda.Stream(device=dev) if depth > 1 else None
+        self.h2d_bytes, self.d2h_bytes = n_in, n_out
+
+    def slot(self, i=None):
+        return self.slots[self.k % self.depth if i is None else i]
+
+    def run(self):
+        s = self.slots[self.k % self.depth]
+        i = self.k % self.depth
+        self.k += 1
+        main = torch.cuda.current_stream(self.device)
+        if self.depth == 1:
+            s["d_in"].copy_(s["h_in"], non_blocking=True)
+            features_batch(s["pos"], fresh_libs=True, want=("conv",), out={"conv": s["conv"]})
+            policy_value_batch(s["conv"], self.B, self.policy, self.value, want_logits=False, probs_out=s["d_probs"],
+                               value_out=s["d_value"])
+            s["h_out"].copy_(s["d_out"], non_blocking=True)
+            return i
+        # rotated buffers: copy-in and copy-out run on their own streams, ordered against the kernels by events
+        self.copy_in.wait_event(s["computed"])            # the kernels that last read this slot's inputs are done
+        with torch.cuda.stream(self.copy_in):
+            s["d_in"].copy_(s["h_in"], non_blocking=True)
+            s["in_done"].record()
+        main.wait_event(s["in_done"])
+        main.wait_event(s["out_done"])                    # the previous results of this slot have left the device
+        features_batch(s["pos"], fresh_libs=True, want=("conv",), out={"conv": s["conv"]})
+        policy_value_batch(s["conv"], self.B, self.policy, self.value, want_logits=False, probs_out=s["d_probs"],
+                           value_out=s["d_value"])
+        s["computed"].record()
+        self.copy_out.wait_event(s["computed"])
+        with torch.cuda.stream(self.copy_out):
+            s["h_out"].copy_(s["d_out"], non_blocking=True)
+            s["out_done"].record()
+        return i
+
+    def drain(self):
+        """make the current stream wait for every outstanding copy"""
+        if self.depth > 1:
+            main = torch.cuda.current_stream(self.device)
+            main.wait_stream(self.copy_in)
+            main.wait_stream(self.copy_out)
 
 
 def playout_step(pos, probs, mode, max_turn, seed=0, game0=0, q_inj=None, moves_out=None):

@@ -247,6 +247,29 @@ def test_forward_is_repeatable_under_cold_and_warm_l2(bk, dev, sd17, n):
         assert torch.equal(l1, ref_l), it
 
 
+@pytest.mark.parametrize("n,depth", [(7, 1), (123, 3), (4096, 3)])
+def test_host_evaluator_matches_device_path(bk, dev, sd17, sd_value, n, depth):
+    """host-resident positions through the packed / rotated staging buffers give exactly the device-path results"""
+    pol, val = bk.PackedNet(sd17, dev), bk.PackedNet(sd_value, dev)
+    ev = bk.HostEvaluator(n, pol, val, dev, depth=depth)
+    sets = []
+    for i in range(depth):
+        bd, ko, last, turn = _legal_positions(bk, dev, 123, 20 + i)
+        idx = (np.arange(n) * (i + 1)) % 123
+        sets.append((bd[idx], ko[idx], last[idx], turn[idx]))
+        for h, a in zip(ev.slot(i)["h"], sets[-1]):
+            h.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+    used = [ev.run() for _ in range(2 * depth + 1)]          # every slot is reused at least once
+    ev.drain()
+    torch.cuda.synchronize()
+    assert used[:depth] == list(range(depth))
+    for i in range(depth):
+        pos = _pos(bk, dev, *sets[i])
+        conv = bk.features_batch(pos, want=("conv",))["conv"]
+        _, p, v = bk.policy_value_batch(conv, n, pol, val, want_logits=False)
+        assert torch.equal(ev.slot(i)["h_probs"], p.cpu()) and torch.equal(ev.slot(i)["h_value"], v.cpu())
+
+
 def test_exp_stream_bit_identical(bk, dev):
     for seed, g0, mv, tr in ((0, 0, 0, 0), (12345678901234, 77, 13, 5), (2**63 + 5, 4000, 80, 81)):
         q = bk.exp_draws(seed, g0, mv, tr, 6, dev).cpu().numpy()
