@@ -22,7 +22,7 @@
 //     place; after the last layer they compute the 1x1 head with the untied bias and finish with the 81-way
 //     softmax (policy) or the small dense tail + tanh (value).
 // Warp roles: warps 0-15 epilogue, warp 16 = bulk-copy producer (+ TMEM allocation), warp 17 = MMA issuer in the
-// leader CTA / barrier forwarder in the peer CTA (tells the leader when the peer's operands have landed).
+// leader CTA / forwarder in the peer CTA (tells the leader when the peer's feature planes have landed).
 // Items that do not fill a whole round of the grid are split into smaller board ranges (fewer M tiles each)
 // so that the last round, and small batches, spread over more SMs.
 //
