@@ -9,12 +9,14 @@ Same search rule as the reference's `MCTS` in its default `no_sim` mode (/root/r
     (mcts.py:208-217); `choose` takes the most visited child and re-roots (mcts.py:110-131).
 What differs is the machinery: the tree is a set of flat arrays indexed by node id (no per-node Python objects, no dict
 caches), positions of all nodes live in one device-resident pool, children are made by one `bk_make_moves` launch per
-expansion, and leaves are evaluated in batches: `leaf_batch` descents are made under a virtual loss before one encoder +
-one policy/value launch scores every new leaf.  With `leaf_batch=1` the visit counts are those of the sequential rule.
+expansion, the descents / back-ups run in a native host-side core of the library, and leaves are evaluated in batches: up to
+`leaf_batch` descents that need the device are parked under a virtual loss before one encoder + one policy/value launch scores
+every new leaf (descents that end in an already evaluated leaf are backed up at once).  With `leaf_batch=1` the visit counts
+are those of the sequential rule.
 
 Ties in the arg-max go to the lowest move index (the reference iterates a Python set, i.e. its tie-break is arbitrary).
 """
-import math
+import ctypes as C
 
 import numpy as np
 import torch
@@ -174,52 +176,28 @@ class MCTS:
         self.n += c
 
     # ---- search -----------------------------------------------------------------------------------------------------------
-    def _select(self, i):
-        lo, c = self.child0[i], self.nchild[i]
-        n = self.N[lo: lo + c]
-        total = max(1, int(n.sum()))
-        avg = np.divide(self.V[lo: lo + c], n, out=np.zeros(c), where=n > 0)
-        p = self.prior[i][self.move[lo: lo + c]].astype(np.float64)
-        score = -avg + self.exploration_weight * p * math.sqrt(total) / (1.0 + n)
-        return lo + int(np.argmax(score))
-
-    def _descend(self):
-        """path from the root to a leaf (mcts.py:172-183); a leaf visited more than expand_thresh times gets its children"""
-        path = [self.root]
-        i = self.root
-        while True:
-            if self.nchild[i] <= 0:
-                if self.nchild[i] < 0 and self.N[i] > self.expand_thresh and not np.isnan(self.val[i]):
-                    self._expand(i)
-                return path
-            i = self._select(i)
-            path.append(i)
-
     def rollout(self, n=1):
-        """n rollouts; leaf_batch descents share one evaluation batch (virtual loss keeps them apart)"""
+        """n rollouts.  The descents, the virtual losses and the back-ups run in the library's host-side tree core
+        (bk_tree_run / bk_tree_finish, csrc/bk_tree.cu: mcts.py:172-234 on the flat arrays); it hands control back whenever
+        up to `leaf_batch` descents wait for the device -- an unevaluated leaf, or a leaf visited more than expand_thresh times
+        that has to get its children -- and those are evaluated / expanded here in one batch."""
+        L = _lib.lib()
+        K, D = self.leaf_batch, 128
+        pend_nodes, pend_len = np.empty((K, D), np.int32), np.empty(K, np.int32)
+        pend_expand, n_pend = np.empty(K, np.int32), C.c_int(0)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
         done = 0
         while done < n:
-            k = min(self.leaf_batch, n - done)
-            paths = []
-            for _ in range(k):
-                path = self._descend()
-                paths.append(path)
-                if k > 1:
-                    for j in path:                      # virtual loss: as if the descent had been lost for whoever chose it
-                        self.N[j] += 1
-                        self.V[j] += 1.0
-            if k > 1:
-                for path in paths:
-                    for j in path:
-                        self.N[j] -= 1
-                        self.V[j] -= 1.0
-            self._evaluate([p[-1] for p in paths])
-            for path in paths:
-                v = self.val[path[-1]]
-                for j in reversed(path):                # mcts.py:208-217
-                    self.N[j] += 1
-                    self.V[j] += v
-                    v = -v
+            done += L.bk_tree_run(p(self.N), p(self.V), p(self.child0), p(self.nchild), p(self.move), p(self.prior), p(self.val),
+                                  int(self.root), n - done, K, int(self.expand_thresh), C.c_double(self.exploration_weight),
+                                  p(pend_nodes), p(pend_len), p(pend_expand), D, C.byref(n_pend))
+            k = n_pend.value
+            if k == 0:
+                continue
+            self._evaluate([int(pend_nodes[j, pend_len[j] - 1]) for j in range(k)])
+            for node in dict.fromkeys(int(x) for x in pend_expand[:k] if x >= 0):
+                self._expand(node)
+            L.bk_tree_finish(p(self.N), p(self.V), p(self.val), p(pend_nodes), p(pend_len), k, D, K)
             done += k
 
     def root_visits(self):

@@ -100,6 +100,19 @@ int bk_score(const int8_t *boards, float komi, float *score_out, int8_t *reward_
 /* the counter-based Exp(1) stream itself: q float32 [B][81] for (seed, game0 + b, move, try) */
 int bk_exp_draws(uint64_t seed, uint32_t game0, uint32_t move, uint32_t tr, float *q, int B, void *stream);
 
+/* ---- host-side core of the batched tree search (bokego/mcts.py:172-234: _descend, _puct_select, _backpropagate) ----------
+ * HOST pointers to the flat arrays of one tree: N visits, V value sums, child0 / nchild (children are contiguous, -1 = not
+ * expanded), move (the move that led to the node), prior float [nodes][81] (policy probabilities of the node's position), val
+ * (value-net output of the node, NaN = not evaluated yet).  bk_tree_run makes descents until n_rollouts are complete or
+ * leaf_batch of them wait for device work (an unevaluated leaf, or a leaf visited more than expand_thresh times that has to be
+ * expanded); those are parked in pend_nodes [leaf_batch][max_depth] / pend_len / pend_expand under a virtual loss.  After the
+ * caller has evaluated / expanded, bk_tree_finish removes the virtual losses and backs the values up. */
+int bk_tree_run(int64_t *N, double *V, const int32_t *child0, const int32_t *nchild, const int16_t *move, const float *prior,
+                const double *val, int root, int n_rollouts, int leaf_batch, int expand_thresh, double c_puct,
+                int32_t *pend_nodes, int32_t *pend_len, int32_t *pend_expand, int max_depth, int *n_pending);
+int bk_tree_finish(int64_t *N, double *V, const double *val, const int32_t *pend_nodes, const int32_t *pend_len,
+                   int n_pending, int max_depth, int leaf_batch);
+
 #ifdef __cplusplus
 }
 #endif
