@@ -153,26 +153,39 @@ class MCTS:
         return self.turn[i] > MAX_TURNS or self.last[i] == PASS      # mcts.py:362-364
 
     def _expand(self, i):
-        if self.nchild[i] >= 0:
+        self._expand_many([i])
+
+    def _expand_many(self, nodes):
+        """children (all legal moves, never PASS, mcts.py:309-317) for every node of `nodes`: one bk_make_moves launch for all"""
+        par, mvs, spans = [], [], []
+        for i in nodes:
+            if self.nchild[i] >= 0:
+                continue
+            if self._terminal(i):
+                self.nchild[i] = 0
+                continue
+            mv = np.flatnonzero(self.legal[i]).astype(np.int16)
+            self.nchild[i] = len(mv)
+            if len(mv):
+                spans.append((i, len(mv)))
+                par.append(np.full(len(mv), i, np.int32))
+                mvs.append(mv)
+        if not spans:
             return
-        if self._terminal(i):
-            self.nchild[i] = 0
-            return
-        mv = np.flatnonzero(self.legal[i]).astype(np.int16)
-        c = len(mv)
-        self.nchild[i] = c
-        if c == 0:
-            return
+        par, mvs = np.concatenate(par), np.concatenate(mvs)
+        c = len(mvs)
         self._grow(c)
         lo = self.n
-        par = torch.full((c,), i, dtype=torch.int32, device=self.device)
-        child, status = make_moves(self.pool, par, torch.from_numpy(mv).to(self.device))
+        child, _ = make_moves(self.pool, torch.from_numpy(par).to(self.device), torch.from_numpy(mvs).to(self.device))
         sl = slice(lo, lo + c)
         self.pool.boards[sl], self.pool.ko[sl], self.pool.last[sl] = child.boards, child.ko, child.last
         self.pool.turn[sl], self.pool.libs[sl] = child.turn, child.libs
-        self.child0[i] = lo
-        self.parent[sl], self.move[sl] = i, mv
-        self.turn[sl], self.last[sl] = self.turn[i] + 1, mv
+        self.parent[sl], self.move[sl] = par, mvs
+        self.turn[sl], self.last[sl] = self.turn[par] + 1, mvs
+        at = lo
+        for i, k in spans:
+            self.child0[i] = at
+            at += k
         self.n += c
 
     # ---- search -----------------------------------------------------------------------------------------------------------
@@ -195,8 +208,7 @@ class MCTS:
             if k == 0:
                 continue
             self._evaluate([int(pend_nodes[j, pend_len[j] - 1]) for j in range(k)])
-            for node in dict.fromkeys(int(x) for x in pend_expand[:k] if x >= 0):
-                self._expand(node)
+            self._expand_many(list(dict.fromkeys(int(x) for x in pend_expand[:k] if x >= 0)))
             L.bk_tree_finish(p(self.N), p(self.V), p(self.val), p(pend_nodes), p(pend_len), k, D, K)
             done += k
 
