@@ -345,6 +345,21 @@ def run_ours(args, rank, world, local_rank):
                                   "kernel_launches_per_batch": sp.launches},
                      "simulate": {"boards_per_gpu": args.simulate_boards, "playouts_per_s": world * args.simulate_boards * 2 / (1e-3 * sim_tot),
                                   "ms_per_batch": sim_tot / 2, "scaling": "weak", "max_turn": 80}}
+            # BASELINE configs[2]: one genmove of the batched tree search, 1600 playouts from the empty board (rank 0's GPU)
+            from bokego_b200 import mcts as bmcts
+            bmcts.MCTS(None, pol, val, device=dev).rollout(10)
+            gm = {}
+            for name, kw in (("reference_parameters", {"expand_thresh": 100, "leaf_batch": 32}),
+                             ("expand_on_second_visit", {"expand_thresh": 1, "leaf_batch": 128})):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                tree = bmcts.MCTS(None, pol, val, device=dev, **kw)
+                tree.rollout(1600)
+                tree.choose()
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                gm[name] = dict(kw, seconds=dt, playouts_per_s=1600 / dt, net_evals=tree.n_evals, eval_batches=tree.n_eval_batches)
+            extra["mcts_genmove"] = dict(gm, playouts=1600, position="empty 9x9 board", timing="host wall clock around the search")
     clocks = cs.summary()
     launches_timed = launches * args.steps // (args.steps + args.warmup)
 
