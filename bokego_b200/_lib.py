@@ -53,6 +53,19 @@ def _sig(L):
     L.bk_score.argtypes = [vp, f32, vp, vp, i32, vp]
     L.bk_exp_draws.restype = i32
     L.bk_exp_draws.argtypes = [u64, u32, u32, u32, vp, i32, vp]
+    L.bk_train_param_count.restype = C.c_size_t
+    L.bk_train_workspace_bytes.restype = C.c_size_t
+    L.bk_train_workspace_bytes.argtypes = [i32]
+    L.bk_train_launches.restype = i32
+    L.bk_train_launches.argtypes = [i32]
+    L.bk_train_forward.restype = i32
+    L.bk_train_forward.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    L.bk_train_backward.restype = i32
+    L.bk_train_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i32, vp, vp]
+    L.bk_train_running_stats.restype = i32
+    L.bk_train_running_stats.argtypes = [vp, vp, vp, i32, f32, vp]
+    L.bk_adamw_step.restype = i32
+    L.bk_adamw_step.argtypes = [vp, vp, vp, vp, C.c_size_t] + [C.c_double] * 5 + [i32, vp]
 
 
 def lib():

@@ -64,6 +64,7 @@ def run_playouts(pos, policy, mode=MODE_MCTS, max_turn=None, seed=0, game0=0, po
     """Play every board of `pos` to the end with moves drawn from the policy net(s).
 
     policy:     PackedNet used for every move, or for the moves made at even `turn` when policy_odd is given
+                (either may be a reinforce.PolicyTrainer: the net being trained plays in train() mode, selfplay.py:148-150)
     policy_odd: PackedNet for the moves at odd turn (self-play of two nets; needs every board at the same turn parity,
                 `first_turn` states it)
     mode:       MODE_MCTS (Go_MCTS.find_random_child, mcts.py:319-364) or MODE_SELFPLAY (legal_sample, selfplay.py:35-47)
@@ -85,8 +86,11 @@ def run_playouts(pos, policy, mode=MODE_MCTS, max_turn=None, seed=0, game0=0, po
 
     def step(k, fresh):
         net = policy if (policy_odd is None or (first_turn + k) % 2 == 0) else policy_odd
-        features_batch(pos, fresh_libs=fresh, want=("conv", "libs"), out=bufs)
-        policy_value_batch(bufs["conv"], B, net, None, want_logits=False, probs_out=probs)
+        if hasattr(net, "play_probs"):     # a net being trained (reinforce.PolicyTrainer): train-mode forward, positions recorded
+            net.play_probs(pos, fresh, bufs, probs)
+        else:
+            features_batch(pos, fresh_libs=fresh, want=("conv", "libs"), out=bufs)
+            policy_value_batch(bufs["conv"], B, net, None, want_logits=False, probs_out=probs)
         playout_step(pos, probs, mode, max_turn, seed=seed, game0=game0, moves_out=moves[k])
 
     k0 = 0

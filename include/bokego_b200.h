@@ -113,6 +113,44 @@ int bk_tree_run(int64_t *N, double *V, const int32_t *child0, const int32_t *nch
 int bk_tree_finish(int64_t *N, double *V, const double *val, const int32_t *pend_nodes, const int32_t *pend_len,
                    int n_pending, int max_depth, int leaf_batch);
 
+/* ---- REINFORCE step (bin/selfplay.py:59-122): train-mode PolicyNet forward, policy-gradient loss, backward, AdamW ---------
+ * All pointers are device pointers.  Parameters, gradients and the Adam moments are flat float32 buffers of
+ * bk_train_param_count() elements in the layout of the training GEMMs (k = tap * Cin + ci, tap = kh * R + kw):
+ *   BK_TP_W0     conv.0.weight   as [25][32][128]  (tap, ci padded 27 -> 32 with zeros, co)
+ *   BK_TP_W1     conv.3..18.weight, six layers of [9][128][128]  (tap, ci, co)
+ *   BK_TP_VEC    seven layers of { conv.N.bias[128], BatchNorm weight[128], BatchNorm bias[128] }
+ *   BK_TP_HEADW  conv.21.weight[128];  BK_TP_HEADB  conv.21.bias[81]
+ * running = BatchNorm running statistics, float32 [2][7][128] (means of the 7 layers, then variances).
+ * bn_mode 0: every position is normalised with its own statistics -- PolicyNet in train() mode called with one position
+ *            per call, which is how policy_dist / policy_sample call it (nnet.py:265-297); 1: running statistics (eval()).
+ * prec 0: TF32 tensor-core operands, fp32 accumulation; 1: 3xTF32 split (fp32-grade); 2: FFMA fp32 (validation path).
+ * bk_train_forward: planes_u8 uint8 [P][27][81] (bk_encode's planes_u8 == nnet.features values) -> logits float32 [P][81]
+ *   (PolicyNet.forward, nnet.py:54-57), probs = SOFT(logits) (nnet.py:16; may be NULL), stats_out (may be NULL) float32
+ *   [P][7][2][128] = per-position channel mean and unbiased variance, i.e. what each train-mode call feeds into the running
+ *   averages.  Activations stay in `workspace` (bk_train_workspace_bytes(P) bytes) for bk_train_backward.
+ * bk_train_backward: loss = sum_p coef[p] * nlp[p], nlp[p] = -Categorical(probs_p).log_prob(moves[p]) (selfplay.py:98-100;
+ *   coef[p] = reward / bs, selfplay.py:115-117); writes nlp_out float32 [P] and d loss / d params into `grads`
+ *   (accumulate != 0: adds to it).  Must follow bk_train_forward with the same P, bn_mode and workspace.
+ * bk_train_running_stats: the BatchNorm momentum filter (momentum 0.1 in the reference) over train-mode calls on positions
+ *   seq[0..S) of stats (seq == NULL: 0..S-1), in call order.
+ * bk_adamw_step: torch.optim.AdamW's update (selfplay.py:138) of n elements; step counts from 1. */
+#define BK_TP_W0 0
+#define BK_TP_W1 102400
+#define BK_TP_VEC 987136
+#define BK_TP_HEADW 989824
+#define BK_TP_HEADB 989952
+#define BK_TP_COUNT 990033
+size_t bk_train_param_count(void);
+size_t bk_train_workspace_bytes(int P);
+int bk_train_launches(int which); /* kernels launched by bk_train_forward (0) / bk_train_backward (1) */
+int bk_train_forward(const float *params, const float *running, const uint8_t *planes_u8, int P, int bn_mode, int prec,
+                     void *workspace, float *logits, float *probs, float *stats_out, void *stream);
+int bk_train_backward(const float *params, const int16_t *moves, const float *coef, int P, int bn_mode, int prec,
+                      void *workspace, float *grads, int accumulate, float *nlp_out, void *stream);
+int bk_train_running_stats(float *running, const float *stats, const int32_t *seq, int S, float momentum, void *stream);
+int bk_adamw_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, size_t n, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, int step, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,164 @@
+"""CPU checks of the REINFORCE row's host logic and of the arithmetic the training kernels implement.
+
+`emulate_*` below restate, in numpy, exactly what csrc/bk_train.cu computes -- the flat parameter layout (k = tap * Cin + ci),
+the implicit-GEMM window gather, the data gradient as the same gather on dZ with mirrored taps and per-tap transposed
+weights, the weight gradient, the per-position BatchNorm backward formula and the head / loss backward -- and compare the
+result with the oracle (torch autograd over the reference's own ops).  The CUDA kernels themselves are compared with the
+oracle on the GPU (tests/test_gpu_train.py); this file pins the conventions they share with the host code."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from bokego_b200 import reinforce as rf
+from oracle import train as ot
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+EPS = 1e-5
+
+
+def taps(R):
+    h = R // 2
+    return [(t // R - h, t % R - h) for t in range(R * R)]
+
+
+def gather(x, R, sign):
+    """x [P,81,C] -> [P*81, R*R*C]: column (tap, ci) of row (p, sq) = x[p, sq shifted by sign * tap, ci], 0 off the board"""
+    P, _, C = x.shape
+    g = x.reshape(P, 9, 9, C)
+    out = np.zeros((P, 9, 9, R * R, C), x.dtype)
+    for t, (dx, dy) in enumerate(taps(R)):
+        dx, dy = sign * dx, sign * dy
+        xs, xe = max(0, -dx), min(9, 9 - dx)
+        ys, ye = max(0, -dy), min(9, 9 - dy)
+        out[:, xs:xe, ys:ye, t] = g[:, xs + dx:xe + dx, ys + dy:ye + dy]
+    return out.reshape(P * 81, R * R * C)
+
+
+def emulate(flat, planes, moves, coef):
+    P = planes.shape[0]
+    x0 = np.zeros((P, 81, 32), np.float64)
+    x0[:, :, :27] = np.transpose(planes.astype(np.float64), (0, 2, 1))
+    W = [flat[rf.TP_W0:rf.TP_W1].reshape(800, 128).astype(np.float64)] + \
+        [flat[rf.TP_W1 + l * 147456: rf.TP_W1 + (l + 1) * 147456].reshape(1152, 128).astype(np.float64) for l in range(6)]
+    vec = flat[rf.TP_VEC:rf.TP_HEADW].reshape(7, 3, 128).astype(np.float64)
+    hw, hb = flat[rf.TP_HEADW:rf.TP_HEADW + 128].astype(np.float64), flat[rf.TP_HEADB:rf.TP_HEADB + 81].astype(np.float64)
+    a, zs, acts, mus, rss = x0, [], [x0], [], []
+    for l in range(7):
+        R = 5 if l == 0 else 3
+        z = (gather(a, R, +1) @ W[l] + vec[l, 0]).reshape(P, 81, 128)
+        mu = z.mean(1, keepdims=True)
+        rs = 1.0 / np.sqrt(z.var(1, keepdims=True) + EPS)
+        a = np.maximum(0.0, (z - mu) * rs * vec[l, 1] + vec[l, 2])
+        zs.append(z); acts.append(a); mus.append(mu); rss.append(rs)
+    logits = a @ hw + hb
+    e = np.exp(logits - logits.max(1, keepdims=True))
+    pr = e / e.sum(1, keepdims=True)
+    pm = pr[np.arange(P), moves]
+    clamped = (pm < ot.PROB_EPS) | (pm > 1 - ot.PROB_EPS)        # Categorical clamps before the log: no gradient there
+    nlp = -np.log(np.clip(pm, ot.PROB_EPS, 1 - ot.PROB_EPS))
+    dl = np.where(clamped[:, None], 0.0, coef[:, None] * (pr - np.eye(81)[moves]))
+    grad = np.zeros(rf.TP_COUNT, np.float64)
+    grad[rf.TP_HEADB:rf.TP_HEADB + 81] = dl.sum(0)
+    grad[rf.TP_HEADW:rf.TP_HEADW + 128] = np.einsum("ps,psc->c", dl, a)
+    da = dl[:, :, None] * hw[None, None, :]
+    gv = grad[rf.TP_VEC:rf.TP_HEADW].reshape(7, 3, 128)
+    for l in range(6, -1, -1):
+        R = 5 if l == 0 else 3
+        g = np.where(acts[l + 1] > 0, da, 0.0)
+        xh = (zs[l] - mus[l]) * rss[l]
+        s1, s2 = g.sum(1, keepdims=True), (g * xh).sum(1, keepdims=True)
+        dz = vec[l, 1] * rss[l] * (g - s1 / 81 - xh * s2 / 81)
+        gv[l, 0], gv[l, 1], gv[l, 2] = dz.sum((0, 1)), s2.sum((0, 1)), s1.sum((0, 1))
+        gw = gather(acts[l], R, +1).T @ dz.reshape(P * 81, 128)
+        if l == 0:
+            grad[rf.TP_W0:rf.TP_W1] = gw.ravel()
+        else:
+            grad[rf.TP_W1 + (l - 1) * 147456: rf.TP_W1 + l * 147456] = gw.ravel()
+            wd = np.transpose(W[l].reshape(9, 128, 128), (0, 2, 1)).reshape(1152, 128)   # [(tap, co)][ci]
+            da = (gather(dz, 3, -1) @ wd).reshape(P, 81, 128)
+    return logits, nlp, grad
+
+
+def test_flat_layout_round_trip():
+    sd = dict(np.load(os.path.join(GOLD, "weights_policy_17.npz")))
+    flat = rf.flat_from_tensors(lambda k: sd[k])
+    assert flat.shape == (rf.TP_COUNT,)
+    back = rf.tensors_from_flat(flat)
+    assert list(back) == rf.param_keys() == ot.param_keys()
+    for k, v in back.items():
+        assert v.shape == sd[k].shape and np.array_equal(v, sd[k]), k
+    w0 = flat[rf.TP_W0:rf.TP_W1].reshape(25, 32, 128)
+    assert np.all(w0[:, 27:] == 0)
+    assert w0[7, 3, 5] == sd["conv.0.weight"][5, 3, 1, 2]          # tap = kh * 5 + kw
+    w3 = flat[rf.TP_W1 + 2 * 147456: rf.TP_W1 + 3 * 147456].reshape(9, 128, 128)
+    assert w3[5, 17, 99] == sd["conv.9.weight"][99, 17, 1, 2]
+
+
+def test_game_major_order():
+    o = rf.game_major(3, 2)
+    assert o.tolist() == [0, 2, 4, 1, 3, 5]
+
+
+def test_kernel_arithmetic_matches_autograd():
+    sd = dict(np.load(os.path.join(GOLD, "weights_policy_17.npz")))
+    G = np.load(os.path.join(GOLD, "reinforce.npz"))
+    planes = G["black3/calls"][[3, 40, 77, 120]]
+    rng = np.random.default_rng(0)
+    moves = rng.integers(0, 81, len(planes))
+    coef = np.array([0.5, -0.25, 1.0, -1.0 / 3])
+    flat = rf.flat_from_tensors(lambda k: sd[k])
+    logits, nlp, grad = emulate(flat, planes, moves, coef)
+    loss, grads, lo = ot.reinforce_grads(sd, planes.astype(np.float32), moves, coef)
+    assert np.abs(logits - lo.numpy()).max() < 2e-3
+    assert abs(float((nlp * coef).sum()) - loss) < 1e-3 * max(1.0, abs(loss))
+    mine = rf.tensors_from_flat(grad.astype(np.float32))
+    for k, g in grads.items():
+        g = g.numpy()
+        scale = np.abs(g).max()
+        if k.endswith(".bias") and k.split(".")[1] in ("0", "3", "6", "9", "12", "15", "18"):
+            assert np.abs(mine[k]).max() < 1e-4 and scale < 1e-4   # conv bias: cancelled by the mean subtraction
+            continue
+        assert np.abs(mine[k] - g).max() <= 2e-4 * scale + 1e-7, (k, np.abs(mine[k] - g).max(), scale)
+
+
+def test_running_filter_and_adamw_against_reference_run():
+    """oracle restatements of the running-average filter and of AdamW against the recorded reference iteration"""
+    sd = dict(np.load(os.path.join(GOLD, "weights_policy_17.npz")))
+    G = np.load(os.path.join(GOLD, "reinforce.npz"))
+    stride = int(G["stride"])
+    for tag in ("black3", "white2"):
+        calls = G[f"{tag}/calls"].astype(np.float32)
+        _, means, uv = ot.train_forward(sd, calls)
+        rs = ot.running_stats(sd, means.numpy(), uv.numpy())
+        for k, v in rs.items():
+            ref = G[f"{tag}/post/{k}"]
+            if k.endswith("tracked"):
+                assert int(v) == int(ref)
+            else:
+                assert np.abs(v - ref).max() < 1e-4, k
+        color, bs = int(G[f"{tag}/color"]), int(G[f"{tag}/bs"])
+        rf_from = int(G[f"{tag}/replay_from"])
+        pos = ot.replay_positions(G[f"{tag}/lengths"], color)
+        assert len(pos) == len(calls) - rf_from
+        mv = np.array([G[f"{tag}/moves"][g, j] for g, j in pos])
+        coef = ot.reference_coef(G[f"{tag}/lengths"], G[f"{tag}/results"], color, bs)
+        _, grads, _ = ot.reinforce_grads(sd, calls[rf_from:], mv, coef)
+        for k, g in grads.items():
+            a = g.numpy().ravel()
+            ref, amax = G[f"{tag}/grad/{k}"], float(G[f"{tag}/grad/{k}/absmax"])
+            s = a if a.size <= 4096 else a[::stride]
+            if amax < 1e-5:
+                assert np.abs(s).max() < 1e-5          # conv biases: round-off noise in the reference as well
+                continue
+            assert np.abs(s - ref).max() <= 1e-4 * amax, k
+            assert abs(np.sqrt((a.astype(np.float64) ** 2).sum()) - float(G[f"{tag}/grad/{k}/l2"])) <= 1e-4 * float(G[f"{tag}/grad/{k}/l2"])
+            p, _, _ = ot.adamw_step(sd[k], g.numpy(), np.zeros_like(sd[k]), np.zeros_like(sd[k]), 1)
+            post = G[f"{tag}/post/{k}"]
+            ps = p.numpy().ravel()
+            ps = ps if ps.size <= 4096 else ps[::stride]
+            # Adam's first step moves every element by lr * g / (|g| + eps): where |g| is at round-off level its sign,
+            # and with it the element's update, is noise -- at most 2 * lr, and only on a handful of elements
+            d = np.abs(ps - post)
+            assert d.max() <= 2.1e-5 and (d > 1e-7).sum() <= max(3, 5e-3 * d.size), (k, d.max(), (d > 1e-7).mean())
