@@ -205,6 +205,73 @@ def cpu_selfplay_rate(n_games, sd17, sd19, seed=1):
     return n_games / dt, cores, dt
 
 
+FLOP_TRAIN = 2 * (2 * 66_706_944 + 6 * 10_240_000 + 10_368)   # forward + weight gradient + data gradient, valid taps, per position
+
+
+def reinforce_leg(dev, sd17, sd19, with_cpu):
+    """REINFORCE row (bin/selfplay.py:59-122): the training step on the 576 positions of a reference-sized
+    batch (bs = 16 games x 36 moves of the training colour), and whole iterations of the loop (self-play + step)."""
+    from bokego_b200 import nnet, reinforce as rf
+    calls = np.load(os.path.join(ROOT, "tests", "golden", "reinforce.npz"))["black3/calls"]
+    P = 576
+    planes = torch.from_numpy(np.ascontiguousarray(calls[np.arange(P) % len(calls)])).to(dev)
+    moves = torch.randint(0, 81, (P,), device=dev).to(torch.int16)
+    coef = torch.full((P,), 1.0 / 16, device=dev)
+    out = {"positions": P, "flop_per_position": FLOP_TRAIN}
+    tf_peak = peaks()[0] / 2            # TF32 runs at half the 16-bit tensor rate
+    for prec, name in ((rf.PREC_3XTF32, "3xtf32 (default, fp32-grade)"), (rf.PREC_TF32, "tf32")):
+        tr = rf.PolicyTrainer(sd17, dev, prec=prec)
+        for _ in range(3):
+            rf.reinforce_step(tr, planes, moves, coef)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 10
+        a.record()
+        for _ in range(n):
+            rf.reinforce_step(tr, planes, moves, coef)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / n
+        ach = FLOP_TRAIN * P / (1e-3 * ms) / 1e12
+        out[name.split(" ")[0]] = {"step_ms": ms, "positions_per_s": P / (1e-3 * ms), "achieved_tflops": ach,
+                                   "frac_of_tf32_peak": ach / tf_peak, "precision": name}
+    out["peak"] = {"tflops": tf_peak, "source": "half of the measured 16-bit dense peak (TF32 operands)"}
+    pi, opp = nnet.PolicyNet(), nnet.PolicyNet()
+    pi.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd17.items()})
+    opp.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd19.items()})
+    pi.to(dev).train()
+    opp.to(dev).eval()
+    opt = torch.optim.AdamW(pi.parameters(), lr=1e-5)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):        # reinforce() prints the win rate like the reference; stdout carries the JSON line only
+        rf.reinforce(pi, opp, opt, "black", n_itrs=2, bs=16, device=dev, stats=[])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 10
+        rf.reinforce(pi, opp, opt, "black", n_itrs=n, bs=16, device=dev, stats=[], seed=100)
+        torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / n
+    out["iteration"] = {"bs": 16, "seconds": dt, "games_per_s": 16 / dt, "iterations_per_s": 1 / dt,
+                        "what": "reinforce(): 16 self-play games in lock step (pi in train mode vs policy_19), running statistics, "
+                                "backward of the last game (the reference's per-game loss reset), AdamW; host wall clock"}
+    if with_cpu:
+        from oracle import train as ot
+        cores = len(os.sched_getaffinity(0))
+        torch.set_num_threads(cores)
+        n_cpu = 72
+        x = calls[:n_cpu].astype(np.float32)
+        mv, cf = np.arange(n_cpu) % 81, np.full(n_cpu, 1.0 / 16, np.float32)
+        ot.reinforce_grads(sd17, x[:8], mv[:8], cf[:8])
+        t0 = time.perf_counter()
+        _, grads, _ = ot.reinforce_grads(sd17, x, mv, cf)
+        for k, g in grads.items():
+            ot.adamw_step(sd17[k], g.numpy(), np.zeros_like(sd17[k]), np.zeros_like(sd17[k]), 1)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "positions/s", "cores": cores, "kind": "port",
+                               "sample": f"{n_cpu} positions: torch CPU autograd forward + backward + AdamW restatement ({dt:.2f} s)"}
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -360,6 +427,8 @@ def run_ours(args, rank, world, local_rank):
                 dt = time.perf_counter() - t0
                 gm[name] = dict(kw, seconds=dt, playouts_per_s=1600 / dt, net_evals=tree.n_evals, eval_batches=tree.n_eval_batches)
             extra["mcts_genmove"] = dict(gm, playouts=1600, position="empty 9x9 board", timing="host wall clock around the search")
+        if world == 1 and not args.no_train:
+            extra["reinforce"] = reinforce_leg(dev, sd17, sd19, not args.no_cpu)
     clocks = cs.summary()
     launches_timed = launches * args.steps // (args.steps + args.warmup)
 
@@ -415,6 +484,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-playouts", action="store_true", help="skip the self-play / simulate secondary measurements")
+    ap.add_argument("--no-train", action="store_true", help="skip the REINFORCE step measurement")
     ap.add_argument("--selfplay-games", type=int, default=4096)
     ap.add_argument("--simulate-boards", type=int, default=65536)
     ap.add_argument("--cpu-selfplay-games", type=int, default=256)

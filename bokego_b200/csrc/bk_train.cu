@@ -55,7 +55,7 @@ __device__ __forceinline__ uint32_t f2tf32(float x)
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
 {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
@@ -121,6 +121,7 @@ __device__ __forceinline__ void warp_tile(float (&acc)[4][4][4], const float *a,
                     if (PREC == 1) {
                         // the tensor core's fp32 accumulation truncates; keep its chains three MMAs short and add the
                         // partial sums with IEEE fp32 adds, otherwise the split buys nothing over a long reduction
+                        // (interleaving the chains of the four column blocks was tried: slower, it spills)
                         float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                         mma_tf32(c, al, bh[j]);
                         mma_tf32(c, ah, bl[j]);
