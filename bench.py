@@ -31,12 +31,13 @@ FLOP_DENSE = 314_700_032     # what nn.Conv2d executes with zero padding -- seco
 
 
 def load_nets():
-    from oracle import nets as onets   # only for the seeded stand-in value head parameters (plain tensors)
     g = os.path.join(ROOT, "tests", "golden")
     sd17 = dict(np.load(os.path.join(g, "weights_policy_17.npz")))
     sd19 = dict(np.load(os.path.join(g, "weights_policy_19.npz")))
     sdv = dict(sd19)
-    sdv.update({k: v.numpy() for k, v in onets.standin_value_head(1234).items()})
+    # seeded stand-in value head (the reference ships no value_1.pt): the same numbers as
+    # oracle.nets.standin_value_head(1234), kept as a fixture so that this arm does not import oracle/
+    sdv.update(dict(np.load(os.path.join(g, "weights_value_head_standin.npz"))))
     return sd17, sd19, sdv
 
 

@@ -8,8 +8,9 @@ runs in the CUDA kernels behind the C ABI (include/bokego_b200.h):
     PolicyNet.forward / ValueNet.forward  -> bk_repack_f32 + bk_forward
     policy_dist / value / policy_sample   -> thin wrappers, as in the reference
 
-There is no CPU path: a `device` that is not an sm_100 CUDA device raises BokegoB200Error, and so does
-forward() in training mode (the REINFORCE / supervised training loops of the reference are out of scope).
+There is no CPU path: a `device` that is not an sm_100 CUDA device raises BokegoB200Error.  forward() in training mode
+evaluates ONE position per call with that position's BatchNorm statistics (how the reference's REINFORCE loop calls a net in
+train() mode); batched training lives in bokego_b200.reinforce, and no autograd graph is ever built.
 The batched entry points that carry the throughput are re-exported from bokego_b200.batched.
 """
 from math import sqrt
@@ -87,10 +88,40 @@ class _FusedNet(nn.Module):
             self.__dict__["_bk_cache"] = cache
         return cache[1]
 
+    def _run_train_mode(self, x):
+        '''forward in train() mode for ONE position, as the reference's policy_dist / policy_sample call a net that is being
+        trained (nnet.py:265-297 with bin/selfplay.py:148-150): BatchNorm normalises with the statistics of this position and
+        filters them into its running averages (momentum 0.1, unbiased variance), exactly as torch does per call.  No autograd
+        graph is built: gradients come from bokego_b200.reinforce.'''
+        from . import reinforce as rf
+        if self._is_value:
+            raise _lib.BokegoB200Error("ValueNet has no train-mode kernel: call .eval() first")
+        x = x.reshape(-1, 27, 9, 9)
+        if x.shape[0] != 1:
+            raise _lib.BokegoB200Error("train-mode forward is defined for one position per call (how the reference calls it); "
+                                       "use bokego_b200.reinforce for batched training, or .eval() for batched inference")
+        dev = _lib.require_device(x.device)
+        stamp = (str(dev),) + tuple(int(p._version) for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+        cache = self.__dict__.get("_bk_train_cache")
+        if cache is None or cache[0] != stamp:
+            cache = (stamp, rf.PolicyTrainer(self.state_dict(), dev))
+            self.__dict__["_bk_train_cache"] = cache
+        tr = cache[1]
+        sd = self.state_dict()
+        r, _ = rf.running_from_state_dict(sd)                  # the module's buffers are the truth (they may have been loaded)
+        tr.running.copy_(torch.from_numpy(r))
+        logits, _, stats = tr.forward(x.to(torch.uint8).reshape(1, 27, 81).contiguous(), rf.BN_POSITION, want_stats=True)
+        tr.update_running(stats)
+        with torch.no_grad():
+            for l, i in enumerate(rf.CONV_IDX):
+                sd[f"conv.{i + 1}.running_mean"].copy_(tr.running[0, l])
+                sd[f"conv.{i + 1}.running_var"].copy_(tr.running[1, l])
+                sd[f"conv.{i + 1}.num_batches_tracked"].add_(1)
+        return logits
+
     def _run(self, x):
         if self.training:
-            raise _lib.BokegoB200Error("bokego_b200 nets are inference-only: call .eval() first "
-                                       "(training-mode BatchNorm / autograd are out of scope)")
+            return self._run_train_mode(x)
         dev = _lib.require_device(x.device)
         x = x.reshape(-1, 27, 9, 9).contiguous().float()
         conv = repack_planes(x)

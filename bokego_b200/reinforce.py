@@ -244,9 +244,8 @@ class PolicyTrainer:
         self.forward(self._rec_planes[k], BN_POSITION, probs_out=probs_out, stats_out=self._rec_stats[k])
 
 
-def reinforce_step(trainer, planes_u8, moves, coef, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                   bn_mode=BN_POSITION, chunk=2048):
-    """forward + backward over P positions (in chunks of `chunk`) and one AdamW step.  Returns the loss as a 0-d tensor."""
+def compute_grads(trainer, planes_u8, moves, coef, bn_mode=BN_POSITION, chunk=2048):
+    """forward + backward over P positions (in chunks of `chunk`): trainer.grads = d loss / d params, returns the loss (0-d)"""
     P = planes_u8.shape[0]
     loss = torch.zeros((), dtype=torch.float32, device=trainer.device)
     for lo in range(0, P, chunk):
@@ -256,8 +255,48 @@ def reinforce_step(trainer, planes_u8, moves, coef, lr=1e-5, betas=(0.9, 0.999),
         loss = loss + (nlp * coef[lo:hi]).sum()
     if P == 0:
         trainer.grads.zero_()
+    return loss
+
+
+def reinforce_step(trainer, planes_u8, moves, coef, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
+                   bn_mode=BN_POSITION, chunk=2048, group=None):
+    """forward + backward over this rank's P positions, the sum of the gradients over the ranks of `group` (one all-reduce of the
+    flat gradient buffer: NCCL on the device; a no-op without an initialised process group), and one AdamW step -- every rank
+    applies the same update to its replica.  Returns the loss summed over ranks as a 0-d tensor."""
+    loss = compute_grads(trainer, planes_u8, moves, coef, bn_mode, chunk)
+    if _world(group) > 1:
+        import torch.distributed as dist
+        dist.all_reduce(trainer.grads, group=group)
+        dist.all_reduce(loss, group=group)
     trainer.adamw_step(lr, betas, eps, weight_decay)
     return loss
+
+
+def _world(group=None):
+    import torch.distributed as dist
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def _rank(group=None):
+    import torch.distributed as dist
+    return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+
+
+def gather_games(local, n_games, group=None):
+    """[n_steps, n_local, ...] blocks of the ranks (rank r holds games shard_range(n_games, r, world)) -> [n_steps, n_games, ...]
+    on every rank, games in global order.  One all_gather (NCCL for CUDA tensors, gloo for CPU tensors); identity for one rank."""
+    world = _world(group)
+    if world == 1:
+        return local
+    import torch.distributed as dist
+    from .playout import shard_range
+    sizes = [hi - lo for lo, hi in (shard_range(n_games, r, world) for r in range(world))]
+    most = max(sizes)
+    pad = torch.zeros((local.shape[0], most) + tuple(local.shape[2:]), dtype=local.dtype, device=local.device)
+    pad[:, : local.shape[1]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad.contiguous(), group=group)
+    return torch.cat([parts[r][:, : sizes[r]] for r in range(world)], dim=1).contiguous()
 
 
 def _adopt_optimizer(trainer, pi, optimizer):
@@ -294,7 +333,10 @@ def reinforce(pi, pi_opp, optimizer, train_color, **kwargs):
         pi: training PolicyNet (bokego_b200.nnet.PolicyNet), pi_opp: opponent PolicyNet,
         optimizer: torch.optim.AdamW over pi.parameters(), train_color: "black" or "white"
     kwargs: n_itrs (60), bs (16), device, stats (list the win counts are appended to), id;
-    additional: accumulate ("reference" | "batch"), seed (random stream of the games), prec (PREC_*).
+    additional: accumulate ("reference" | "batch"), seed (random stream of the games), prec (PREC_*), group (process group).
+    With torch.distributed initialised (one process per GPU) the `bs` games of an iteration are sharded over the ranks by global
+    game id, the per-call statistics are all-gathered, the gradients all-reduced (NCCL), and every rank applies the same step:
+    the replicas stay identical and the games do not depend on the number of ranks.
     The trained weights, running statistics and optimizer state are written back into `pi` / `optimizer`.'''
     from .playout import SELFPLAY_MAX_TURN, run_playouts
     from .batched import MODE_SELFPLAY, PackedNet, Positions
@@ -309,6 +351,11 @@ def reinforce(pi, pi_opp, optimizer, train_color, **kwargs):
     seed = kwargs.get("seed", 0)
     dev = _lib.require_device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
     white = train_color == "white"
+    group = kwargs.get("group")
+    rank, world = _rank(group), _world(group)
+    from .playout import shard_range
+    lo, hi = shard_range(bs, rank, world)            # this rank's games (global ids: the random stream is keyed by them)
+    nb = hi - lo
     trainer = PolicyTrainer(pi.state_dict(), dev, prec=kwargs.get("prec", PREC_3XTF32))
     hyper = _adopt_optimizer(trainer, pi, optimizer)
     opp = PackedNet(pi_opp.state_dict(), dev, is_value=False)
@@ -316,29 +363,41 @@ def reinforce(pi, pi_opp, optimizer, train_color, **kwargs):
     order = torch.from_numpy(game_major(n_mine, bs)).to(dev)
     winlist = []
     for itr in range(n_itrs):
-        pos = Positions.empty(bs, dev, track_libs=False)
-        trainer.begin_recording(n_mine, bs)
-        res = run_playouts(pos, opp if white else trainer, MODE_SELFPLAY, SELFPLAY_MAX_TURN, seed=seed + itr, game0=0,
-                           policy_odd=trainer if white else opp, graph=False)
-        results = res.reward.to(torch.float32)                  # +1 black wins, -1 otherwise (sign of Game.score())
+        pos = Positions.empty(nb, dev, track_libs=False)
+        trainer.begin_recording(n_mine, nb)
+        if nb > 0:
+            res = run_playouts(pos, opp if white else trainer, MODE_SELFPLAY, SELFPLAY_MAX_TURN, seed=seed + itr, game0=lo,
+                               policy_odd=trainer if white else opp, graph=False)
+            results = res.reward.to(torch.float32)              # +1 black wins, -1 otherwise (sign of Game.score())
+            # the moves of the training colour, [step][game] like the recorded planes; a finished game has codes < PASS there
+            mine = res.moves[:, (1 if white else 0)::2].t().contiguous()
+        else:
+            results = torch.zeros(0, dtype=torch.float32, device=dev)
+            mine = torch.zeros(n_mine, 0, dtype=torch.int16, device=dev)
         reward = -results if white else results
-        # the moves of the training colour, [step][game] like the recorded planes; a finished game has codes < PASS there
-        mine = res.moves[:, (1 if white else 0)::2].t().contiguous()
         played = mine >= 0
-        coef = (reward / bs)[None, :].expand(n_mine, bs).clone()
+        coef = (reward / bs)[None, :].expand(n_mine, nb).clone()
         if accumulate == "reference":
-            coef[:, : bs - 1] = 0.0                             # `loss` is reset per game: only the last one is differentiated
-        elif accumulate != "batch":
+            # `loss` is reset per game (selfplay.py:86): only the last game of the batch is differentiated
+            sel = slice(nb - 1, nb) if (hi == bs and nb > 0) else slice(0, 0)
+        elif accumulate == "batch":
+            sel = slice(0, nb)
+        else:
             raise ValueError('accumulate must be "reference" or "batch"')
         coef = torch.where(played, coef, torch.zeros_like(coef))
-        stats_rows = trainer._rec_stats.reshape(n_mine * bs, 7, 2, 128)
-        # running statistics: the self-play calls game by game, then the replay calls on the same positions
+        # running statistics: the self-play calls game by game, then the replay calls on the same positions (all ranks' games)
+        stats_rows = gather_games(trainer._rec_stats, bs, group).reshape(n_mine * bs, 7, 2, 128)
         trainer.update_running(stats_rows, torch.cat([order, order]))
-        sel = slice(bs - 1, bs) if accumulate == "reference" else slice(0, bs)   # positions are independent: skip zero coefficients
+        # positions are independent under per-position BatchNorm, so games with a zero coefficient are skipped
         reinforce_step(trainer, trainer._rec_planes[:, sel].reshape(-1, 27, 81).contiguous(),
-                       mine[:, sel].reshape(-1).clamp(min=0).contiguous(), coef[:, sel].reshape(-1).contiguous(), **hyper)
-        winlist.append(int((reward == 1).sum().item()))
-        if len(winlist) > 0 and len(winlist) % 10 == 0:
+                       mine[:, sel].reshape(-1).clamp(min=0).contiguous(), coef[:, sel].reshape(-1).contiguous(), group=group,
+                       **hyper)
+        wins = (reward == 1).sum()
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(wins, group=group)
+        winlist.append(int(wins.item()))
+        if len(winlist) > 0 and len(winlist) % 10 == 0 and rank == 0:
             avg_win = sum(winlist[-10:]) / (bs * 10)
             print(f"Winrate ({train_color}{idn}): {avg_win:.2f}")
     _hand_back(trainer, pi, optimizer)

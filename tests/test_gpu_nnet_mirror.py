@@ -54,9 +54,30 @@ def test_nets_and_wrappers(positions, nets_golden, sd17, sd_value):
     pi.load_state_dict({k: torch.from_numpy(np.asarray(a)) * (0.5 if k == "conv.21.bias" else 1.0) for k, a in sd17.items()})
     l2 = pi(x[:1])
     assert float((l2 - logits[:1]).abs().max()) > 1e-3
+    # train() mode: one position per call, normalised with its own statistics, running averages filtered like torch does
+    # (how policy_dist calls a net that bin/selfplay.py:148-150 has put in train mode); batches and the ValueNet raise
+    from oracle import train as ot
+    pi.load_state_dict({k: torch.from_numpy(np.asarray(a)) for k, a in sd17.items()})
     pi.train()
     with pytest.raises(_lib.BokegoB200Error):
-        pi(x[:1])
+        pi(x[:2])
+    v.train()
+    with pytest.raises(_lib.BokegoB200Error):
+        v(x[:1])
+    nbt = int(pi.state_dict()["conv.1.num_batches_tracked"])
+    lt = pi(x[5:6])
+    want, means, uvars = ot.train_forward(sd17, x[5:6].cpu())
+    assert float((lt.cpu() - want).abs().max()) < 2e-3
+    assert float((lt.cpu() - logits[5:6].cpu()).abs().max()) > 1e-2          # not the eval-mode function
+    rs = ot.running_stats(sd17, means.numpy(), uvars.numpy())
+    sd_after = pi.state_dict()
+    for k, w in rs.items():
+        if k.endswith("tracked"):
+            assert int(sd_after[k]) == nbt + 1
+        else:
+            assert float((sd_after[k].cpu() - torch.from_numpy(w)).abs().max()) < 1e-3 * (1 + float(np.abs(w).max())), k
+    d = nnet.policy_dist(pi, g, device=DEV)                                   # the reference's call, net in train mode
+    assert abs(float(d.probs.sum()) - 1) < 1e-5 and int(sd_after["conv.1.num_batches_tracked"]) == nbt + 2
 
 
 def test_prefill_caches(positions, nets_golden, sd17, sd_value):

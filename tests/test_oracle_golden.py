@@ -114,3 +114,14 @@ def test_exp_stream_is_exponential():
     # different counters give different streams; same counters repeat
     assert np.array_equal(ocpu.exp_draws(1, 2, 3, 4), ocpu.exp_draws(1, 2, 3, 4))
     assert not np.array_equal(ocpu.exp_draws(1, 2, 3, 4), ocpu.exp_draws(1, 2, 3, 5))
+
+
+def test_standin_value_head_fixture_matches_generator():
+    """bench.py's own arm loads the stand-in value head from a fixture (it must not import oracle/): same numbers"""
+    import os
+    from oracle import nets as onets
+    fx = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "weights_value_head_standin.npz")))
+    gen = onets.standin_value_head(1234)
+    assert set(fx) == set(gen)
+    for k, v in gen.items():
+        assert np.array_equal(fx[k], v.numpy()), k

@@ -83,3 +83,37 @@ def test_record_round_trips_through_sgf(tmp_path):
     for m in g.moves:                           # ... and the moves replay legally
         g.play_move(m)
     assert g.turn == 20
+
+
+# ---- REINFORCE row: the exchange step of data-parallel training (gather of per-call statistics, sum of gradients) ----------
+def _train_worker(rank, world, port, n_games, out_dir):
+    from bokego_b200 import reinforce as rf
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(n_games, rank, world)
+    full = torch.arange(3 * n_games * 5, dtype=torch.float32).reshape(3, n_games, 5)       # [step][game][...]
+    got = rf.gather_games(full[:, lo:hi].contiguous(), n_games)
+    assert rf._world() == world and rf._rank() == rank
+    g = torch.full((7,), float(rank + 1))
+    dist.all_reduce(g)                                                                      # what reinforce_step does to the gradients
+    np.save(os.path.join(out_dir, f"games_{rank}.npy"), got.numpy())
+    np.save(os.path.join(out_dir, f"grads_{rank}.npy"), g.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("n_games", [4, 5, 1])
+def test_gather_games_two_ranks(tmp_path, n_games):
+    world = 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_train_worker, args=(world, port, n_games, str(tmp_path)), nprocs=world, join=True)
+    full = np.arange(3 * n_games * 5, dtype=np.float32).reshape(3, n_games, 5)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"games_{r}.npy"), full)                  # uneven and empty shards included
+        assert np.array_equal(np.load(tmp_path / f"grads_{r}.npy"), np.full(7, 3.0, np.float32))
+
+
+def test_gather_games_single_rank_is_identity():
+    from bokego_b200 import reinforce as rf
+    t = torch.zeros(2, 3, 4)
+    assert rf.gather_games(t, 3) is t and rf._world() == 1 and rf._rank() == 0
