@@ -220,7 +220,8 @@ def reinforce_leg(dev, sd17, sd19, with_cpu):
     coef = torch.full((P,), 1.0 / 16, device=dev)
     out = {"positions": P, "flop_per_position": FLOP_TRAIN}
     tf_peak = peaks()[0] / 2            # TF32 runs at half the 16-bit tensor rate
-    for prec, name in ((rf.PREC_3XTF32, "3xtf32 (default, fp32-grade)"), (rf.PREC_TF32, "tf32")):
+    for prec, name in ((rf.PREC_TC_3XTF32, "3xtf32 (tcgen05; default, fp32-grade)"), (rf.PREC_TC_TF32, "tf32 (tcgen05)"),
+                       (rf.PREC_3XTF32, "3xtf32_mma_sync (warp-level MMA)"), (rf.PREC_TF32, "tf32_mma_sync (warp-level MMA)")):
         tr = rf.PolicyTrainer(sd17, dev, prec=prec)
         for _ in range(3):
             rf.reinforce_step(tr, planes, moves, coef)

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libbokego_b200.so")
-SOURCES = ["bk_api.cu", "bk_encode.cu", "bk_forward.cu", "bk_step.cu", "bk_tree.cu", "bk_train.cu"]
+SOURCES = ["bk_api.cu", "bk_encode.cu", "bk_forward.cu", "bk_step.cu", "bk_tree.cu", "bk_train.cu", "bk_train_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-diag-suppress", "1886"] + os.environ.get("BK_NVCC_DEFS", "").split()   # e.g. -DBK_KSTEPS_PER_STAGE=1

@@ -22,6 +22,7 @@
 #include <stdint.h>
 
 #include "../../include/bokego_b200.h"
+#include "bk_train_args.h"
 
 namespace {
 
@@ -140,11 +141,7 @@ __device__ __forceinline__ void warp_tile(float (&acc)[4][4][4], const float *a,
 // ---- implicit-GEMM convolution: out[m][co] = sum_{tap,ci} in[m shifted by sign*tap][ci] * w[(tap,ci)][co] (+ bias[co]) ----
 // sign = +1: forward conv (cross-correlation, zero padding R/2).  sign = -1 with w = the per-tap transposed weights: the
 // data gradient.  in: [M/81][81][Cin], w: [R*R*Cin][128], out: [M][128].
-struct ConvArgs {
-    const float *in, *w, *bias;
-    float *out;
-    int M, Cin, R, sign;
-};
+using ConvArgs = BkConvArgs;
 
 template <int PREC>
 __global__ void __launch_bounds__(NT, 2) bk_train_conv_kernel(const ConvArgs a)
@@ -226,11 +223,7 @@ __global__ void __launch_bounds__(NT, 2) bk_train_conv_kernel(const ConvArgs a)
 
 // ---- weight gradient: part[split][k][co] = sum over the split's rows m of act[m shifted by tap(k)][ci(k)] * dz[m][co] ----
 // grid = (k tiles of 128, splits).  For Cin = 128 a k tile is one tap; for Cin = 32 it is four taps.
-struct WgradArgs {
-    const float *act, *dz;
-    float *part;
-    int M, Cin, R, K, rows_per_split;
-};
+using WgradArgs = BkWgradArgs;
 
 template <int PREC>
 __global__ void __launch_bounds__(NT, 2) bk_train_wgrad_kernel(const WgradArgs a)
@@ -353,6 +346,15 @@ __global__ void bk_train_transpose_kernel(const float *w, float *wd, int n_mat)
     for (int r = threadIdx.y; r < 32; r += 8) tile[r][threadIdx.x] = src[(size_t)(by + r) * C + bx + threadIdx.x];
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += 8) dst[(size_t)(bx + r) * C + by + threadIdx.x] = tile[threadIdx.x][r];
+}
+
+// wp[k / 4][co][k % 4] = w[k][co]: the K-major B operand of the tcgen05 kernels (bk_train_tc.cu), n floats in total
+__global__ void bk_train_pack_w_kernel(const float *w, float *wp, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = i / C, co = i - k * C;
+    wp[(size_t)(k >> 2) * (4 * C) + co * 4 + (k & 3)] = w[i];
 }
 
 // ---- BatchNorm (+ ReLU) forward for one position per CTA, thread = channel ----
@@ -548,7 +550,7 @@ __global__ void bk_adamw_kernel(float *p, const float *g, float *m, float *v, si
 
 // ---- workspace (floats) ----
 struct Ws {
-    size_t x0, z[7], a[7], mean[7], rstd[7], da, dz, logits, dlogit, part, dwpart, wd, wpart, total;
+    size_t x0, z[7], a[7], mean[7], rstd[7], da, dz, logits, dlogit, part, dwpart, wd, wpack, wdpack, wpart, total;
     int splits, rows_per_split;
 };
 
@@ -576,6 +578,8 @@ Ws ws_layout(int P)
     w.part = take((size_t)P * 3 * C);
     w.dwpart = take((size_t)P * C);
     w.wd = take((size_t)6 * 9 * C * C);
+    w.wpack = take((size_t)BK_TP_VEC);              // all conv weights, K-major packed (tcgen05 path)
+    w.wdpack = take((size_t)6 * 9 * C * C);         // the transposed weights of the data gradient, packed
     const int M = P * NSQ;
     int splits = (M + 1023) / 1024;                 // >= 1024 rows per split, at most 32 splits
     splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
@@ -601,7 +605,7 @@ int set_attrs()
     BK_SET(bk_train_wgrad_kernel<1>, WGRAD_SMEM);
     BK_SET(bk_train_wgrad_kernel<2>, WGRAD_SMEM);
 #undef BK_SET
-    if (e != cudaSuccess) return -3;
+    if (e != cudaSuccess || bk_tc_set_attrs() != 0) return -3;
     attrs_set = true;
     return 0;
 }
@@ -609,7 +613,8 @@ int set_attrs()
 void launch_conv(const ConvArgs &a, int prec, cudaStream_t st)
 {
     const int grid = (a.M + BM - 1) / BM;
-    if (prec == 1) bk_train_conv_kernel<1><<<grid, NT, CONV_SMEM, st>>>(a);
+    if (prec >= 4) bk_tc_launch_conv(a, prec == 5, st);
+    else if (prec == 1) bk_train_conv_kernel<1><<<grid, NT, CONV_SMEM, st>>>(a);
     else if (prec == 2) bk_train_conv_kernel<2><<<grid, NT, CONV_SMEM, st>>>(a);
     else bk_train_conv_kernel<0><<<grid, NT, CONV_SMEM, st>>>(a);
 }
@@ -617,7 +622,8 @@ void launch_conv(const ConvArgs &a, int prec, cudaStream_t st)
 void launch_wgrad(const WgradArgs &a, int splits, int prec, cudaStream_t st)
 {
     const dim3 grid((a.K + 127) / 128, splits);
-    if (prec == 1) bk_train_wgrad_kernel<1><<<grid, NT, WGRAD_SMEM, st>>>(a);
+    if (prec >= 4) bk_tc_launch_wgrad(a, splits, prec == 5, st);
+    else if (prec == 1) bk_train_wgrad_kernel<1><<<grid, NT, WGRAD_SMEM, st>>>(a);
     else if (prec == 2) bk_train_wgrad_kernel<2><<<grid, NT, WGRAD_SMEM, st>>>(a);
     else bk_train_wgrad_kernel<0><<<grid, NT, WGRAD_SMEM, st>>>(a);
 }
@@ -638,16 +644,17 @@ extern "C" int bk_train_forward(const float *params, const float *running, const
 {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (P <= 0) return 0;
-    if (!params || !running || !planes_u8 || !workspace || bn_mode < 0 || bn_mode > 1 || prec < 0 || prec > 2) return -1;
+    if (!params || !running || !planes_u8 || !workspace || bn_mode < 0 || bn_mode > 1 || prec < 0 || prec > 5 || prec == 3) return -1;
     if (set_attrs() != 0) return -3;
     const Ws w = ws_layout(P);
     float *ws = static_cast<float *>(workspace);
     const int n0 = P * NSQ * C0;
     bk_train_pack_kernel<<<(n0 + 255) / 256, 256, 0, st>>>(planes_u8, ws + w.x0, P);
+    if (prec >= 4) bk_train_pack_w_kernel<<<(BK_TP_VEC + 255) / 256, 256, 0, st>>>(params, ws + w.wpack, BK_TP_VEC);
     for (int l = 0; l < 7; ++l) {
         ConvArgs a;
         a.in = l == 0 ? ws + w.x0 : ws + w.a[l - 1];
-        a.w = params + w_off(l);
+        a.w = prec >= 4 ? ws + w.wpack + w_off(l) : params + w_off(l);
         a.bias = params + vec_off(l, 0);
         a.out = ws + w.z[l];
         a.M = P * NSQ;
@@ -670,12 +677,13 @@ extern "C" int bk_train_backward(const float *params, const int16_t *moves, cons
 {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (P <= 0) return 0;
-    if (!params || !moves || !coef || !workspace || !grads || !nlp_out || bn_mode < 0 || bn_mode > 1 || prec < 0 || prec > 2) return -1;
+    if (!params || !moves || !coef || !workspace || !grads || !nlp_out || bn_mode < 0 || bn_mode > 1 || prec < 0 || prec > 5 || prec == 3) return -1;
     if (set_attrs() != 0) return -3;
     const Ws w = ws_layout(P);
     float *ws = static_cast<float *>(workspace);
     const int M = P * NSQ;
     bk_train_transpose_kernel<<<dim3(4, 4, 54), dim3(32, 8), 0, st>>>(params + BK_TP_W1, ws + w.wd, 54);
+    if (prec >= 4) bk_train_pack_w_kernel<<<(6 * 9 * C * C + 255) / 256, 256, 0, st>>>(ws + w.wd, ws + w.wdpack, 6 * 9 * C * C);
     bk_train_head_bwd_kernel<<<P, 128, 0, st>>>(ws + w.logits, ws + w.a[6], params + BK_TP_HEADW, moves, coef, nlp_out,
                                                 ws + w.dlogit, ws + w.da, ws + w.dwpart);
     bk_train_colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(ws + w.dwpart, grads + BK_TP_HEADW, P, C, accumulate);
@@ -700,7 +708,7 @@ extern "C" int bk_train_backward(const float *params, const int16_t *moves, cons
         if (l > 0) {
             ConvArgs a;
             a.in = ws + w.dz;
-            a.w = ws + w.wd + (size_t)(l - 1) * 9 * C * C;
+            a.w = (prec >= 4 ? ws + w.wdpack : ws + w.wd) + (size_t)(l - 1) * 9 * C * C;
             a.bias = nullptr;
             a.out = ws + w.da;
             a.M = M;

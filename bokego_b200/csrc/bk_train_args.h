@@ -1,0 +1,28 @@
+/* bk_train_args.h -- argument blocks shared by the two implementations of the training GEMMs
+ * (bk_train.cu: warp-level mma.sync / FFMA; bk_train_tc.cu: tcgen05 with TMEM accumulators). */
+#ifndef BK_TRAIN_ARGS_H
+#define BK_TRAIN_ARGS_H
+
+#include <cuda_runtime.h>
+
+/* implicit-GEMM convolution: out[m][co] = sum_{tap,ci} in[m shifted by sign*tap][ci] * w[(tap,ci)][co] (+ bias[co])
+ * in: [M/81][81][Cin], w: [R*R*Cin][128], out: [M][128].  sign = -1 with per-tap transposed weights = data gradient. */
+struct BkConvArgs {
+    const float *in, *w, *bias;
+    float *out;
+    int M, Cin, R, sign;
+};
+
+/* weight gradient: part[split][k][co] = sum over the split's rows m of act[m shifted by tap(k)][ci(k)] * dz[m][co] */
+struct BkWgradArgs {
+    const float *act, *dz;
+    float *part;
+    int M, Cin, R, K, rows_per_split;
+};
+
+/* tcgen05 versions (bk_train_tc.cu); three_x != 0: 3xTF32 split operands.  Return a cudaError_t as int. */
+int bk_tc_set_attrs(void);
+void bk_tc_launch_conv(const BkConvArgs &a, int three_x, cudaStream_t st);
+void bk_tc_launch_wgrad(const BkWgradArgs &a, int splits, int three_x, cudaStream_t st);
+
+#endif

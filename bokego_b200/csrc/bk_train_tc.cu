@@ -1,0 +1,438 @@
+// bk_train_tc.cu -- the three GEMMs of the REINFORCE step (forward conv, data gradient, weight gradient; see bk_train.cu) on the
+// 5th-generation tensor cores: tcgen05.mma kind::tf32 issued by one thread, operands staged in shared memory, accumulators in TMEM.
+//
+// One CTA computes a 128 x 128 output tile.  Warp roles (288 threads):
+//   warps 4-7  producers: gather the operands of a 32-deep slab with 16-byte cp.async (zero fill for taps that leave the board),
+//              and -- in 3xTF32 mode -- split every value into a TF32 high part and a TF32 low part (hi = rna(x), lo = rna(x - hi));
+//   warp  8    issues the MMAs of a slab (4 K steps of 8; 3xTF32: lo*hi, hi*lo, hi*hi per step) and commits the slab's buffers back;
+//   warps 0-3  own the result: thread = output row.  The tensor core's fp32 accumulation truncates every time it adds to the
+//              accumulator (measured: chains of 48 MMAs leave errors of 1e-3 in the data gradient, whose sums cancel heavily), so in
+//              3xTF32 mode a chain is ONE K step (three MMAs): the MMA warp rotates through four TMEM accumulators, and these
+//              warps add each finished chain into fp32 registers with IEEE adds while the next chains run -- the same reason
+//              bk_train.cu keeps its mma.sync chains three MMAs short.  At the end they add the bias and store the rows.
+// Operand layout in shared memory: every operand is K-major without swizzle, [chunk of 4 along the reduction][row][4 floats]
+// (8 x 16-byte core matrices, SBO 128 B between 8-row groups, LBO 2048 B between the two reduction chunks of one K = 8 MMA).
+// MN-major TF32 operands without swizzle are not accepted by the tensor core (tools/probes/tc_probe.cu: the MMA returns zeros),
+// so whatever arrives with its GEMM-M / GEMM-N index contiguous is turned on the way in:
+//   conv:  A = gathered activation rows [m][ci] -- K-major as they come, 16-byte cp.async;
+//          B = weights, repacked once per step by bk_train_pack_w_kernel into [k / 4][co][k % 4] -- 16-byte cp.async;
+//   wgrad: A = activation rows [m][k index] and B = dZ rows [m][co], reduction over m: the producers load 4 rows x 4 columns into
+//          registers, transpose the 4 x 4 block and store it (the 3xTF32 split happens in the same registers).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bk_train_args.h"
+
+namespace {
+
+constexpr int C = 128;
+constexpr int NSQ = 81;
+constexpr int SLAB = 32;                 // reduction depth of one stage
+constexpr int MAX_STAGES = 6;
+constexpr int NBUF = 4;                  // TMEM accumulators of 128 columns (all 512 columns)
+constexpr int OP_BYTES = 128 * SLAB * 4; // one operand tile of a stage: 16 KiB
+constexpr int N_THREADS = 288;
+constexpr int WARP_MMA = 8;
+enum { BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_ACCF = 2 * MAX_STAGES, BAR_ACCE = 2 * MAX_STAGES + NBUF, N_BARS = 2 * MAX_STAGES + 2 * NBUF };
+
+template <int PREC>
+struct Sizes {
+    static constexpr int STAGE = (PREC ? 4 : 2) * OP_BYTES;          // A_hi, B_hi (, A_lo, B_lo)
+    static constexpr int STAGES = PREC ? 3 : 6;                      // 192 KiB of operand stages either way
+    static constexpr int LOOKAHEAD = STAGES - 1;                     // slabs a producer keeps in flight (conv: cp.async groups)
+    static constexpr int CHAIN = PREC ? 1 : 4;                       // K steps (of 8) accumulated in the tensor core before the fp32 add
+    static constexpr int SMEM = STAGES * STAGE + 256;
+};
+
+// instruction descriptor: D = f32 (bit 4), A = B = TF32 (2 at bits 7, 10), majors at bits 15 / 16 (1 = MN-major), N >> 3 at 17, M >> 4 at 24
+constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t DESC_HI_K = (128u >> 4) | (1u << 14);                 // SBO 128 B, descriptor version 1
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must end in a trap (launch error), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *g, bool valid)
+{
+    const int sz = valid ? 16 : 0;                            // 0 source bytes = 16 bytes of zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// completion of all MMAs issued so far by this thread -> one arrival on the barrier
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ float tf32_rna(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t hi)
+{
+    return ((uint64_t)hi << 32) | (((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16));
+}
+
+// MODE 0: convolution / data gradient (BkConvArgs).  MODE 1: weight gradient (BkWgradArgs), grid = (k tiles, splits).
+template <int MODE, int PREC, typename Args>
+__global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Args a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int STAGE = Sizes<PREC>::STAGE, STAGES = Sizes<PREC>::STAGES, LOOKAHEAD = Sizes<PREC>::LOOKAHEAD;
+    constexpr int CHAIN = Sizes<PREC>::CHAIN;
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_bar = s_base + STAGES * STAGE;
+    const uint32_t s_tmem = s_bar + 8 * N_BARS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- the reduction range of this CTA ----
+    int KT;                       // slabs
+    int m0 = 0, r_lo = 0, r_hi = 0, kb = 0;
+    if constexpr (MODE == 0) {
+        m0 = blockIdx.x * 128;
+        KT = a.R * a.R * a.Cin / SLAB;
+    } else {
+        kb = blockIdx.x;
+        r_lo = blockIdx.y * a.rows_per_split;
+        r_hi = min(a.M, r_lo + a.rows_per_split);
+        KT = r_hi > r_lo ? (r_hi - r_lo + SLAB - 1) / SLAB : 0;
+    }
+    const int n_chains = KT * (SLAB / 8) / CHAIN;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(s_bar + 8 * (BAR_FULL + s), 128);    // every producer thread
+            mbar_init(s_bar + 8 * (BAR_EMPTY + s), 1);     // tcgen05.commit
+        }
+        for (int b = 0; b < NBUF; ++b) {
+            mbar_init(s_bar + 8 * (BAR_ACCF + b), 1);      // tcgen05.commit
+            mbar_init(s_bar + 8 * (BAR_ACCE + b), 128);    // every result thread
+        }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(s_tmem, 128 * NBUF);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem + STAGES * STAGE + 8 * N_BARS);
+
+    if (warp >= 4 && warp < 8) {
+        // =============================== producers ===============================
+        const int pw = warp - 4, ptid = tid - 128;
+        const int half = a.R >> 1;
+        if constexpr (MODE == 0) {
+            // ---- conv: both operands by 16-byte cp.async; chunk i of this thread = (k chunk (i >> 2) * 4 + q4, row (pw + 4 (i & 3)) * 8 + r8)
+            const int r8 = lane & 7, q4 = lane >> 3;
+            uint32_t off[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) off[i] = (uint32_t)(((i >> 2) * 4 + q4) * 2048 + ((pw + 4 * (i & 3)) * 8 + r8) * 16);
+            int rbase[4], rx[4], ry[4];
+            bool rvalid[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int m = m0 + (pw + 4 * q) * 8 + r8;
+                rvalid[q] = m < a.M;
+                const int p = m / NSQ, sq = m - p * NSQ;
+                rx[q] = sq / 9;
+                ry[q] = sq - 9 * rx[q];
+                rbase[q] = p * NSQ;
+            }
+            auto issue = [&](int kt) {
+                const uint32_t st = s_base + (uint32_t)((kt % STAGES) * STAGE);
+                const int k0 = kt * SLAB;
+                const int tap = k0 / a.Cin, c0 = k0 - tap * a.Cin;
+                const int ti = tap / a.R;
+                const int dx = a.sign * (ti - half), dy = a.sign * (tap - ti * a.R - half);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int q = i & 3, kc = (i >> 2) * 4 + q4;
+                    const int x = rx[q] + dx, y = ry[q] + dy;
+                    const bool ok = rvalid[q] && (unsigned)x < 9u && (unsigned)y < 9u;
+                    const float *src = ok ? a.in + ((size_t)(rbase[q] + 9 * x + y) * a.Cin + c0 + 4 * kc) : a.in;
+                    cp_async16(st + off[i], src, ok);
+                    // packed weights [k / 4][co][4]: chunk (kc, co) of this slab
+                    cp_async16(st + OP_BYTES + off[i], a.w + ((size_t)(k0 / 4 + kc) * C + (pw + 4 * q) * 8 + r8) * 4, true);
+                }
+            };
+            auto publish = [&](int kt) {
+                const int s = kt % STAGES;
+                if constexpr (PREC != 0) {
+                    uint8_t *st = smem + s * STAGE;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t o = (i < 8 ? 0u : (uint32_t)OP_BYTES) + off[i & 7];
+                        float4 *hp = reinterpret_cast<float4 *>(st + o);
+                        const float4 v = *hp;
+                        float4 h, l;
+                        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+                        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                        *hp = h;
+                        *reinterpret_cast<float4 *>(st + 2 * OP_BYTES + o) = l;
+                    }
+                }
+                fence_proxy_async();                          // the tensor core reads shared memory through the async proxy
+                mbar_arrive(s_bar + 8 * (BAR_FULL + s));
+            };
+            for (int kt = 0; kt < KT + LOOKAHEAD; ++kt) {
+                if (kt < KT) {
+                    if (kt >= STAGES) mbar_wait(s_bar + 8 * (BAR_EMPTY + kt % STAGES), ((kt / STAGES) & 1) ^ 1);
+                    issue(kt);
+                }
+                cp_commit();
+                if (kt >= LOOKAHEAD) {
+                    cp_wait<LOOKAHEAD>();
+                    publish(kt - LOOKAHEAD);
+                }
+            }
+        } else {
+            // ---- wgrad: 4 x 4 blocks (4 rows m x 4 consecutive columns) through registers, transposed on the way.
+            // Block (j, mc): columns 4j .. 4j+3, rows 4 mc .. 4 mc + 3 of the slab.  This thread: j = lane, mc = pw and pw + 4,
+            // for A (activation rows, column = k index) and for B (dZ rows, column = co).
+            const int j = ptid & 31;
+            const int kglob = kb * 128 + 4 * j;
+            const int tap = kglob / a.Cin, ci = kglob - tap * a.Cin;
+            const bool tap_ok = tap < a.R * a.R;
+            const int ti = tap / a.R;
+            const int dx = ti - half, dy = tap - ti * a.R - half;
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                float4 va[2][4], vb[2][4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int mc = pw + 4 * u;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int m = r_lo + kt * SLAB + 4 * mc + r;
+                        const bool in_rows = m < r_hi;
+                        const int p = m / NSQ, sq = m - p * NSQ;
+                        const int x = sq / 9 + dx, y = sq - 9 * (sq / 9) + dy;
+                        const bool ok = in_rows && tap_ok && (unsigned)x < 9u && (unsigned)y < 9u;
+                        va[u][r] = ok ? __ldg(reinterpret_cast<const float4 *>(a.act + ((size_t)(p * NSQ + 9 * x + y) * a.Cin + ci)))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                        vb[u][r] = in_rows ? __ldg(reinterpret_cast<const float4 *>(a.dz + (size_t)m * C + 4 * j))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                if (kt >= STAGES) mbar_wait(s_bar + 8 * (BAR_EMPTY + s), ((kt / STAGES) & 1) ^ 1);
+                uint8_t *st = smem + s * STAGE;
+                auto put = [&](const float4 (&v)[4], uint32_t base) {
+                    // column c of the block = the four rows' c-th components: one 16-byte K chunk of row (4 j + c)
+                    const float cx[4][4] = {{v[0].x, v[1].x, v[2].x, v[3].x}, {v[0].y, v[1].y, v[2].y, v[3].y},
+                                            {v[0].z, v[1].z, v[2].z, v[3].z}, {v[0].w, v[1].w, v[2].w, v[3].w}};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float4 h = make_float4(cx[c][0], cx[c][1], cx[c][2], cx[c][3]);
+                        if constexpr (PREC != 0) {
+                            float4 l;
+                            const float4 x = h;
+                            h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+                            l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+                            *reinterpret_cast<float4 *>(st + 2 * OP_BYTES + base + (4 * j + c) * 16) = l;
+                        }
+                        *reinterpret_cast<float4 *>(st + base + (4 * j + c) * 16) = h;
+                    }
+                };
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    put(va[u], (uint32_t)((pw + 4 * u) * 2048));
+                    put(vb[u], (uint32_t)(OP_BYTES + (pw + 4 * u) * 2048));
+                }
+                fence_proxy_async();
+                mbar_arrive(s_bar + 8 * (BAR_FULL + s));
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        // =============================== MMA issue ===============================
+        int c = 0;                                     // chain counter: chain c accumulates in TMEM buffer c % NBUF
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            mbar_wait(s_bar + 8 * (BAR_FULL + s), (kt / STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t st = s_base + (uint32_t)(s * STAGE);
+                int cc = c;
+#pragma unroll
+                for (int g = 0; g < SLAB / 8; ++g) {
+                    const int b = cc % NBUF;
+                    const bool first = g % CHAIN == 0;
+                    if (first) {
+                        mbar_wait(s_bar + 8 * (BAR_ACCE + b), ((cc / NBUF) & 1) ^ 1);   // the result warps have drained this accumulator
+                        tc_fence_after();
+                    }
+                    const uint32_t d = tmem + (uint32_t)(b * 128);
+                    const uint64_t ah = make_desc(st + g * 4096, 2048, DESC_HI_K);
+                    const uint64_t bh = make_desc(st + OP_BYTES + g * 4096, 2048, DESC_HI_K);
+                    const uint64_t al = make_desc(st + 2 * OP_BYTES + g * 4096, 2048, DESC_HI_K);      // 3xTF32 only
+                    const uint64_t bl = make_desc(st + 3 * OP_BYTES + g * 4096, 2048, DESC_HI_K);
+                    constexpr uint32_t idesc = IDESC_BASE;
+                    if constexpr (PREC != 0) {
+                        umma_tf32(d, al, bh, idesc, first ? 0u : 1u);
+                        umma_tf32(d, ah, bl, idesc, 1u);
+                        umma_tf32(d, ah, bh, idesc, 1u);
+                    } else {
+                        umma_tf32(d, ah, bh, idesc, first ? 0u : 1u);
+                    }
+                    if (g % CHAIN == CHAIN - 1) {
+                        umma_commit(s_bar + 8 * (BAR_ACCF + b));          // this chain is complete
+                        ++cc;
+                    }
+                }
+                umma_commit(s_bar + 8 * (BAR_EMPTY + s));                 // slab consumed -> the producers may refill it
+            }
+            c += (SLAB / 8) / CHAIN;
+            __syncwarp();
+        }
+    } else {
+        // =============================== result warps (thread = output row) ===============================
+        float acc[C];
+#pragma unroll
+        for (int i = 0; i < C; ++i) acc[i] = 0.0f;
+        const uint32_t t_lane = tmem + ((uint32_t)(32 * warp) << 16);
+        for (int c = 0; c < n_chains; ++c) {
+            const int b = c % NBUF;
+            mbar_wait(s_bar + 8 * (BAR_ACCF + b), (c / NBUF) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                uint32_t v[32];
+                tmem_ld32(t_lane + (uint32_t)(b * 128 + h * 32), v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[h * 32 + i] += __uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            mbar_arrive(s_bar + 8 * (BAR_ACCE + b));
+        }
+        const int row = 32 * warp + lane;
+        if constexpr (MODE == 0) {
+            const int m = m0 + row;
+            if (m < a.M) {
+                float4 *o = reinterpret_cast<float4 *>(a.out + (size_t)m * C);
+#pragma unroll
+                for (int i = 0; i < C / 4; ++i) {
+                    float4 v = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                    if (a.bias) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(a.bias + 4 * i);
+                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                    }
+                    o[i] = v;
+                }
+            }
+        } else {
+            const int k = kb * 128 + row;
+            if (k < a.K) {
+                float4 *o = reinterpret_cast<float4 *>(a.part + ((size_t)blockIdx.y * a.K + k) * C);
+#pragma unroll
+                for (int i = 0; i < C / 4; ++i) o[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 128 * NBUF);
+    }
+}
+
+}   // namespace
+
+int bk_tc_set_attrs(void)
+{
+    cudaError_t e = cudaSuccess;
+#define BK_SET(k, n) if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, n)
+    BK_SET((bk_train_gemm_tc_kernel<0, 0, BkConvArgs>), Sizes<0>::SMEM);
+    BK_SET((bk_train_gemm_tc_kernel<0, 1, BkConvArgs>), Sizes<1>::SMEM);
+    BK_SET((bk_train_gemm_tc_kernel<1, 0, BkWgradArgs>), Sizes<0>::SMEM);
+    BK_SET((bk_train_gemm_tc_kernel<1, 1, BkWgradArgs>), Sizes<1>::SMEM);
+#undef BK_SET
+    return e == cudaSuccess ? 0 : -3;
+}
+
+void bk_tc_launch_conv(const BkConvArgs &a, int three_x, cudaStream_t st)
+{
+    const int grid = (a.M + 127) / 128;
+    if (three_x) bk_train_gemm_tc_kernel<0, 1, BkConvArgs><<<grid, N_THREADS, Sizes<1>::SMEM, st>>>(a);
+    else bk_train_gemm_tc_kernel<0, 0, BkConvArgs><<<grid, N_THREADS, Sizes<0>::SMEM, st>>>(a);
+}
+
+void bk_tc_launch_wgrad(const BkWgradArgs &a, int splits, int three_x, cudaStream_t st)
+{
+    const dim3 grid((a.K + 127) / 128, splits);
+    if (three_x) bk_train_gemm_tc_kernel<1, 1, BkWgradArgs><<<grid, N_THREADS, Sizes<1>::SMEM, st>>>(a);
+    else bk_train_gemm_tc_kernel<1, 0, BkWgradArgs><<<grid, N_THREADS, Sizes<0>::SMEM, st>>>(a);
+}

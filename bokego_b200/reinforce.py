@@ -28,7 +28,8 @@ CONV_IDX = (0, 3, 6, 9, 12, 15, 18)     # Conv2d modules inside PolicyNet.conv; 
 HEAD_IDX = 21
 TP_W0, TP_W1, TP_VEC, TP_HEADW, TP_HEADB, TP_COUNT = 0, 102400, 987136, 989824, 989952, 990033   # include/bokego_b200.h
 BN_POSITION, BN_EVAL = 0, 1
-PREC_TF32, PREC_3XTF32, PREC_FFMA = 0, 1, 2
+PREC_TF32, PREC_3XTF32, PREC_FFMA = 0, 1, 2          # warp-level mma.sync kernels / FFMA validation path
+PREC_TC_TF32, PREC_TC_3XTF32 = 4, 5                    # the same GEMMs on tcgen05 (TMEM accumulators)
 MOMENTUM = 0.1
 
 
@@ -108,7 +109,7 @@ def game_major(n_steps, n_games):
 class PolicyTrainer:
     """Device-resident training state of one PolicyNet: flat parameters, gradients, Adam moments, running statistics."""
 
-    def __init__(self, state_dict, device, prec=PREC_3XTF32):
+    def __init__(self, state_dict, device, prec=PREC_TC_3XTF32):
         dev = _lib.require_device(device)
         self.device, self.prec = dev, prec
         self.params = torch.from_numpy(flat_from_tensors(lambda k: state_dict[k])).to(dev)
@@ -356,7 +357,7 @@ def reinforce(pi, pi_opp, optimizer, train_color, **kwargs):
     from .playout import shard_range
     lo, hi = shard_range(bs, rank, world)            # this rank's games (global ids: the random stream is keyed by them)
     nb = hi - lo
-    trainer = PolicyTrainer(pi.state_dict(), dev, prec=kwargs.get("prec", PREC_3XTF32))
+    trainer = PolicyTrainer(pi.state_dict(), dev, prec=kwargs.get("prec", PREC_TC_3XTF32))
     hyper = _adopt_optimizer(trainer, pi, optimizer)
     opp = PackedNet(pi_opp.state_dict(), dev, is_value=False)
     n_mine = (SELFPLAY_MAX_TURN + 2) // 2                      # 36 moves of the training colour in a 72-move game

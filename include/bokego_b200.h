@@ -123,7 +123,9 @@ int bk_tree_finish(int64_t *N, double *V, const double *val, const int32_t *pend
  * running = BatchNorm running statistics, float32 [2][7][128] (means of the 7 layers, then variances).
  * bn_mode 0: every position is normalised with its own statistics -- PolicyNet in train() mode called with one position
  *            per call, which is how policy_dist / policy_sample call it (nnet.py:265-297); 1: running statistics (eval()).
- * prec 0: TF32 tensor-core operands, fp32 accumulation; 1: 3xTF32 split (fp32-grade); 2: FFMA fp32 (validation path).
+ * prec 5: 3xTF32 on tcgen05 (operands split into two TF32 values, TMEM accumulation chains kept short and summed in fp32
+ *         registers: fp32-grade, the default of the host mirror); 4: TF32 on tcgen05; 1 / 0: the same two on warp-level
+ *         mma.sync; 2: FFMA fp32 (validation path).
  * bk_train_forward: planes_u8 uint8 [P][27][81] (bk_encode's planes_u8 == nnet.features values) -> logits float32 [P][81]
  *   (PolicyNet.forward, nnet.py:54-57), probs = SOFT(logits) (nnet.py:16; may be NULL), stats_out (may be NULL) float32
  *   [P][7][2][128] = per-position channel mean and unbiased variance, i.e. what each train-mode call feeds into the running

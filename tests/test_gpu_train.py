@@ -1,14 +1,18 @@
 """REINFORCE row on the device (csrc/bk_train.cu through the C ABI) against the oracle (oracle/train.py: torch CPU autograd over
 the reference's own ops) and against the iteration recorded from the unmodified reference (tests/golden/reinforce.npz).
 
+Precisions: 5 = tcgen05 3xTF32 (default), 4 = tcgen05 TF32, 1 / 0 = the same two on warp-level mma.sync, 2 = FFMA validation path.
 Tolerances (float32 storage everywhere), gradients measured per tensor against the tensor's largest entry:
-  prec 3xTF32 (default) and FFMA (validation path): logits 2e-3 abs; gradients 1e-3.  Typical agreement is 3e-6; the limit is
-      set by ReLU: a pre-activation within round-off of zero takes the other branch in one of the two implementations, and
-      the gradient of that one unit (one term among thousands in every weight-gradient entry) appears or disappears.
-  prec TF32 (opt-in fast mode: operands rounded to 10 mantissa bits -- what cuDNN does by default for the reference on a
+  3xTF32 (5, 1) and FFMA (2): logits 2e-3 abs; gradients 1e-3.  Typical agreement is 3e-6; the limit is set by ReLU: a
+      pre-activation within round-off of zero takes the other branch in one of the two implementations, and the gradient of
+      that one unit (one term among thousands in every weight-gradient entry) appears or disappears.
+  TF32 (4, 0; opt-in fast modes: operands cut to 10 mantissa bits -- what cuDNN does by default for the reference on a
       GPU): logits 5e-2 abs with the same arg-max wherever the margin allows; gradients within 0.2 per tensor and cosine
       similarity of the whole gradient >= 0.99 (rounding errors compound through 14 GEMMs and the per-position
-      normalisation's 1/sigma).
+      normalisation's 1/sigma).  Mode 4 hands raw fp32 words to the tensor core, which TRUNCATES them (a biased error,
+      where mode 0 rounds to nearest): logits 0.25, gradients 0.3.
+  The recorded reference iteration (108 positions, the coefficient on 36 of them) is held to 5e-3 at the worst entry and to
+  1e-4 at the 90th percentile of every tensor: ReLU flips touch few entries, everything else agrees to fp32 accuracy.
   conv biases: their true gradient under per-position BatchNorm is zero (the mean subtraction cancels them); the reference
   and the kernels both produce round-off noise there (|g| < 1e-4 against 0.1 .. 10 elsewhere).
 """
@@ -24,7 +28,7 @@ from oracle import train as ot
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CONV_BIAS = {f"conv.{i}.bias" for i in (0, 3, 6, 9, 12, 15, 18)}
-TOL = {0: (5e-2, 0.2), 1: (2e-3, 1e-3), 2: (2e-3, 1e-3)}      # prec -> (logits abs, gradient relative to the largest entry)
+TOL = {0: (5e-2, 0.2), 1: (2e-3, 1e-3), 2: (2e-3, 1e-3), 4: (0.25, 0.3), 5: (2e-3, 1e-3)}      # prec -> (logits abs, gradient relative to the largest entry)
 
 
 @pytest.fixture(scope="module")
@@ -60,7 +64,7 @@ def _check_grads(mine, want, rel, what=""):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("prec", [2, 1, 0])
+@pytest.mark.parametrize("prec", [2, 1, 0, 5, 4])
 @pytest.mark.parametrize("P", [1, 37, 130])
 def test_train_mode_forward(env, sd17, prec, P):
     """PolicyNet.forward in train() mode, one position per call (nnet.py:265-275): logits, SOFT probabilities and the
@@ -72,21 +76,21 @@ def test_train_mode_forward(env, sd17, prec, P):
     want, means, uvars = ot.train_forward(sd17, planes.astype(np.float32))
     lg = logits.cpu()
     assert float((lg - want).abs().max()) < TOL[prec][0]
-    if prec != 0:
+    if prec not in (0, 4):
         assert bool((lg.argmax(1) == want.argmax(1)).all())
     else:
         top2 = want.topk(2, dim=1).values
-        safe = (top2[:, 0] - top2[:, 1]) > 2 * TOL[0][0]
+        safe = (top2[:, 0] - top2[:, 1]) > 2 * TOL[prec][0]
         assert bool((lg.argmax(1) == want.argmax(1))[safe].all())
-    assert float((probs.cpu() - torch.softmax(want, 1)).abs().max()) < (2e-2 if prec == 0 else 1e-3)
+    assert float((probs.cpu() - torch.softmax(want, 1)).abs().max()) < ({0: 2e-2, 4: 6e-2}.get(prec, 1e-3))
     assert float((probs.cpu().sum(1) - 1).abs().max()) < 1e-5
     st = stats.cpu()
-    tol = 3e-2 if prec == 0 else 1e-3
+    tol = {0: 3e-2, 4: 8e-2}.get(prec, 1e-3)
     assert float(((st[:, :, 0] - means).abs() / (1 + means.abs())).max()) < tol
     assert float(((st[:, :, 1] - uvars).abs() / (1 + uvars.abs())).max()) < tol
 
 
-@pytest.mark.parametrize("prec", [2, 0])
+@pytest.mark.parametrize("prec", [2, 0, 5, 4])
 def test_eval_mode_forward(env, sd17, prec):
     """bn_mode 1 = running statistics: the same function as the fused inference kernel / PolicyNet.eval()"""
     rf, dev, G = env
@@ -97,7 +101,7 @@ def test_eval_mode_forward(env, sd17, prec):
     assert float((logits.cpu() - want).abs().max()) < TOL[prec][0]
 
 
-@pytest.mark.parametrize("prec", [2, 1, 0])
+@pytest.mark.parametrize("prec", [2, 1, 0, 5, 4])
 @pytest.mark.parametrize("bn", ["position", "eval"])
 def test_gradients_vs_autograd(env, sd17, prec, bn):
     rf, dev, G = env
@@ -112,12 +116,12 @@ def test_gradients_vs_autograd(env, sd17, prec, bn):
     nlp = tr.backward(_dev(moves, dev, torch.int16), _dev(coef, dev, torch.float32))
     loss, grads, logits = ot.reinforce_grads(sd17, planes.astype(np.float32), moves, coef, bn)
     want_nlp = -ot.log_prob(logits, torch.from_numpy(moves))
-    assert float((nlp.cpu() - want_nlp).abs().max()) < (5e-2 if prec == 0 else 2e-3)
+    assert float((nlp.cpu() - want_nlp).abs().max()) < ({0: 5e-2, 4: 0.25}.get(prec, 2e-3))
     _check_grads(tr.grads_dict(), grads, TOL[prec][1], f"prec {prec} bn {bn}")
     flat_want = torch.from_numpy(rf.flat_from_tensors(lambda k: grads[k])).double()
     cos = float(torch.dot(tr.grads.cpu().double(), flat_want) / (tr.grads.cpu().double().norm() * flat_want.norm()))
     print(f"[grad cosine] prec {prec} bn {bn}: {cos:.6f}")
-    assert cos >= (0.99 if prec == 0 else 0.999999)
+    assert cos >= (0.99 if prec in (0, 4) else 0.999999)
     # deterministic: a second pass gives the same bits; accumulate adds
     g1 = tr.grads.clone()
     tr.forward(_dev(planes, dev, torch.uint8), mode)
@@ -157,7 +161,7 @@ def test_chunked_step_equals_single_pass(env, sd17):
 
 
 @pytest.mark.parametrize("tag", ["black3", "white2"])
-@pytest.mark.parametrize("prec", [1, 2, 0])
+@pytest.mark.parametrize("prec", [5, 1, 2, 0, 4])
 def test_reference_iteration(env, sd17, tag, prec):
     """one iteration of the unmodified reference's `reinforce` (bin/selfplay.py:59-122): its stream of train-mode calls, the
     games it played and their results go in; p.grad, the parameters after AdamW and the running statistics must come out"""
@@ -177,9 +181,9 @@ def test_reference_iteration(env, sd17, tag, prec):
     planes = _dev(calls[rfrom:], dev, torch.uint8)
     loss = rf.reinforce_step(tr, planes, _dev(mv, dev, torch.int16), _dev(coef, dev, torch.float32))
     want_loss, _, _ = ot.reinforce_grads(sd17, calls[rfrom:].astype(np.float32), mv, coef)
-    assert abs(float(loss) - want_loss) < (5e-2 if prec == 0 else 2e-3) * max(1.0, abs(want_loss))
+    assert abs(float(loss) - want_loss) < ({0: 5e-2, 4: 0.25}.get(prec, 2e-3)) * max(1.0, abs(want_loss))
     grads, post = tr.grads_dict(), tr.state_dict()
-    rel = TOL[prec][1]
+    rel = max(TOL[prec][1], 5e-3)
     for k in rf.param_keys():
         ref, amax = G[f"{tag}/grad/{k}"], float(G[f"{tag}/grad/{k}/absmax"])
         a = grads[k].numpy().ravel()
@@ -187,7 +191,10 @@ def test_reference_iteration(env, sd17, tag, prec):
         if amax < 1e-5:
             assert np.abs(s).max() < 1e-4, k
         else:
-            assert np.abs(s - ref).max() <= rel * amax, (k, np.abs(s - ref).max(), amax)
+            e = np.abs(s - ref)
+            assert e.max() <= rel * amax, (k, e.max(), amax)
+            if prec not in (0, 4):       # fp32-grade modes: almost every entry agrees to 1e-4; ReLU flips touch a few
+                assert np.quantile(e, 0.9) <= 1e-4 * amax, (k, np.quantile(e, 0.9), amax)
             l2 = float(np.sqrt((a.astype(np.float64) ** 2).sum()))
             assert abs(l2 - float(G[f"{tag}/grad/{k}/l2"])) <= rel * float(G[f"{tag}/grad/{k}/l2"]), k
         # AdamW's first step moves an element by lr * g / (|g| + eps): +-lr wherever |g| >> eps, so parameters agree to a
@@ -196,13 +203,13 @@ def test_reference_iteration(env, sd17, tag, prec):
         p = p if p.size <= 4096 else p[::stride]
         d = np.abs(p - G[f"{tag}/post/{k}"])
         assert d.max() <= 2.1e-5, k
-        if k not in CONV_BIAS and prec != 0:
+        if k not in CONV_BIAS and prec not in (0, 4):
             assert (d > 1e-7).mean() < 0.02, (k, (d > 1e-7).mean())
     for i in (1, 4, 7, 10, 13, 16, 19):
         for w in ("running_mean", "running_var"):
             ref = G[f"{tag}/post/conv.{i}.{w}"]
             err = np.abs(post[f"conv.{i}.{w}"].numpy() - ref) / (1 + np.abs(ref))
-            assert err.max() < (3e-2 if prec == 0 else 1e-4), (i, w, err.max())
+            assert err.max() < ({0: 3e-2, 4: 8e-2}.get(prec, 1e-4)), (i, w, err.max())
         assert int(post[f"conv.{i}.num_batches_tracked"]) == int(G[f"{tag}/post/conv.{i}.num_batches_tracked"])
 
 

@@ -48,7 +48,7 @@ def main():
         planes = torch.from_numpy(np.ascontiguousarray(calls[np.arange(P) % len(calls)])).to(dev)
         moves = torch.randint(0, 81, (P,), device=dev).to(torch.int16)
         coef = torch.full((P,), 1.0 / 16, device=dev)
-        for prec, name in ((0, "tf32"), (1, "3xtf32"), (2, "ffma")):
+        for prec, name in ((5, "tc_3xtf32"), (4, "tc_tf32"), (0, "tf32"), (1, "3xtf32"), (2, "ffma")):
             tr = rf.PolicyTrainer(sd17, dev, prec=prec)
             f = timed(lambda: tr.forward(planes), args.iters)
             tr.forward(planes)

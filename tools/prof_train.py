@@ -18,7 +18,7 @@ P = int(sys.argv[1]) if len(sys.argv) > 1 else 576
 planes = torch.from_numpy(np.ascontiguousarray(calls[np.arange(P) % len(calls)])).to(dev)
 moves = torch.randint(0, 81, (P,), device=dev).to(torch.int16)
 coef = torch.full((P,), 1.0 / 16, device=dev)
-for prec in (rf.PREC_3XTF32, rf.PREC_TF32):
+for prec in (rf.PREC_TC_3XTF32, rf.PREC_TC_TF32):
     tr = rf.PolicyTrainer(sd17, dev, prec=prec)
     for _ in range(2):
         rf.reinforce_step(tr, planes, moves, coef)
