@@ -348,13 +348,17 @@ __global__ void bk_train_transpose_kernel(const float *w, float *wd, int n_mat)
     for (int r = threadIdx.y; r < 32; r += 8) dst[(size_t)(bx + r) * C + by + threadIdx.x] = tile[threadIdx.x][r];
 }
 
-// wp[k / 4][co][k % 4] = w[k][co]: the K-major B operand of the tcgen05 kernels (bk_train_tc.cu), n floats in total
-__global__ void bk_train_pack_w_kernel(const float *w, float *wp, int n)
+// The K-major B operand of the tcgen05 kernels (bk_train_tc.cu), split for 3xTF32 once per step instead of once per tile:
+// hi[k / 4][co][k % 4] = rna_tf32(w[k][co]), lo[...] = rna_tf32(w - hi); n floats in total
+__global__ void bk_train_pack_w_kernel(const float *w, float *hi, float *lo, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int k = i / C, co = i - k * C;
-    wp[(size_t)(k >> 2) * (4 * C) + co * 4 + (k & 3)] = w[i];
+    const size_t o = (size_t)(k >> 2) * (4 * C) + co * 4 + (k & 3);
+    const float x = w[i], h = __uint_as_float(f2tf32(x));
+    hi[o] = h;
+    lo[o] = __uint_as_float(f2tf32(x - h));
 }
 
 // ---- BatchNorm (+ ReLU) forward for one position per CTA, thread = channel ----
@@ -550,7 +554,7 @@ __global__ void bk_adamw_kernel(float *p, const float *g, float *m, float *v, si
 
 // ---- workspace (floats) ----
 struct Ws {
-    size_t x0, z[7], a[7], mean[7], rstd[7], da, dz, logits, dlogit, part, dwpart, wd, wpack, wdpack, wpart, total;
+    size_t x0, z[7], a[7], mean[7], rstd[7], da, dz, logits, dlogit, part, dwpart, wd, wpack, wpack_lo, wdpack, wdpack_lo, wpart, total;
     int splits, rows_per_split;
 };
 
@@ -578,8 +582,10 @@ Ws ws_layout(int P)
     w.part = take((size_t)P * 3 * C);
     w.dwpart = take((size_t)P * C);
     w.wd = take((size_t)6 * 9 * C * C);
-    w.wpack = take((size_t)BK_TP_VEC);              // all conv weights, K-major packed (tcgen05 path)
-    w.wdpack = take((size_t)6 * 9 * C * C);         // the transposed weights of the data gradient, packed
+    w.wpack = take((size_t)BK_TP_VEC);              // all conv weights, K-major packed TF32 high parts (tcgen05 path)
+    w.wpack_lo = take((size_t)BK_TP_VEC);           // ... and low parts
+    w.wdpack = take((size_t)6 * 9 * C * C);         // the transposed weights of the data gradient, packed the same way
+    w.wdpack_lo = take((size_t)6 * 9 * C * C);
     const int M = P * NSQ;
     int splits = (M + 1023) / 1024;                 // >= 1024 rows per split, at most 32 splits
     splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
@@ -650,11 +656,12 @@ extern "C" int bk_train_forward(const float *params, const float *running, const
     float *ws = static_cast<float *>(workspace);
     const int n0 = P * NSQ * C0;
     bk_train_pack_kernel<<<(n0 + 255) / 256, 256, 0, st>>>(planes_u8, ws + w.x0, P);
-    if (prec >= 4) bk_train_pack_w_kernel<<<(BK_TP_VEC + 255) / 256, 256, 0, st>>>(params, ws + w.wpack, BK_TP_VEC);
+    if (prec >= 4) bk_train_pack_w_kernel<<<(BK_TP_VEC + 255) / 256, 256, 0, st>>>(params, ws + w.wpack, ws + w.wpack_lo, BK_TP_VEC);
     for (int l = 0; l < 7; ++l) {
         ConvArgs a;
         a.in = l == 0 ? ws + w.x0 : ws + w.a[l - 1];
         a.w = prec >= 4 ? ws + w.wpack + w_off(l) : params + w_off(l);
+        a.w_lo = ws + w.wpack_lo + w_off(l);
         a.bias = params + vec_off(l, 0);
         a.out = ws + w.z[l];
         a.M = P * NSQ;
@@ -683,7 +690,7 @@ extern "C" int bk_train_backward(const float *params, const int16_t *moves, cons
     float *ws = static_cast<float *>(workspace);
     const int M = P * NSQ;
     bk_train_transpose_kernel<<<dim3(4, 4, 54), dim3(32, 8), 0, st>>>(params + BK_TP_W1, ws + w.wd, 54);
-    if (prec >= 4) bk_train_pack_w_kernel<<<(6 * 9 * C * C + 255) / 256, 256, 0, st>>>(ws + w.wd, ws + w.wdpack, 6 * 9 * C * C);
+    if (prec >= 4) bk_train_pack_w_kernel<<<(6 * 9 * C * C + 255) / 256, 256, 0, st>>>(ws + w.wd, ws + w.wdpack, ws + w.wdpack_lo, 6 * 9 * C * C);
     bk_train_head_bwd_kernel<<<P, 128, 0, st>>>(ws + w.logits, ws + w.a[6], params + BK_TP_HEADW, moves, coef, nlp_out,
                                                 ws + w.dlogit, ws + w.da, ws + w.dwpart);
     bk_train_colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(ws + w.dwpart, grads + BK_TP_HEADW, P, C, accumulate);
@@ -709,6 +716,7 @@ extern "C" int bk_train_backward(const float *params, const int16_t *moves, cons
             ConvArgs a;
             a.in = ws + w.dz;
             a.w = (prec >= 4 ? ws + w.wdpack : ws + w.wd) + (size_t)(l - 1) * 9 * C * C;
+            a.w_lo = ws + w.wdpack_lo + (size_t)(l - 1) * 9 * C * C;
             a.bias = nullptr;
             a.out = ws + w.da;
             a.M = M;

@@ -11,6 +11,7 @@ struct BkConvArgs {
     const float *in, *w, *bias;
     float *out;
     int M, Cin, R, sign;
+    const float *w_lo;   /* tcgen05 path only: w = packed TF32 high parts [k / 4][co][k % 4], w_lo = the low parts (3xTF32) */
 };
 
 /* weight gradient: part[split][k][co] = sum over the split's rows m of act[m shifted by tap(k)][ci(k)] * dz[m][co] */

@@ -15,7 +15,8 @@
 // MN-major TF32 operands without swizzle are not accepted by the tensor core (tools/probes/tc_probe.cu: the MMA returns zeros),
 // so whatever arrives with its GEMM-M / GEMM-N index contiguous is turned on the way in:
 //   conv:  A = gathered activation rows [m][ci] -- K-major as they come, 16-byte cp.async;
-//          B = weights, repacked once per step by bk_train_pack_w_kernel into [k / 4][co][k % 4] -- 16-byte cp.async;
+//          B = weights, repacked and split into TF32 high / low parts once per step by bk_train_pack_w_kernel into
+//              [k / 4][co][k % 4]: a slab is 16 KiB contiguous and already in operand layout -- one cp.async.bulk per part;
 //   wgrad: A = activation rows [m][k index] and B = dZ rows [m][co], reduction over m: the producers load 4 rows x 4 columns into
 //          registers, transpose the 4 x 4 block and store it (the 3xTF32 split happens in the same registers).
 #include <cuda_runtime.h>
@@ -39,7 +40,7 @@ template <int PREC>
 struct Sizes {
     static constexpr int STAGE = (PREC ? 4 : 2) * OP_BYTES;          // A_hi, B_hi (, A_lo, B_lo)
     static constexpr int STAGES = PREC ? 3 : 6;                      // 192 KiB of operand stages either way
-    static constexpr int LOOKAHEAD = STAGES - 1;                     // slabs a producer keeps in flight (conv: cp.async groups)
+    static constexpr int LOOKAHEAD = PREC ? 1 : 3;                   // slabs of cp.async a producer keeps in flight; the other stages are slack for the MMAs
     static constexpr int CHAIN = PREC ? 1 : 4;                       // K steps (of 8) accumulated in the tensor core before the fp32 add
     static constexpr int SMEM = STAGES * STAGE + 256;
 };
@@ -81,6 +82,17 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *g, bool val
 {
     const int sz = valid ? 16 : 0;                            // 0 source bytes = 16 bytes of zeros
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// contiguous global -> shared bulk copy (async proxy); its bytes complete on the barrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -175,7 +187,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(s_bar + 8 * (BAR_FULL + s), 128);    // every producer thread
+            mbar_init(s_bar + 8 * (BAR_FULL + s), MODE == 0 ? 129 : 128);    // every producer thread (+ the weight slab's expect_tx)
             mbar_init(s_bar + 8 * (BAR_EMPTY + s), 1);     // tcgen05.commit
         }
         for (int b = 0; b < NBUF; ++b) {
@@ -224,8 +236,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
                     const bool ok = rvalid[q] && (unsigned)x < 9u && (unsigned)y < 9u;
                     const float *src = ok ? a.in + ((size_t)(rbase[q] + 9 * x + y) * a.Cin + c0 + 4 * kc) : a.in;
                     cp_async16(st + off[i], src, ok);
-                    // packed weights [k / 4][co][4]: chunk (kc, co) of this slab
-                    cp_async16(st + OP_BYTES + off[i], a.w + ((size_t)(k0 / 4 + kc) * C + (pw + 4 * q) * 8 + r8) * 4, true);
+                }
+                if (ptid == 0) {
+                    // the weight slab: 8 K chunks x 128 co x 16 bytes, contiguous in the packed (and pre-split) weights and
+                    // already in the K-major operand layout: one bulk copy per part, no thread touches it
+                    const uint32_t bar = s_bar + 8 * (BAR_FULL + kt % STAGES);
+                    mbar_arrive_expect_tx(bar, PREC ? 2u * OP_BYTES : (uint32_t)OP_BYTES);
+                    bulk_g2s(st + OP_BYTES, a.w + (size_t)(k0 / 4) * (4 * C), OP_BYTES, bar);
+                    if (PREC) bulk_g2s(st + 3 * OP_BYTES, a.w_lo + (size_t)(k0 / 4) * (4 * C), OP_BYTES, bar);
                 }
             };
             auto publish = [&](int kt) {
@@ -233,8 +251,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
                 if constexpr (PREC != 0) {
                     uint8_t *st = smem + s * STAGE;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint32_t o = (i < 8 ? 0u : (uint32_t)OP_BYTES) + off[i & 7];
+                    for (int i = 0; i < 8; ++i) {                 // the activation chunks this thread gathered
+                        const uint32_t o = off[i];
                         float4 *hp = reinterpret_cast<float4 *>(st + o);
                         const float4 v = *hp;
                         float4 h, l;
@@ -268,9 +286,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
             const bool tap_ok = tap < a.R * a.R;
             const int ti = tap / a.R;
             const int dx = ti - half, dy = tap - ti * a.R - half;
-            for (int kt = 0; kt < KT; ++kt) {
-                const int s = kt % STAGES;
-                float4 va[2][4], vb[2][4];
+            float4 va[2][4], vb[2][4], na[2][4], nb[2][4];
+            auto fetch = [&](int kt, float4 (&A)[2][4], float4 (&B)[2][4]) {
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int mc = pw + 4 * u;
@@ -281,21 +298,30 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
                         const int p = m / NSQ, sq = m - p * NSQ;
                         const int x = sq / 9 + dx, y = sq - 9 * (sq / 9) + dy;
                         const bool ok = in_rows && tap_ok && (unsigned)x < 9u && (unsigned)y < 9u;
-                        va[u][r] = ok ? __ldg(reinterpret_cast<const float4 *>(a.act + ((size_t)(p * NSQ + 9 * x + y) * a.Cin + ci)))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-                        vb[u][r] = in_rows ? __ldg(reinterpret_cast<const float4 *>(a.dz + (size_t)m * C + 4 * j))
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                        A[u][r] = ok ? __ldg(reinterpret_cast<const float4 *>(a.act + ((size_t)(p * NSQ + 9 * x + y) * a.Cin + ci)))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                        B[u][r] = in_rows ? __ldg(reinterpret_cast<const float4 *>(a.dz + (size_t)m * C + 4 * j))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
+            };
+            // (starting each lane at a different column of its block makes the 16-byte stores below conflict-free on paper; measured,
+            // the kernel was 25 % slower with it, so every lane stores its columns in order)
+            constexpr int rot = 0;
+            if (KT > 0) fetch(0, va, vb);
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                if (kt + 1 < KT) fetch(kt + 1, na, nb);           // the next slab's loads are in flight while this one is stored
                 if (kt >= STAGES) mbar_wait(s_bar + 8 * (BAR_EMPTY + s), ((kt / STAGES) & 1) ^ 1);
                 uint8_t *st = smem + s * STAGE;
                 auto put = [&](const float4 (&v)[4], uint32_t base) {
                     // column c of the block = the four rows' c-th components: one 16-byte K chunk of row (4 j + c)
-                    const float cx[4][4] = {{v[0].x, v[1].x, v[2].x, v[3].x}, {v[0].y, v[1].y, v[2].y, v[3].y},
-                                            {v[0].z, v[1].z, v[2].z, v[3].z}, {v[0].w, v[1].w, v[2].w, v[3].w}};
+                    const float4 c0 = make_float4(v[0].x, v[1].x, v[2].x, v[3].x), c1 = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+                    const float4 c2 = make_float4(v[0].z, v[1].z, v[2].z, v[3].z), c3 = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float4 h = make_float4(cx[c][0], cx[c][1], cx[c][2], cx[c][3]);
+                    for (int t = 0; t < 4; ++t) {
+                        const int c = (t + rot) & 3;
+                        float4 h = c == 0 ? c0 : (c == 1 ? c1 : (c == 2 ? c2 : c3));
                         if constexpr (PREC != 0) {
                             float4 l;
                             const float4 x = h;
@@ -313,6 +339,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
                 }
                 fence_proxy_async();
                 mbar_arrive(s_bar + 8 * (BAR_FULL + s));
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        va[u][r] = na[u][r];
+                        vb[u][r] = nb[u][r];
+                    }
             }
         }
     } else if (warp == WARP_MMA) {
