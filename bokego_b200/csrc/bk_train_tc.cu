@@ -31,23 +31,29 @@ constexpr int NSQ = 81;
 constexpr int SLAB = 32;                 // reduction depth of one stage
 constexpr int MAX_STAGES = 6;
 constexpr int NBUF = 4;                  // TMEM accumulators of 128 columns (all 512 columns)
-constexpr int OP_BYTES = 128 * SLAB * 4; // one operand tile of a stage: 16 KiB
 constexpr int N_THREADS = 288;
 constexpr int WARP_MMA = 8;
 enum { BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_ACCF = 2 * MAX_STAGES, BAR_ACCE = 2 * MAX_STAGES + NBUF, N_BARS = 2 * MAX_STAGES + 2 * NBUF };
 
-template <int PREC>
+template <int MODE, int PREC>
 struct Sizes {
+    // Byte distance between consecutive 8-row core matrices.  The conv operands are written one core matrix per quarter
+    // warp (dense, 128 B); the weight-gradient operands are written transposed, one row of every second core matrix per
+    // lane, and a pitch of 144 B spreads those 16-byte stores over all banks (ncu: 75 % of the wavefronts of the dense
+    // version were bank conflicts).
+    static constexpr int SBO = MODE == 0 ? 128 : 144;
+    static constexpr int LBO = 16 * SBO;                             // between the K chunks (of 4) of a 128-row operand
+    static constexpr int OP_BYTES = (SLAB / 4) * LBO;                // one operand tile of a stage: 16 / 18 KiB
     static constexpr int STAGE = (PREC ? 4 : 2) * OP_BYTES;          // A_hi, B_hi (, A_lo, B_lo)
-    static constexpr int STAGES = PREC ? 3 : 6;                      // 192 KiB of operand stages either way
+    static constexpr int STAGES = PREC ? 3 : 6;
     static constexpr int LOOKAHEAD = PREC ? 1 : 3;                   // slabs of cp.async a producer keeps in flight; the other stages are slack for the MMAs
     static constexpr int CHAIN = PREC ? 1 : 4;                       // K steps (of 8) accumulated in the tensor core before the fp32 add
     static constexpr int SMEM = STAGES * STAGE + 256;
+    static constexpr uint32_t DESC_HI = ((uint32_t)SBO >> 4) | (1u << 14);   // SBO, descriptor version 1
 };
 
 // instruction descriptor: D = f32 (bit 4), A = B = TF32 (2 at bits 7, 10), majors at bits 15 / 16 (1 = MN-major), N >> 3 at 17, M >> 4 at 24
 constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-constexpr uint32_t DESC_HI_K = (128u >> 4) | (1u << 14);                 // SBO 128 B, descriptor version 1
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
@@ -164,8 +170,10 @@ template <int MODE, int PREC, typename Args>
 __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Args a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr int STAGE = Sizes<PREC>::STAGE, STAGES = Sizes<PREC>::STAGES, LOOKAHEAD = Sizes<PREC>::LOOKAHEAD;
-    constexpr int CHAIN = Sizes<PREC>::CHAIN;
+    using SZ = Sizes<MODE, PREC>;
+    constexpr int STAGE = SZ::STAGE, STAGES = SZ::STAGES, LOOKAHEAD = SZ::LOOKAHEAD, CHAIN = SZ::CHAIN;
+    constexpr int OP_BYTES = SZ::OP_BYTES, SBO = SZ::SBO, LBO = SZ::LBO;
+    constexpr uint32_t DESC_HI_K = SZ::DESC_HI;
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_bar = s_base + STAGES * STAGE;
     const uint32_t s_tmem = s_bar + 8 * N_BARS;
@@ -211,7 +219,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
             const int r8 = lane & 7, q4 = lane >> 3;
             uint32_t off[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) off[i] = (uint32_t)(((i >> 2) * 4 + q4) * 2048 + ((pw + 4 * (i & 3)) * 8 + r8) * 16);
+            for (int i = 0; i < 8; ++i) off[i] = (uint32_t)(((i >> 2) * 4 + q4) * LBO + ((pw + 4 * (i & 3)) * 8 + r8) * 16);
             int rbase[4], rx[4], ry[4];
             bool rvalid[4];
 #pragma unroll
@@ -327,15 +335,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
                             const float4 x = h;
                             h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
                             l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
-                            *reinterpret_cast<float4 *>(st + 2 * OP_BYTES + base + (4 * j + c) * 16) = l;
+                            *reinterpret_cast<float4 *>(st + 2 * OP_BYTES + base + ((4 * j + c) >> 3) * SBO + ((4 * j + c) & 7) * 16) = l;
                         }
-                        *reinterpret_cast<float4 *>(st + base + (4 * j + c) * 16) = h;
+                        *reinterpret_cast<float4 *>(st + base + ((4 * j + c) >> 3) * SBO + ((4 * j + c) & 7) * 16) = h;
                     }
                 };
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    put(va[u], (uint32_t)((pw + 4 * u) * 2048));
-                    put(vb[u], (uint32_t)(OP_BYTES + (pw + 4 * u) * 2048));
+                    put(va[u], (uint32_t)((pw + 4 * u) * LBO));
+                    put(vb[u], (uint32_t)(OP_BYTES + (pw + 4 * u) * LBO));
                 }
                 fence_proxy_async();
                 mbar_arrive(s_bar + 8 * (BAR_FULL + s));
@@ -367,10 +375,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
                         tc_fence_after();
                     }
                     const uint32_t d = tmem + (uint32_t)(b * 128);
-                    const uint64_t ah = make_desc(st + g * 4096, 2048, DESC_HI_K);
-                    const uint64_t bh = make_desc(st + OP_BYTES + g * 4096, 2048, DESC_HI_K);
-                    const uint64_t al = make_desc(st + 2 * OP_BYTES + g * 4096, 2048, DESC_HI_K);      // 3xTF32 only
-                    const uint64_t bl = make_desc(st + 3 * OP_BYTES + g * 4096, 2048, DESC_HI_K);
+                    const uint64_t ah = make_desc(st + g * 2 * LBO, LBO, DESC_HI_K);
+                    const uint64_t bh = make_desc(st + OP_BYTES + g * 2 * LBO, LBO, DESC_HI_K);
+                    const uint64_t al = make_desc(st + 2 * OP_BYTES + g * 2 * LBO, LBO, DESC_HI_K);      // 3xTF32 only
+                    const uint64_t bl = make_desc(st + 3 * OP_BYTES + g * 2 * LBO, LBO, DESC_HI_K);
                     constexpr uint32_t idesc = IDESC_BASE;
                     if constexpr (PREC != 0) {
                         umma_tf32(d, al, bh, idesc, first ? 0u : 1u);
@@ -448,10 +456,10 @@ int bk_tc_set_attrs(void)
 {
     cudaError_t e = cudaSuccess;
 #define BK_SET(k, n) if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, n)
-    BK_SET((bk_train_gemm_tc_kernel<0, 0, BkConvArgs>), Sizes<0>::SMEM);
-    BK_SET((bk_train_gemm_tc_kernel<0, 1, BkConvArgs>), Sizes<1>::SMEM);
-    BK_SET((bk_train_gemm_tc_kernel<1, 0, BkWgradArgs>), Sizes<0>::SMEM);
-    BK_SET((bk_train_gemm_tc_kernel<1, 1, BkWgradArgs>), Sizes<1>::SMEM);
+    BK_SET((bk_train_gemm_tc_kernel<0, 0, BkConvArgs>), (Sizes<0, 0>::SMEM));
+    BK_SET((bk_train_gemm_tc_kernel<0, 1, BkConvArgs>), (Sizes<0, 1>::SMEM));
+    BK_SET((bk_train_gemm_tc_kernel<1, 0, BkWgradArgs>), (Sizes<1, 0>::SMEM));
+    BK_SET((bk_train_gemm_tc_kernel<1, 1, BkWgradArgs>), (Sizes<1, 1>::SMEM));
 #undef BK_SET
     return e == cudaSuccess ? 0 : -3;
 }
@@ -459,13 +467,13 @@ int bk_tc_set_attrs(void)
 void bk_tc_launch_conv(const BkConvArgs &a, int three_x, cudaStream_t st)
 {
     const int grid = (a.M + 127) / 128;
-    if (three_x) bk_train_gemm_tc_kernel<0, 1, BkConvArgs><<<grid, N_THREADS, Sizes<1>::SMEM, st>>>(a);
-    else bk_train_gemm_tc_kernel<0, 0, BkConvArgs><<<grid, N_THREADS, Sizes<0>::SMEM, st>>>(a);
+    if (three_x) bk_train_gemm_tc_kernel<0, 1, BkConvArgs><<<grid, N_THREADS, Sizes<0, 1>::SMEM, st>>>(a);
+    else bk_train_gemm_tc_kernel<0, 0, BkConvArgs><<<grid, N_THREADS, Sizes<0, 0>::SMEM, st>>>(a);
 }
 
 void bk_tc_launch_wgrad(const BkWgradArgs &a, int splits, int three_x, cudaStream_t st)
 {
     const dim3 grid((a.K + 127) / 128, splits);
-    if (three_x) bk_train_gemm_tc_kernel<1, 1, BkWgradArgs><<<grid, N_THREADS, Sizes<1>::SMEM, st>>>(a);
-    else bk_train_gemm_tc_kernel<1, 0, BkWgradArgs><<<grid, N_THREADS, Sizes<0>::SMEM, st>>>(a);
+    if (three_x) bk_train_gemm_tc_kernel<1, 1, BkWgradArgs><<<grid, N_THREADS, Sizes<1, 1>::SMEM, st>>>(a);
+    else bk_train_gemm_tc_kernel<1, 0, BkWgradArgs><<<grid, N_THREADS, Sizes<1, 0>::SMEM, st>>>(a);
 }
