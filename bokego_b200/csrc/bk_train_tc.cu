@@ -1,7 +1,8 @@
 // bk_train_tc.cu -- the three GEMMs of the REINFORCE step (forward conv, data gradient, weight gradient; see bk_train.cu) on the
 // 5th-generation tensor cores: tcgen05.mma kind::tf32 issued by one thread, operands staged in shared memory, accumulators in TMEM.
 //
-// One CTA computes a 128 x 128 output tile.  Warp roles (288 threads):
+// One CTA computes a 128 x 128 output tile.  Warp roles (288 threads; measured alternatives that were slower: 8 + 8 producer / result warps
+// at 96 registers, 8 result warps on column halves, 16-deep slabs in six stages for 3xTF32):
 //   warps 4-7  producers: gather the operands of a 32-deep slab with 16-byte cp.async (zero fill for taps that leave the board),
 //              and -- in 3xTF32 mode -- split every value into a TF32 high part and a TF32 low part (hi = rna(x), lo = rna(x - hi));
 //   warp  8    issues the MMAs of a slab (4 K steps of 8; 3xTF32: lo*hi, hi*lo, hi*hi per step) and commits the slab's buffers back;
