@@ -4,7 +4,8 @@
 // One CTA computes a 128 x 128 output tile.  Warp roles (288 threads; measured alternatives that were slower: 8 + 8 producer / result warps
 // at 96 registers, 8 result warps on column halves, 16-deep slabs in six stages for 3xTF32):
 //   warps 4-7  producers: gather the operands of a 32-deep slab with 16-byte cp.async (zero fill for taps that leave the board),
-//              and -- in 3xTF32 mode -- split every value into a TF32 high part and a TF32 low part (hi = rna(x), lo = rna(x - hi));
+//              and -- in 3xTF32 mode -- split every value into a TF32 high part and a TF32 low part (hi = x cut to 10 mantissa
+//              bits, lo = the exact remainder cut the same way: two ANDs, where cvt.rna costs a sequence of instructions);
 //   warp  8    issues the MMAs of a slab (4 K steps of 8; 3xTF32: lo*hi, hi*lo, hi*hi per step) and commits the slab's buffers back;
 //   warps 0-3  own the result: thread = output row.  The tensor core's fp32 accumulation truncates every time it adds to the
 //              accumulator (measured: chains of 48 MMAs leave errors of 1e-3 in the data gradient, whose sums cancel heavily), so in
@@ -161,6 +162,9 @@ __device__ __forceinline__ float tf32_rna(float x)
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// the producers' split: high part = the value cut to TF32 (what the tensor core would do with the raw word), low part = the exact
+// remainder cut to TF32.  One AND each instead of cvt.rna's multi-instruction sequence; what is dropped is below 2^-21 of the value.
+__device__ __forceinline__ float tf32_cut(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t hi)
 {
     return ((uint64_t)hi << 32) | (((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16));
@@ -265,8 +269,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
                         float4 *hp = reinterpret_cast<float4 *>(st + o);
                         const float4 v = *hp;
                         float4 h, l;
-                        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                        h.x = tf32_cut(v.x); h.y = tf32_cut(v.y); h.z = tf32_cut(v.z); h.w = tf32_cut(v.w);
+                        l.x = tf32_cut(v.x - h.x); l.y = tf32_cut(v.y - h.y); l.z = tf32_cut(v.z - h.z); l.w = tf32_cut(v.w - h.w);
                         *hp = h;
                         *reinterpret_cast<float4 *>(st + 2 * OP_BYTES + o) = l;
                     }
@@ -334,8 +338,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
                         if constexpr (PREC != 0) {
                             float4 l;
                             const float4 x = h;
-                            h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
-                            l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+                            h.x = tf32_cut(x.x); h.y = tf32_cut(x.y); h.z = tf32_cut(x.z); h.w = tf32_cut(x.w);
+                            l.x = tf32_cut(x.x - h.x); l.y = tf32_cut(x.y - h.y); l.z = tf32_cut(x.z - h.z); l.w = tf32_cut(x.w - h.w);
                             *reinterpret_cast<float4 *>(st + 2 * OP_BYTES + base + ((4 * j + c) >> 3) * SBO + ((4 * j + c) & 7) * 16) = l;
                         }
                         *reinterpret_cast<float4 *>(st + base + ((4 * j + c) >> 3) * SBO + ((4 * j + c) & 7) * 16) = h;
