@@ -270,3 +270,30 @@ def test_reinforce_loop(env, sd17, sd19, color):
     assert (planes[0, :, 0].sum(1) == 0).all()                 # plane 0 = stones of the player to move: none at pi's first move
     assert (planes[0, :, 1].sum(1) == (1 if color == "white" else 0)).all()   # plane 1 = opponent stones
     assert (planes[-1, :, 2].sum(1) < 50).all()                # plane 2 = empty squares, at the training colour's last move
+
+
+def test_properties_at_scale(env, sd17):
+    """size-independent properties on a batch the oracle would take minutes for (1,024 positions, two forward/backward chunks):
+    the gradient is linear in the coefficients -- scaling them by 2 scales every entry by exactly 2 (a power of two: bit for bit) --
+    positions with a zero coefficient contribute nothing, and the order of the positions only changes the order of the sums"""
+    rf, dev, G = env
+    P = 1024
+    calls = np.concatenate([G["black3/calls"], G["white2/calls"]])
+    planes = _dev(calls[np.arange(P) % len(calls)], dev, torch.uint8)
+    rng = np.random.default_rng(11)
+    moves = _dev(rng.integers(0, 81, P), dev, torch.int16)
+    coef = _dev(rng.uniform(-1, 1, P), dev, torch.float32)
+    coef[rng.integers(0, P, 300)] = 0.0
+    tr = rf.PolicyTrainer(sd17, dev)
+    rf.compute_grads(tr, planes, moves, coef, chunk=512)
+    g1 = tr.grads.clone()
+    assert bool(torch.isfinite(g1).all()) and float(g1.abs().max()) > 0
+    rf.compute_grads(tr, planes, moves, 2 * coef, chunk=512)
+    assert torch.equal(tr.grads, 2 * g1)
+    keep = torch.nonzero(coef != 0).reshape(-1)
+    rf.compute_grads(tr, planes[keep].contiguous(), moves[keep].contiguous(), coef[keep].contiguous(), chunk=512)
+    scale = float(g1.abs().max())
+    assert float((tr.grads - g1).abs().max()) <= 2e-5 * scale
+    perm = torch.from_numpy(rng.permutation(P)).to(dev)
+    rf.compute_grads(tr, planes[perm].contiguous(), moves[perm].contiguous(), coef[perm].contiguous(), chunk=512)
+    assert float((tr.grads - g1).abs().max()) <= 2e-5 * scale
