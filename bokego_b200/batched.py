@@ -230,13 +230,15 @@ class HostEvaluator:
             s["h_out"].copy_(s["d_out"], non_blocking=True)
             return i
         # rotated buffers: copy-in and copy-out run on their own streams, ordered against the kernels by events
-        self.copy_in.wait_event(s["computed"])            # the kernels that last read this slot's inputs are done
+        self.copy_in.wait_event(s["computed"])            # the kernels that last read this slot's inputs / planes are done
         with torch.cuda.stream(self.copy_in):
             s["d_in"].copy_(s["h_in"], non_blocking=True)
+            # the encoder runs behind the copy on the same side stream: its small CTAs fit next to the persistent conv
+            # CTAs of the previous call, so the feature planes are ready when that call's forward ends
+            features_batch(s["pos"], fresh_libs=True, want=("conv",), out={"conv": s["conv"]})
             s["in_done"].record()
         main.wait_event(s["in_done"])
         main.wait_event(s["out_done"])                    # the previous results of this slot have left the device
-        features_batch(s["pos"], fresh_libs=True, want=("conv",), out={"conv": s["conv"]})
         policy_value_batch(s["conv"], self.B, self.policy, self.value, want_logits=False, probs_out=s["d_probs"],
                            value_out=s["d_value"])
         s["computed"].record()
