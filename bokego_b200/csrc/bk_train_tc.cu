@@ -2,7 +2,8 @@
 // 5th-generation tensor cores: tcgen05.mma kind::tf32 issued by one thread, operands staged in shared memory, accumulators in TMEM.
 //
 // One CTA computes a 128 x 128 output tile.  Warp roles (288 threads; measured alternatives that were slower: 8 + 8 producer / result warps
-// at 96 registers, 8 result warps on column halves, 16-deep slabs in six stages for 3xTF32):
+// at 96 registers, 8 result warps on column halves, 16-deep slabs in six stages for 3xTF32, a separate raw landing ring with three
+// slabs of gathers in flight and two operand stages for 3xTF32):
 //   warps 4-7  producers: gather the operands of a 32-deep slab with 16-byte cp.async (zero fill for taps that leave the board),
 //              and -- in 3xTF32 mode -- split every value into a TF32 high part and a TF32 low part (hi = x cut to 10 mantissa
 //              bits, lo = the exact remainder cut the same way: two ANDs, where cvt.rna costs a sequence of instructions);
