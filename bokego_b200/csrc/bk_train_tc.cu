@@ -33,6 +33,9 @@ constexpr int C = 128;
 constexpr int NSQ = 81;
 constexpr int SLAB = 32;                 // reduction depth of one stage
 constexpr int MAX_STAGES = 6;
+#ifndef BK_TC_CHAIN
+#define BK_TC_CHAIN 1    // K steps per 3xTF32 accumulation chain.  Measured: 2 and 4 (one slab) are as accurate (1e-6) and 5 % faster,
+#endif                   // 16 (four slabs, 48 MMAs) leaves 1e-3 in the early layers' gradients; 1 keeps the largest margin
 constexpr int NBUF = 4;                  // TMEM accumulators of 128 columns (all 512 columns)
 constexpr int N_THREADS = 288;
 constexpr int WARP_MMA = 8;
@@ -50,7 +53,7 @@ struct Sizes {
     static constexpr int STAGE = (PREC ? 4 : 2) * OP_BYTES;          // A_hi, B_hi (, A_lo, B_lo)
     static constexpr int STAGES = PREC ? 3 : 6;
     static constexpr int LOOKAHEAD = PREC ? 1 : 3;                   // slabs of cp.async a producer keeps in flight; the other stages are slack for the MMAs
-    static constexpr int CHAIN = PREC ? 1 : 4;                       // K steps (of 8) accumulated in the tensor core before the fp32 add
+    static constexpr int CHAIN = PREC ? BK_TC_CHAIN : 4;                       // K steps (of 8) accumulated in the tensor core before the fp32 add
     static constexpr int SMEM = STAGES * STAGE + 256;
     static constexpr uint32_t DESC_HI = ((uint32_t)SBO >> 4) | (1u << 14);   // SBO, descriptor version 1
 };
