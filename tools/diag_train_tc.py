@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Error profile (max / 90th percentile / median per tensor) of the tcgen05 and mma.sync 3xTF32 gradients against the FFMA path on the
+recorded reference iteration (black, 3 games): the instrument that showed long TMEM accumulation chains losing 1e-3 in the early layers."""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

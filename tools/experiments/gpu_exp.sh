@@ -1,4 +1,5 @@
 #!/bin/bash
+# stress run of the two stress-clean variants of the tile-by-tile epilogue experiment (apply tile_tail_epilogue_overlap.patch first)
 for k in 1 2; do
   BK_NVCC_DEFS="-DBK_EXP=$k" python -m bokego_b200.build --force > /dev/null 2>&1
   echo "=== BK_EXP=$k"
