@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libbokego_b200.so")
+SO_PATH = os.environ.get("BOKEGO_B200_SO") or os.path.join(_HERE, "libbokego_b200.so")   # the override is for measurement builds (tools/)
 
 _lib = None
 _checked_devices = set()

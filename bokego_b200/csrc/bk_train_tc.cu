@@ -33,6 +33,11 @@ constexpr int C = 128;
 constexpr int NSQ = 81;
 constexpr int SLAB = 32;                 // reduction depth of one stage
 constexpr int MAX_STAGES = 6;
+// measurement only (results are wrong): 1 = no 3xTF32 split in the conv producers, 2 = no gathers / loads of the A and dZ operands,
+// 4 = no MMAs (commits only), 8 = no TMEM read-out / adds in the result warps, 16 = no weight bulk copies
+#ifndef BK_TC_DIAG
+#define BK_TC_DIAG 0
+#endif
 #ifndef BK_TC_CHAIN
 #define BK_TC_CHAIN 1    // K steps per 3xTF32 accumulation chain.  Measured: 2 and 4 (one slab) are as accurate (1e-6) and 5 % faster,
 #endif                   // 16 (four slabs, 48 MMAs) leaves 1e-3 in the early layers' gradients; 1 keeps the largest margin
@@ -160,12 +165,6 @@ __device__ __forceinline__ bool elect_one()
         : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ float tf32_rna(float x)
-{
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
 // the producers' split: high part = the value cut to TF32 (what the tensor core would do with the raw word), low part = the exact
 // remainder cut to TF32.  One AND each instead of cvt.rna's multi-instruction sequence; what is dropped is below 2^-21 of the value.
 __device__ __forceinline__ float tf32_cut(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
@@ -252,20 +251,24 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
                     const int x = rx[q] + dx, y = ry[q] + dy;
                     const bool ok = rvalid[q] && (unsigned)x < 9u && (unsigned)y < 9u;
                     const float *src = ok ? a.in + ((size_t)(rbase[q] + 9 * x + y) * a.Cin + c0 + 4 * kc) : a.in;
-                    cp_async16(st + off[i], src, ok);
+                    if (!(BK_TC_DIAG & 2)) cp_async16(st + off[i], src, ok);
                 }
                 if (ptid == 0) {
                     // the weight slab: 8 K chunks x 128 co x 16 bytes, contiguous in the packed (and pre-split) weights and
                     // already in the K-major operand layout: one bulk copy per part, no thread touches it
                     const uint32_t bar = s_bar + 8 * (BAR_FULL + kt % STAGES);
-                    mbar_arrive_expect_tx(bar, PREC ? 2u * OP_BYTES : (uint32_t)OP_BYTES);
-                    bulk_g2s(st + OP_BYTES, a.w + (size_t)(k0 / 4) * (4 * C), OP_BYTES, bar);
-                    if (PREC) bulk_g2s(st + 3 * OP_BYTES, a.w_lo + (size_t)(k0 / 4) * (4 * C), OP_BYTES, bar);
+                    if (BK_TC_DIAG & 16) {
+                        mbar_arrive(bar);
+                    } else {
+                        mbar_arrive_expect_tx(bar, PREC ? 2u * OP_BYTES : (uint32_t)OP_BYTES);
+                        bulk_g2s(st + OP_BYTES, a.w + (size_t)(k0 / 4) * (4 * C), OP_BYTES, bar);
+                        if (PREC) bulk_g2s(st + 3 * OP_BYTES, a.w_lo + (size_t)(k0 / 4) * (4 * C), OP_BYTES, bar);
+                    }
                 }
             };
             auto publish = [&](int kt) {
                 const int s = kt % STAGES;
-                if constexpr (PREC != 0) {
+                if constexpr (PREC != 0 && !(BK_TC_DIAG & 1)) {
                     uint8_t *st = smem + s * STAGE;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {                 // the activation chunks this thread gathered
@@ -315,9 +318,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
                         const int p = m / NSQ, sq = m - p * NSQ;
                         const int x = sq / 9 + dx, y = sq - 9 * (sq / 9) + dy;
                         const bool ok = in_rows && tap_ok && (unsigned)x < 9u && (unsigned)y < 9u;
-                        A[u][r] = ok ? __ldg(reinterpret_cast<const float4 *>(a.act + ((size_t)(p * NSQ + 9 * x + y) * a.Cin + ci)))
+                        A[u][r] = (ok && !(BK_TC_DIAG & 2)) ? __ldg(reinterpret_cast<const float4 *>(a.act + ((size_t)(p * NSQ + 9 * x + y) * a.Cin + ci)))
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-                        B[u][r] = in_rows ? __ldg(reinterpret_cast<const float4 *>(a.dz + (size_t)m * C + 4 * j))
+                        B[u][r] = (in_rows && !(BK_TC_DIAG & 2)) ? __ldg(reinterpret_cast<const float4 *>(a.dz + (size_t)m * C + 4 * j))
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
@@ -389,7 +392,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
                     const uint64_t al = make_desc(st + 2 * OP_BYTES + g * 2 * LBO, LBO, DESC_HI_K);      // 3xTF32 only
                     const uint64_t bl = make_desc(st + 3 * OP_BYTES + g * 2 * LBO, LBO, DESC_HI_K);
                     constexpr uint32_t idesc = IDESC_BASE;
-                    if constexpr (PREC != 0) {
+                    if constexpr ((BK_TC_DIAG & 4) != 0) {
+                    } else if constexpr (PREC != 0) {
                         umma_tf32(d, al, bh, idesc, first ? 0u : 1u);
                         umma_tf32(d, ah, bl, idesc, 1u);
                         umma_tf32(d, ah, bh, idesc, 1u);
@@ -419,6 +423,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
                 uint32_t v[32];
+                if (BK_TC_DIAG & 8) continue;
                 tmem_ld32(t_lane + (uint32_t)(b * 128 + h * 32), v);
                 tc_wait_ld();
 #pragma unroll
