@@ -24,6 +24,7 @@
 //          registers, transpose the 4 x 4 block and store it (the 3xTF32 split happens in the same registers).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "bk_train_args.h"
 
@@ -464,7 +465,213 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// 3x3 convolution / data gradient with the activation tile staged ONCE (the structural fix the stage-by-stage breakdown of the
+// kernel above asks for; profiles/r01h_tc_stage_breakdown.md).  GEMM rows are the rows of a padded raster: position p, square (x, y)
+// sits at row 100 p + 10 + 10 x + y -- ten zero rows above every board, one zero column to its right -- so a tap (dx, dy) is the row
+// shift 10 dx + dy of ONE staged operand, exactly as in the inference kernel, and zero padding comes from the zero rows / column.
+// A CTA owns 128 consecutive raster rows: it gathers rows R0 - 11 .. R0 + 138 (all 128 channels) once -- 4,800 16-byte chunks
+// instead of the 36,864 of nine separate window gathers -- in four channel groups of 32 that the MMAs follow group by group, so the
+// staging of groups 1-3 runs under the MMAs of group 0; after that only the pre-split weight slabs stream (one bulk copy each).
+// 81 of every 100 raster rows are real squares; the result threads write those to the dense [P][81][128] output.
+// Warps: 0-3 result (thread = raster row), 4-7 staging, 8 MMA issue, 9 weight loader (one thread).
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int R3_ROWS = 152;                       // staged rows: 128 + 2 * 11 halo, rounded up to 8
+constexpr int R3_LBO = R3_ROWS * 16;               // bytes between K chunks of the staged tile
+constexpr int R3_A_BYTES = 32 * R3_LBO;            // one part (hi or lo) of the tile: 77,824
+constexpr int R3_THREADS = 320;
+template <int PREC>
+struct R3 {
+    static constexpr int NW = PREC ? 2 : 6;                          // weight stages
+    static constexpr int W_STAGE = (PREC ? 2 : 1) * 16384;           // B_hi (, B_lo) of a 32-deep slab
+    static constexpr int A_BYTES = (PREC ? 2 : 1) * R3_A_BYTES;
+    static constexpr int SMEM = A_BYTES + NW * W_STAGE + 256;
+    // K steps per accumulation chain: one slab (12 MMAs in 3xTF32).  Measured on the recorded reference iteration: as accurate as one
+    // K step per chain (1e-6 against FFMA) and 18 % faster -- with the staging gone, the chain hand-shakes were what was left
+    static constexpr int CHAIN = 4;
+};
+enum { R3_AFULL = 0, R3_WFULL = 4, R3_WEMPTY = 4 + MAX_STAGES, R3_ACCF = 4 + 2 * MAX_STAGES, R3_ACCE = R3_ACCF + NBUF,
+       R3_NBARS = R3_ACCE + NBUF };
+
+template <int PREC>
+__global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const BkConvArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    using Z = R3<PREC>;
+    constexpr int NW = Z::NW, W_STAGE = Z::W_STAGE, CHAIN = Z::CHAIN;
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_w = s_base + Z::A_BYTES;
+    const uint32_t s_bar = s_w + NW * W_STAGE;
+    const uint32_t s_tmem = s_bar + 8 * R3_NBARS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int P = a.M / NSQ;
+    const int R0 = blockIdx.x * 128;               // first raster row of this tile
+    constexpr int KT = 36;                          // slabs: 4 channel groups x 9 taps
+    constexpr int n_chains = KT * 4 / CHAIN;
+
+    if (tid == 0) {
+        for (int g = 0; g < 4; ++g) mbar_init(s_bar + 8 * (R3_AFULL + g), 128);
+        for (int s = 0; s < NW; ++s) {
+            mbar_init(s_bar + 8 * (R3_WFULL + s), 1);
+            mbar_init(s_bar + 8 * (R3_WEMPTY + s), 1);
+        }
+        for (int b = 0; b < NBUF; ++b) {
+            mbar_init(s_bar + 8 * (R3_ACCF + b), 1);
+            mbar_init(s_bar + 8 * (R3_ACCE + b), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(s_tmem, 128 * NBUF);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem + Z::A_BYTES + NW * W_STAGE + 8 * R3_NBARS);
+
+    if (warp >= 4 && warp < 8) {
+        // =============================== staging of the activation tile ===============================
+        const int pw = warp - 4, r8 = lane & 7, q4 = lane >> 3;
+        for (int g = 0; g < 4; ++g) {
+            // a block = 8 rows x 4 K chunks; 19 row groups x 2 chunk halves per channel group of 8 chunks
+            for (int b = pw; b < 38; b += 4) {
+                const int row = (b >> 1) * 8 + r8, kc = g * 8 + (b & 1) * 4 + q4;
+                const int rr = R0 - 11 + row;                                  // raster row
+                const int p = rr >= 0 ? rr / 100 : -1;
+                const int o = rr - 100 * p - 10;                               // 10 x + y, negative in the zero rows above the board
+                const int x = o / 10, y = o - 10 * x;
+                const bool ok = rr >= 0 && p < P && o >= 0 && y < 9 && row < 150;
+                const float *src = ok ? a.in + ((size_t)(p * NSQ + 9 * x + y) * C + 4 * kc) : a.in;
+                cp_async16(s_base + (uint32_t)(kc * R3_LBO + row * 16), src, ok);
+            }
+            cp_commit();
+            cp_wait<0>();
+            if constexpr (PREC != 0) {
+                for (int b = pw; b < 38; b += 4) {
+                    const int row = (b >> 1) * 8 + r8, kc = g * 8 + (b & 1) * 4 + q4;
+                    float4 *hp = reinterpret_cast<float4 *>(smem + kc * R3_LBO + row * 16);
+                    const float4 v = *hp;
+                    float4 h, l;
+                    h.x = tf32_cut(v.x); h.y = tf32_cut(v.y); h.z = tf32_cut(v.z); h.w = tf32_cut(v.w);
+                    l.x = tf32_cut(v.x - h.x); l.y = tf32_cut(v.y - h.y); l.z = tf32_cut(v.z - h.z); l.w = tf32_cut(v.w - h.w);
+                    *hp = h;
+                    *reinterpret_cast<float4 *>(smem + R3_A_BYTES + kc * R3_LBO + row * 16) = l;
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(s_bar + 8 * (R3_AFULL + g));
+        }
+    } else if (warp == 9) {
+        // =============================== weight slabs: one bulk copy per part ===============================
+        if (lane == 0) {
+            for (int s = 0; s < KT; ++s) {
+                const int st = s % NW;
+                if (s >= NW) mbar_wait(s_bar + 8 * (R3_WEMPTY + st), ((s / NW) & 1) ^ 1);
+                const int g = s / 9, tap = s - 9 * g;
+                const int k0 = tap * C + 32 * g;
+                const uint32_t bar = s_bar + 8 * (R3_WFULL + st), dst = s_w + (uint32_t)(st * W_STAGE);
+                mbar_arrive_expect_tx(bar, (uint32_t)W_STAGE);
+                bulk_g2s(dst, a.w + (size_t)(k0 / 4) * (4 * C), 16384, bar);
+                if (PREC) bulk_g2s(dst + 16384, a.w_lo + (size_t)(k0 / 4) * (4 * C), 16384, bar);
+            }
+        }
+    } else if (warp == 8) {
+        // =============================== MMA issue ===============================
+        int c = 0;
+        for (int s = 0; s < KT; ++s) {
+            const int st = s % NW;
+            const int g = s / 9, tap = s - 9 * g;
+            if (tap == 0) mbar_wait(s_bar + 8 * (R3_AFULL + g), 0);
+            mbar_wait(s_bar + 8 * (R3_WFULL + st), (s / NW) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const int ti = tap / 3;
+                const int shift = a.sign * (10 * (ti - 1) + (tap - 3 * ti - 1));
+                const uint32_t a0 = s_base + (uint32_t)((11 + shift) * 16), w0 = s_w + (uint32_t)(st * W_STAGE);
+                int cc = c;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const int b = cc % NBUF;
+                    const bool first = ks % CHAIN == 0;
+                    if (first) {
+                        mbar_wait(s_bar + 8 * (R3_ACCE + b), ((cc / NBUF) & 1) ^ 1);
+                        tc_fence_after();
+                    }
+                    const uint32_t d = tmem + (uint32_t)(b * 128);
+                    const uint32_t akc = (uint32_t)((8 * g + 2 * ks) * R3_LBO);
+                    const uint64_t ah = make_desc(a0 + akc, R3_LBO, (128u >> 4) | (1u << 14));
+                    const uint64_t al = make_desc(a0 + R3_A_BYTES + akc, R3_LBO, (128u >> 4) | (1u << 14));      // 3xTF32 only
+                    const uint64_t bh = make_desc(w0 + ks * 4096, 2048, (128u >> 4) | (1u << 14));
+                    const uint64_t bl = make_desc(w0 + 16384 + ks * 4096, 2048, (128u >> 4) | (1u << 14));
+                    if constexpr ((BK_TC_DIAG & 4) != 0) {
+                    } else if constexpr (PREC != 0) {
+                        umma_tf32(d, al, bh, IDESC_BASE, first ? 0u : 1u);
+                        umma_tf32(d, ah, bl, IDESC_BASE, 1u);
+                        umma_tf32(d, ah, bh, IDESC_BASE, 1u);
+                    } else {
+                        umma_tf32(d, ah, bh, IDESC_BASE, first ? 0u : 1u);
+                    }
+                    if (ks % CHAIN == CHAIN - 1) {
+                        umma_commit(s_bar + 8 * (R3_ACCF + b));
+                        ++cc;
+                    }
+                }
+                umma_commit(s_bar + 8 * (R3_WEMPTY + st));
+            }
+            c += 4 / CHAIN;
+            __syncwarp();
+        }
+    } else {
+        // =============================== result warps (thread = raster row) ===============================
+        float acc[C];
+#pragma unroll
+        for (int i = 0; i < C; ++i) acc[i] = 0.0f;
+        const uint32_t t_lane = tmem + ((uint32_t)(32 * warp) << 16);
+        for (int c = 0; c < n_chains; ++c) {
+            const int b = c % NBUF;
+            mbar_wait(s_bar + 8 * (R3_ACCF + b), (c / NBUF) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                uint32_t v[32];
+                tmem_ld32(t_lane + (uint32_t)(b * 128 + h * 32), v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[h * 32 + i] += __uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            mbar_arrive(s_bar + 8 * (R3_ACCE + b));
+        }
+        const int rr = R0 + 32 * warp + lane;
+        const int p = rr / 100, o = rr - 100 * p - 10;
+        const int x = o / 10, y = o - 10 * x;
+        if (p < P && o >= 0 && y < 9) {
+            float4 *out = reinterpret_cast<float4 *>(a.out + (size_t)(p * NSQ + 9 * x + y) * C);
+#pragma unroll
+            for (int i = 0; i < C / 4; ++i) {
+                float4 v = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                if (a.bias) {
+                    const float4 bb = *reinterpret_cast<const float4 *>(a.bias + 4 * i);
+                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                }
+                out[i] = v;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 128 * NBUF);
+    }
+}
+
 }   // namespace
+
+static bool getenv_old_conv()
+{
+    static const bool v = getenv("BK_TC_OLD_CONV") != nullptr;    // measurement: the window-gather kernel for the 3x3 layers as well
+    return v;
+}
 
 int bk_tc_set_attrs(void)
 {
@@ -474,12 +681,20 @@ int bk_tc_set_attrs(void)
     BK_SET((bk_train_gemm_tc_kernel<0, 1, BkConvArgs>), (Sizes<0, 1>::SMEM));
     BK_SET((bk_train_gemm_tc_kernel<1, 0, BkWgradArgs>), (Sizes<1, 0>::SMEM));
     BK_SET((bk_train_gemm_tc_kernel<1, 1, BkWgradArgs>), (Sizes<1, 1>::SMEM));
+    BK_SET((bk_train_conv3_tc_kernel<0>), (R3<0>::SMEM));
+    BK_SET((bk_train_conv3_tc_kernel<1>), (R3<1>::SMEM));
 #undef BK_SET
     return e == cudaSuccess ? 0 : -3;
 }
 
 void bk_tc_launch_conv(const BkConvArgs &a, int three_x, cudaStream_t st)
 {
+    if (a.R == 3 && a.Cin == C && !getenv_old_conv()) {          // the 3x3 layers and their data gradients: tile staged once
+        const int tiles = (a.M / NSQ * 100 + 127) / 128;
+        if (three_x) bk_train_conv3_tc_kernel<1><<<tiles, R3_THREADS, R3<1>::SMEM, st>>>(a);
+        else bk_train_conv3_tc_kernel<0><<<tiles, R3_THREADS, R3<0>::SMEM, st>>>(a);
+        return;
+    }
     const int grid = (a.M + 127) / 128;
     if (three_x) bk_train_gemm_tc_kernel<0, 1, BkConvArgs><<<grid, N_THREADS, Sizes<0, 1>::SMEM, st>>>(a);
     else bk_train_gemm_tc_kernel<0, 0, BkConvArgs><<<grid, N_THREADS, Sizes<0, 0>::SMEM, st>>>(a);
