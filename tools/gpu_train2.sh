@@ -8,6 +8,6 @@ timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; ech
 timeout 600 python tools/bench_train.py --out gpurun_out/train.jsonl > gpurun_out/bench_train.log 2>&1; tail -3 gpurun_out/bench_train.log
 timeout 300 python tools/prof_train.py > gpurun_out/prof_train_plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_train.csv python tools/prof_train.py > gpurun_out/ncu_list_train.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"bk_train_gemm_tc" -s 14 -c 6 -o gpurun_out/prof_train_tc python tools/prof_train.py > gpurun_out/ncu_full_train.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"bk_train_(gemm|conv3)_tc" -s 14 -c 8 -o gpurun_out/prof_train_tc python tools/prof_train.py > gpurun_out/ncu_full_train.log 2>&1
 tail -3 gpurun_out/ncu_full_train.log
 ls -la gpurun_out | tail -8
