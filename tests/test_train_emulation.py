@@ -162,3 +162,28 @@ def test_running_filter_and_adamw_against_reference_run():
             # and with it the element's update, is noise -- at most 2 * lr, and only on a handful of elements
             d = np.abs(ps - post)
             assert d.max() <= 2.1e-5 and (d > 1e-7).sum() <= max(3, 5e-3 * d.size), (k, d.max(), (d > 1e-7).mean())
+
+
+def test_reinforce_argument_errors_need_no_device():
+    """the mirror of `reinforce` keeps the reference's ValueError for a bad colour (bin/selfplay.py:84), raised before anything touches a device"""
+    with pytest.raises(ValueError):
+        rf.reinforce(None, None, None, "green")
+
+
+def test_trainer_has_no_cpu_path():
+    """no CPU fallback: the training state refuses a non-CUDA device"""
+    from bokego_b200 import _lib
+    sd = dict(np.load(os.path.join(GOLD, "weights_policy_17.npz")))
+    with pytest.raises(_lib.BokegoB200Error):
+        rf.PolicyTrainer(sd, torch.device("cpu"))
+
+
+def test_training_symbols_exported():
+    """every training entry point of include/bokego_b200.h is exported by the built library"""
+    from bokego_b200 import _lib
+    L = _lib.lib()
+    for name in ("bk_train_param_count", "bk_train_workspace_bytes", "bk_train_launches", "bk_train_forward", "bk_train_backward",
+                 "bk_train_running_stats", "bk_adamw_step"):
+        assert hasattr(L, name), name
+    assert L.bk_train_param_count() == rf.TP_COUNT
+    assert L.bk_train_workspace_bytes(0) == 0 and L.bk_train_workspace_bytes(16) > 16 * 81 * 128 * 4 * 14
