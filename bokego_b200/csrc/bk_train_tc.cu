@@ -40,8 +40,8 @@ constexpr int MAX_STAGES = 6;
 #define BK_TC_DIAG 0
 #endif
 #ifndef BK_TC_CHAIN
-#define BK_TC_CHAIN 1    // K steps per 3xTF32 accumulation chain.  Measured: 2 and 4 (one slab) are as accurate (1e-6) and 5 % faster,
-#endif                   // 16 (four slabs, 48 MMAs) leaves 1e-3 in the early layers' gradients; 1 keeps the largest margin
+#define BK_TC_CHAIN 4    // K steps per 3xTF32 accumulation chain = one slab (12 MMAs).  Measured on the recorded reference iteration: 1, 2 and 4
+#endif                   // are equally accurate (1e-6 against FFMA) and 4 is 5 % faster; 16 (four slabs, 48 MMAs) leaves 1e-3 in the early layers
 constexpr int NBUF = 4;                  // TMEM accumulators of 128 columns (all 512 columns)
 constexpr int N_THREADS = 288;
 constexpr int WARP_MMA = 8;
