@@ -15,7 +15,6 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bokego_b200 import batched as bk, mcts  # noqa: E402
-from oracle import nets as onets             # noqa: E402  (seeded stand-in value head parameters only)
 
 
 def main():
@@ -23,7 +22,7 @@ def main():
     g = os.path.join(ROOT, "tests", "golden")
     sd17 = dict(np.load(os.path.join(g, "weights_policy_17.npz")))
     sdv = dict(np.load(os.path.join(g, "weights_policy_19.npz")))
-    sdv.update({k: v.numpy() for k, v in onets.standin_value_head(1234).items()})
+    sdv.update(dict(np.load(os.path.join(g, "weights_value_head_standin.npz"))))   # seeded stand-in value head
     pol, val = bk.PackedNet(sd17, dev), bk.PackedNet(sdv, dev)
     mcts.MCTS(None, pol, val, device=dev).rollout(10)      # warm-up (kernel attributes, allocator)
     for thresh in (100, 1):

@@ -6,7 +6,6 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bokego_b200 import reinforce as rf
-from oracle import train as ot
 dev = torch.device("cuda", 0)
 g = os.path.join(ROOT, "tests", "golden")
 sd17 = dict(np.load(os.path.join(g, "weights_policy_17.npz")))
@@ -15,9 +14,10 @@ tag = "black3"
 color, bs = int(G[f"{tag}/color"]), int(G[f"{tag}/bs"])
 calls, rfrom = G[f"{tag}/calls"], int(G[f"{tag}/replay_from"])
 lengths, results, moves = G[f"{tag}/lengths"], G[f"{tag}/results"], G[f"{tag}/moves"]
-pos = ot.replay_positions(lengths, color)
+pos = [(i, j) for i, n in enumerate(lengths) for j in range(1 if color else 0, int(n), 2)]   # the training colour's turns, game by game
 mv = np.array([moves[g_, j] for g_, j in pos], np.int16)
-coef = ot.reference_coef(lengths, results, color, bs)
+last = len(lengths) - 1                      # the reference differentiates the last game only (selfplay.py:86)
+coef = np.array([(-results[last] if color else results[last]) / bs if g_ == last else 0.0 for g_, _ in pos], np.float32)
 planes = torch.from_numpy(np.ascontiguousarray(calls[rfrom:])).to(dev)
 mvd, cfd = torch.from_numpy(mv).to(dev), torch.from_numpy(coef).to(dev)
 def grads(prec, sub=None):
