@@ -238,6 +238,26 @@ def reinforce_leg(dev, sd17, sd19, with_cpu):
         out[name.split(" ")[0]] = {"step_ms": ms, "positions_per_s": P / (1e-3 * ms), "achieved_tflops": ach,
                                    "frac_of_tf32_peak": ach / tf_peak, "precision": name}
     out["peak"] = {"tflops": tf_peak, "source": "half of the measured 16-bit dense peak (TF32 operands)"}
+    # the same step on a batch that fills the GPU (2,048 positions = one forward / backward chunk), default precision
+    P2 = 2048
+    planes2 = torch.from_numpy(np.ascontiguousarray(calls[np.arange(P2) % len(calls)])).to(dev)
+    moves2 = torch.randint(0, 81, (P2,), device=dev).to(torch.int16)
+    coef2 = torch.full((P2,), 1.0 / 16, device=dev)
+    tr = rf.PolicyTrainer(sd17, dev)
+    for _ in range(2):
+        rf.reinforce_step(tr, planes2, moves2, coef2)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        rf.reinforce_step(tr, planes2, moves2, coef2)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    ach = FLOP_TRAIN * P2 / (1e-3 * ms) / 1e12
+    out["at_2048_positions"] = {"step_ms": ms, "positions_per_s": P2 / (1e-3 * ms), "achieved_tflops": ach, "frac_of_tf32_peak": ach / tf_peak,
+                                "precision": "3xtf32 (tcgen05; default)"}
+    del tr, planes2
     pi, opp = nnet.PolicyNet(), nnet.PolicyNet()
     pi.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd17.items()})
     opp.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd19.items()})
