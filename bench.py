@@ -483,13 +483,13 @@ def run_ours(args, rank, world, local_rank):
                                      "achieved": 4461 * B / (1e-3 * float(np.mean(e_ms))) / 1e9, "peak": hbm_peak, "unit": "GB/s"}},
         }
         if world == 1 and not args.no_cpu:
-            rate, cores, ts = cpu_rate(args.cpu_sample, sd17, sdv)
+            rate, cores, ts = cpu_rate(args.cpu_sample, sd17, sdv, repeats=args.cpu_passes)      # ~10 s of CPU work
             if "selfplay" in extra:
                 sp_rate, sp_cores, sp_dt = cpu_selfplay_rate(args.cpu_selfplay_games, sd17, sd19)
                 extra["selfplay"]["cpu_baseline"] = {"value": sp_rate, "unit": "games/s", "cores": sp_cores, "kind": "port",
                                                      "sample": f"{args.cpu_selfplay_games} games x 72 moves in lock step ({sp_dt:.1f} s)"}
             line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_sample} positions, 1 pass ({ts[0]:.1f} s); C feature oracle (OpenMP) + fp32 torch CPU forward, {cores} threads"}
+                                    "sample": f"{args.cpu_sample} positions x {len(ts)} passes ({sum(ts):.1f} s); C feature oracle (OpenMP) + fp32 torch CPU forward, {cores} threads"}
         line.update(extra)
         print(json.dumps(line))
     if dist:
@@ -504,6 +504,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=4096)
+    ap.add_argument("--cpu-passes", type=int, default=8, help="passes of the CPU baseline over its sample (bounded: about 10 s)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-playouts", action="store_true", help="skip the self-play / simulate secondary measurements")
     ap.add_argument("--no-train", action="store_true", help="skip the REINFORCE step measurement")
