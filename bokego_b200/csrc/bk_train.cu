@@ -35,6 +35,7 @@ constexpr int B_LD = C + 8;         // 136 floats: conflict-free fragment reads 
 constexpr int NT = 256;
 constexpr int CONV_SMEM = 2 * (BM * A_LD + BK * B_LD) * 4;   // 71,680
 constexpr int WGRAD_SMEM = 2 * 2 * BK * B_LD * 4;            // 69,632
+constexpr int SPLIT_MAX_P = 64;     // up to this many positions the tcgen05 3x3 forward convs run one CTA per channel group (4 partial results)
 constexpr float BN_EPS = 1e-5f;
 constexpr float PROB_EPS = 1.1920928955078125e-07f;          // torch.finfo(float32).eps (Categorical's clamp)
 
@@ -361,6 +362,20 @@ __global__ void bk_train_pack_w_kernel(const float *w, float *hi, float *lo, int
     lo[o] = __uint_as_float(f2tf32(x - h));
 }
 
+// z[i] = z[i] + z[n + i] + z[2n + i] + z[3n + i] (in that order): the four channel-group partial results of a small-batch conv
+__global__ void bk_train_sum4_kernel(float4 *z, size_t n4)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 v = z[i];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        const float4 u = z[k * n4 + i];
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    z[i] = v;
+}
+
 // ---- BatchNorm (+ ReLU) forward for one position per CTA, thread = channel ----
 // bn_mode 0: statistics of this position (train-mode batch of one); 1: running statistics.
 __global__ void __launch_bounds__(C) bk_train_bn_fwd_kernel(const float *z, const float *gamma, const float *beta,
@@ -570,7 +585,7 @@ Ws ws_layout(int P)
     const size_t act = (size_t)P * NSQ * C;
     w.x0 = take((size_t)P * NSQ * C0);
     for (int l = 0; l < 7; ++l) {
-        w.z[l] = take(act);
+        w.z[l] = take(P <= SPLIT_MAX_P ? 4 * act : act);           // small batches: four channel-group partial results, summed into the first
         w.a[l] = take(act);
         w.mean[l] = take((size_t)P * C);
         w.rstd[l] = take((size_t)P * C);
@@ -643,7 +658,12 @@ extern "C" size_t bk_train_param_count(void) { return BK_TP_COUNT; }
 
 extern "C" size_t bk_train_workspace_bytes(int P) { return P <= 0 ? 0 : ws_layout(P).total * sizeof(float); }
 
-extern "C" int bk_train_launches(int which) { return which == 0 ? 1 + 7 * 2 + 1 : 1 + 1 + 2 + 7 * 4 + 6; }
+extern "C" int bk_train_launches(int which, int P, int prec)
+{
+    const int tc = prec >= 4 ? 1 : 0;                               // the tcgen05 path repacks the weights once per call
+    if (which == 0) return 1 + tc + 7 * 2 + 1 + (tc && P <= SPLIT_MAX_P ? 6 : 0);
+    return 1 + tc + 1 + 2 + 7 * 4 + 6;
+}
 
 extern "C" int bk_train_forward(const float *params, const float *running, const uint8_t *planes_u8, int P, int bn_mode, int prec,
                                 void *workspace, float *logits, float *probs, float *stats_out, void *stream)
@@ -668,7 +688,12 @@ extern "C" int bk_train_forward(const float *params, const float *running, const
         a.Cin = l == 0 ? C0 : C;
         a.R = l == 0 ? 5 : 3;
         a.sign = 1;
+        a.ksplit = (prec >= 4 && l > 0 && P <= SPLIT_MAX_P) ? 4 : 1;
         launch_conv(a, prec, st);
+        if (a.ksplit > 1) {
+            const size_t n4 = (size_t)P * NSQ * C / 4;
+            bk_train_sum4_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4 *>(ws + w.z[l]), n4);
+        }
         bk_train_bn_fwd_kernel<<<P, C, 0, st>>>(ws + w.z[l], params + vec_off(l, 1), params + vec_off(l, 2), running + l * C,
                                                 running + (7 + l) * C, ws + w.a[l], ws + w.mean[l], ws + w.rstd[l], stats_out, l,
                                                 bn_mode);
@@ -723,6 +748,7 @@ extern "C" int bk_train_backward(const float *params, const int16_t *moves, cons
             a.Cin = C;
             a.R = 3;
             a.sign = -1;
+            a.ksplit = 1;
             launch_conv(a, prec, st);
         }
     }

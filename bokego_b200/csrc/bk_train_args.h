@@ -12,6 +12,9 @@ struct BkConvArgs {
     float *out;
     int M, Cin, R, sign;
     const float *w_lo;   /* tcgen05 path only: w = packed TF32 high parts [k / 4][co][k % 4], w_lo = the low parts (3xTF32) */
+    int ksplit;          /* staged-once 3x3 kernel only: 1, or 4 = one CTA per channel group of 32 (grid.y), group g writes its partial
+                            result to out + g * M * 128 and bk_train_sum4_kernel adds them in order.  For small batches: a 16-position
+                            forward has 13 tiles, this puts 52 CTAs to work on a quarter of the K loop each. */
 };
 
 /* weight gradient: part[split][k][co] = sum over the split's rows m of act[m shifted by tap(k)][ci(k)] * dz[m][co] */

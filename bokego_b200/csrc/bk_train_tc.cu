@@ -507,8 +507,9 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int P = a.M / NSQ;
     const int R0 = blockIdx.x * 128;               // first raster row of this tile
-    constexpr int KT = 36;                          // slabs: 4 channel groups x 9 taps
-    constexpr int n_chains = KT * 4 / CHAIN;
+    const int g_lo = a.ksplit > 1 ? (int)blockIdx.y : 0, g_hi = a.ksplit > 1 ? g_lo + 1 : 4;   // channel groups of this CTA
+    const int KT = (g_hi - g_lo) * 9;               // slabs: channel groups x 9 taps
+    const int n_chains = KT * 4 / CHAIN;
 
     if (tid == 0) {
         for (int g = 0; g < 4; ++g) mbar_init(s_bar + 8 * (R3_AFULL + g), 128);
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
     if (warp >= 4 && warp < 8) {
         // =============================== staging of the activation tile ===============================
         const int pw = warp - 4, r8 = lane & 7, q4 = lane >> 3;
-        for (int g = 0; g < 4; ++g) {
+        for (int g = g_lo; g < g_hi; ++g) {
             // a block = 8 rows x 4 K chunks; 19 row groups x 2 chunk halves per channel group of 8 chunks
             for (int b = pw; b < 38; b += 4) {
                 const int row = (b >> 1) * 8 + r8, kc = g * 8 + (b & 1) * 4 + q4;
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
             for (int s = 0; s < KT; ++s) {
                 const int st = s % NW;
                 if (s >= NW) mbar_wait(s_bar + 8 * (R3_WEMPTY + st), ((s / NW) & 1) ^ 1);
-                const int g = s / 9, tap = s - 9 * g;
+                const int g = g_lo + s / 9, tap = s % 9;
                 const int k0 = tap * C + 32 * g;
                 const uint32_t bar = s_bar + 8 * (R3_WFULL + st), dst = s_w + (uint32_t)(st * W_STAGE);
                 mbar_arrive_expect_tx(bar, (uint32_t)W_STAGE);
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
         int c = 0;
         for (int s = 0; s < KT; ++s) {
             const int st = s % NW;
-            const int g = s / 9, tap = s - 9 * g;
+            const int g = g_lo + s / 9, tap = s % 9;
             if (tap == 0) mbar_wait(s_bar + 8 * (R3_AFULL + g), 0);
             mbar_wait(s_bar + 8 * (R3_WFULL + st), (s / NW) & 1);
             tc_fence_after();
@@ -645,11 +646,11 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
         const int p = rr / 100, o = rr - 100 * p - 10;
         const int x = o / 10, y = o - 10 * x;
         if (p < P && o >= 0 && y < 9) {
-            float4 *out = reinterpret_cast<float4 *>(a.out + (size_t)(p * NSQ + 9 * x + y) * C);
+            float4 *out = reinterpret_cast<float4 *>(a.out + ((size_t)g_lo * (a.ksplit > 1 ? a.M : 0) + p * NSQ + 9 * x + y) * C);
 #pragma unroll
             for (int i = 0; i < C / 4; ++i) {
                 float4 v = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
-                if (a.bias) {
+                if (a.bias && g_lo == 0) {
                     const float4 bb = *reinterpret_cast<const float4 *>(a.bias + 4 * i);
                     v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
                 }
@@ -690,7 +691,7 @@ int bk_tc_set_attrs(void)
 void bk_tc_launch_conv(const BkConvArgs &a, int three_x, cudaStream_t st)
 {
     if (a.R == 3 && a.Cin == C && !getenv_old_conv()) {          // the 3x3 layers and their data gradients: tile staged once
-        const int tiles = (a.M / NSQ * 100 + 127) / 128;
+        const dim3 tiles((a.M / NSQ * 100 + 127) / 128, a.ksplit > 1 ? 4 : 1);
         if (three_x) bk_train_conv3_tc_kernel<1><<<tiles, R3_THREADS, R3<1>::SMEM, st>>>(a);
         else bk_train_conv3_tc_kernel<0><<<tiles, R3_THREADS, R3<0>::SMEM, st>>>(a);
         return;

@@ -155,7 +155,7 @@ class PolicyTrainer:
             rc = L.bk_train_forward(_lib.ptr(self.params), _lib.ptr(self.running), _lib.ptr(planes_u8), P, bn_mode, self.prec,
                                     _lib.ptr(ws), _lib.ptr(logits), _lib.ptr(probs), _lib.ptr(stats), _lib.stream_ptr(dev))
         _lib.check(rc, "bk_train_forward")
-        _lib.count_launch(L.bk_train_launches(0))
+        _lib.count_launch(L.bk_train_launches(0, P, self.prec))
         self._fwd = (P, bn_mode)
         return logits, probs, stats
 
@@ -176,7 +176,7 @@ class PolicyTrainer:
                                      _lib.ptr(self._ws), _lib.ptr(self.grads), 1 if accumulate else 0, _lib.ptr(nlp),
                                      _lib.stream_ptr(dev))
         _lib.check(rc, "bk_train_backward")
-        _lib.count_launch(L.bk_train_launches(1))
+        _lib.count_launch(L.bk_train_launches(1, P, self.prec))
         return nlp
 
     def update_running(self, stats, seq=None, momentum=MOMENTUM):

@@ -144,7 +144,7 @@ int bk_tree_finish(int64_t *N, double *V, const double *val, const int32_t *pend
 #define BK_TP_COUNT 990033
 size_t bk_train_param_count(void);
 size_t bk_train_workspace_bytes(int P);
-int bk_train_launches(int which); /* kernels launched by bk_train_forward (0) / bk_train_backward (1) */
+int bk_train_launches(int which, int P, int prec); /* kernels launched by bk_train_forward (0) / bk_train_backward (1) for P positions */
 int bk_train_forward(const float *params, const float *running, const uint8_t *planes_u8, int P, int bn_mode, int prec,
                      void *workspace, float *logits, float *probs, float *stats_out, void *stream);
 int bk_train_backward(const float *params, const int16_t *moves, const float *coef, int P, int bn_mode, int prec,
