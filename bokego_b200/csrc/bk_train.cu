@@ -602,7 +602,7 @@ Ws ws_layout(int P)
     w.wdpack = take((size_t)6 * 9 * C * C);         // the transposed weights of the data gradient, packed the same way
     w.wdpack_lo = take((size_t)6 * 9 * C * C);
     const int M = P * NSQ;
-    int splits = (M + 1023) / 1024;                 // >= 1024 rows per split, at most 32 splits
+    int splits = (M + 255) / 256;                   // >= 256 rows per split, at most 32 splits (small batches: more CTAs, shorter loops)
     splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
     int rps = (M + splits - 1) / splits;
     rps = (rps + BK - 1) / BK * BK;
