@@ -88,8 +88,9 @@ def features_batch(pos, fresh_libs=None, want=("conv", "legal", "libs"), out=Non
     _lib.check(rc, "bk_encode")
     _lib.count_launch()
     if "libs" in want:
-        # the kernel never updates the cache in place: swap the buffers (a fresh position adopts its exact
-        # liberties as the cache, exactly like Game._libs after the first get_liberties call)
+        # without a caller-supplied buffer the cache is written to a spare tensor and the two are swapped (a fresh position
+        # adopts its exact liberties as the cache, exactly like Game._libs after the first get_liberties call); callers that
+        # pass out["libs"] = pos.libs (the playout loops) get the in-place update the C ABI allows (libs_out may alias libs_in)
         pos._libs_spare, pos.libs = pos.libs, out["libs"]
     return out
 
@@ -256,8 +257,11 @@ class HostEvaluator:
             main.wait_stream(self.copy_out)
 
 
-def playout_step(pos, probs, mode, max_turn, seed=0, game0=0, q_inj=None, moves_out=None):
-    """One playout move for every unfinished board (kernel c); updates `pos` in place, returns moves int16 [B]."""
+def playout_step(pos, probs, mode, max_turn, seed=0, game0=0, q_inj=None, moves_out=None, encode_into=None):
+    """One playout move for every unfinished board (kernel c); updates `pos` in place, returns moves int16 [B].
+    encode_into: the "conv" buffer of a previous features_batch of these boards -- the same launch then also encodes the
+    position after the move into it (carried liberty cache pos.libs, updated in place), so the next policy evaluation needs
+    no encoder launch."""
     L = _lib.lib()
     dev, B = pos.device, pos.B
     _want(probs, torch.float32, (B, 81), "probs", dev)
@@ -270,10 +274,20 @@ def playout_step(pos, probs, mode, max_turn, seed=0, game0=0, q_inj=None, moves_
     if moves_out is None:
         moves_out = torch.empty(B, dtype=torch.int16, device=dev)
     with torch.cuda.device(dev):
-        rc = L.bk_playout_step(_lib.ptr(pos.boards), _lib.ptr(pos.ko), _lib.ptr(pos.last), _lib.ptr(pos.turn),
-                               _lib.ptr(pos.libs), _lib.ptr(pos.done), _lib.ptr(probs), _lib.ptr(q_inj), qv,
-                               C.c_uint64(seed), C.c_uint32(game0), mode, max_turn, _lib.ptr(moves_out), B,
-                               _lib.stream_ptr(dev))
+        if encode_into is None:
+            rc = L.bk_playout_step(_lib.ptr(pos.boards), _lib.ptr(pos.ko), _lib.ptr(pos.last), _lib.ptr(pos.turn),
+                                   _lib.ptr(pos.libs), _lib.ptr(pos.done), _lib.ptr(probs), _lib.ptr(q_inj), qv,
+                                   C.c_uint64(seed), C.c_uint32(game0), mode, max_turn, _lib.ptr(moves_out), B,
+                                   _lib.stream_ptr(dev))
+        else:
+            if pos.libs is None:
+                raise ValueError("encode_into needs the carried liberty cache pos.libs")
+            if encode_into.device != dev or encode_into.numel() < L.bk_feats_conv_bytes(B):
+                raise ValueError("encode_into: wrong device or too small for B")
+            rc = L.bk_playout_step_encode(_lib.ptr(pos.boards), _lib.ptr(pos.ko), _lib.ptr(pos.last), _lib.ptr(pos.turn),
+                                          _lib.ptr(pos.libs), _lib.ptr(pos.done), _lib.ptr(probs), _lib.ptr(q_inj), qv,
+                                          C.c_uint64(seed), C.c_uint32(game0), mode, max_turn, _lib.ptr(moves_out),
+                                          _lib.ptr(encode_into), B, _lib.stream_ptr(dev))
     _lib.check(rc, "bk_playout_step")
     _lib.count_launch()
     return moves_out

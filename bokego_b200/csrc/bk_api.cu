@@ -17,12 +17,23 @@ extern "C" const char *bk_strerror(int code)
     }
 }
 
+// The binary holds sm_100a code only (arch-specific: it does not run on sm_103 or any other 10.x part).
 extern "C" int bk_device_check(void)
 {
-    int dev = 0, major = 0;
+    int dev = 0, major = 0, minor = -1;
     if (cudaGetDevice(&dev) != cudaSuccess) return -2;
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return -2;
-    return major == 10 ? 0 : -2;
+    if (cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) return -2;
+    return (major == 10 && minor == 0) ? 0 : -2;
+}
+
+// Index of the current device for the per-device launch state the .cu files keep (kernel attributes, SM count, tensor
+// maps): -1 when there is no current device or it is beyond BK_MAX_DEVICES.
+int bk_current_device_slot(void)
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= BK_MAX_DEVICES) return -1;
+    return dev;
 }
 
 extern "C" size_t bk_feats_conv_bytes(int B)

@@ -23,23 +23,17 @@
 #include <stdint.h>
 
 #include "bk_bitboard.cuh"
+#include "bk_encode_core.cuh"
 #include "bk_layout.h"
 
 namespace {
 
-__device__ __forceinline__ uint32_t half_bits(int n)   // fp16 bit pattern of a small non-negative integer
-{
-    return (uint32_t)__half_as_ushort(__int2half_rn(n));
-}
-
-__device__ __forceinline__ uint32_t pack2(int lo, int hi) { return half_bits(lo) | (half_bits(hi) << 16); }
-
 __global__ void __launch_bounds__(96)
 bk_encode_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ ko_arr,
                  const int16_t *__restrict__ last_arr, const int16_t *__restrict__ turn_arr,
-                 const uint8_t *__restrict__ libs_in, uint4 *__restrict__ feats_conv,
+                 const uint8_t *libs_in, uint4 *__restrict__ feats_conv,
                  float *__restrict__ feats_f32, uint8_t *__restrict__ planes_u8,
-                 uint8_t *__restrict__ legal_out, uint8_t *__restrict__ libs_out, int B, int slots)
+                 uint8_t *__restrict__ legal_out, uint8_t *libs_out, int B, int slots)   // libs_out may alias libs_in
 {
     // one block of three warps per board: warp w owns squares 32w .. 32w+31 (one square per thread)
     const int slot = (int)blockIdx.x;
@@ -48,8 +42,7 @@ bk_encode_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ 
 
     uint4 *conv_base = nullptr;
     if (feats_conv) {
-        const int g = slot / BK_GROUP, bi = slot - g * BK_GROUP;
-        conv_base = feats_conv + (size_t)g * (BK_F_CHUNKS * BK_F_ROWS_G) + bi * BK_F_ROWS_B;
+        conv_base = bk_conv_base(feats_conv, slot);
         // zero rows/columns of this board's block (and the whole block for a slot past the batch)
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         for (int r = threadIdx.x; r < BK_F_ROWS_B; r += 96) {
@@ -81,7 +74,6 @@ bk_encode_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ 
     white.w[1] = ((wh[0] >> 27) | (wh[1] << 5)) & BK_M27;
     white.w[2] = ((wh[1] >> 22) | (wh[2] << 10)) & BK_M27;
     const bool blk = (turn & 1) == 0;
-    const BB own = blk ? black : white, opp = blk ? white : black;
     const bool carried = libs_in != nullptr;
     const bool stale = carried && last >= 0 && libs_in[(size_t)b * BK_NSQ + last] == 0;
 
@@ -91,67 +83,13 @@ bk_encode_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ 
     __shared__ BKGroups grp;
     const int p = lane + 32 * wsq;
     const bool active = p < BK_NSQ;
-    const bool mine = active && bb_test(own, p), theirs = active && bb_test(opp, p);
     bk_groups_build(grp, black, white, p);
     __syncthreads();   // the table is complete; also: every thread has read libs_in[last], so libs_out may alias libs_in
     if (!active) return;
 
-    // ---- per-square evaluation --------------------------------------------------------------------
-    {
-        int lib = 0;
-        if (mine || theirs) {
-            if (!carried) lib = bb_count(bk_group_libs(grp, p));            // fresh Game: exact liberties
-            else lib = bk_groups_lazy_lib(grp, black, white, last, stale, p, (int)libs_in[(size_t)b * BK_NSQ + p]);
-        } else if (carried) {
-            lib = (int)libs_in[(size_t)b * BK_NSQ + p];                      // stale values persist on empty squares (go.py:220-243)
-        }
-        int la = 0, cp = 0;
-        bool lg = false;
-        if (!mine && !theirs) {
-            // the move "own stone on p" (nnet.py:241-247, go.py:404-418): a dead opponent group is counted once per
-            // neighbour of p that belongs to it; liberties of the merged own group after the removal
-            const Cand c = bk_groups_candidate(grp, own, opp, p, nullptr);
-            lg = bb_listed_legal(own, opp, ko, p, c);
-            if (lg) { la = c.libs_after; cp = c.caps; }
-        }
-        if (libs_out) libs_out[(size_t)b * BK_NSQ + p] = (uint8_t)lib;
-        if (legal_out) legal_out[(size_t)b * BK_NSQ + p] = (uint8_t)lg;
-
-        // plane values (nnet.py:249-262): planes 6..12 / 13..19 / 20..26 hold min(v,7) in slot min(v,7)-1
-        const int l7 = lib > 6 ? 7 : lib, a7 = la > 6 ? 7 : la, c7 = cp > 6 ? 7 : cp;
-        int v[32];
-        v[0] = mine; v[1] = theirs; v[2] = (!mine && !theirs); v[3] = blk; v[4] = (p == last); v[5] = lg;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            v[6 + i] = (l7 == i + 1) ? l7 : 0;
-            v[13 + i] = (a7 == i + 1) ? a7 : 0;
-            v[20 + i] = (c7 == i + 1) ? c7 : 0;
-        }
-#pragma unroll
-        for (int i = 27; i < 32; ++i) v[i] = 0;
-
-        if (planes_u8) {
-#pragma unroll
-            for (int c = 0; c < 27; ++c) planes_u8[((size_t)b * 27 + c) * BK_NSQ + p] = (uint8_t)v[c];
-        }
-        if (feats_f32) {
-#pragma unroll
-            for (int c = 0; c < 27; ++c) feats_f32[((size_t)b * 27 + c) * BK_NSQ + p] = (float)v[c];
-        }
-        if (conv_base) {
-            const int x = p / 9, y = p - 9 * x;
-            const int r = 22 + 11 * x + y;
-#pragma unroll
-            for (int c = 0; c < BK_F_CHUNKS; ++c) {
-                uint4 o;
-                o.x = pack2(v[8 * c + 0], v[8 * c + 1]);
-                o.y = pack2(v[8 * c + 2], v[8 * c + 3]);
-                o.z = pack2(v[8 * c + 4], v[8 * c + 5]);
-                o.w = pack2(v[8 * c + 6], v[8 * c + 7]);
-                conv_base[c * BK_F_ROWS_G + r] = o;
-            }
-        }
-    }
+    // ---- per-square evaluation (bk_encode_core.cuh) ---------------------------------------------------
+    bk_encode_square(grp, black, white, blk, ko, last, carried, stale, carried ? (int)libs_in[(size_t)b * BK_NSQ + p] : 0, p,
+                     (size_t)b, conv_base, feats_f32, planes_u8, legal_out, libs_out);
 }
 
 // float32 planes [B][27][81] (what nnet.features returns) -> the conv kernel's fp16 operand layout.

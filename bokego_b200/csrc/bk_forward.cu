@@ -34,6 +34,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "bk_layout.h"
 
 namespace {
@@ -909,7 +911,19 @@ extern "C" int bk_weights_pack(const float *w0, const float *w16, const float *b
     return 0;
 }
 
-static unsigned int *g_dbg_host = nullptr;   // pinned, device-visible; survives a trapped kernel
+// Host-side launch state.  Everything that depends on the device (kernel attributes, SM count, tensor maps over a blob) is
+// kept PER DEVICE and guarded by one mutex, so the entry points may be called from several host threads and for several
+// devices of one process (ctypes releases the GIL during a call).
+static std::mutex g_fwd_mutex;
+static unsigned int *g_dbg_host = nullptr;   // pinned, portable, device-visible; survives a trapped kernel
+struct FwdMapEntry { const void *blob; CUtensorMap stage, bias; unsigned long long used; };
+struct FwdDeviceState {
+    int n_sm = 0;                    // 0 = tcgen05 kernel attributes not set yet on this device
+    bool simt_attr = false;
+    FwdMapEntry maps[8] = {};        // tensor maps depend on the blob address only; a handful of nets are live at a time
+    unsigned long long tick = 0;
+};
+static FwdDeviceState g_fwd_dev[BK_MAX_DEVICES];
 
 // Tensor map over the conv weights of one blob: rows of 512 bytes, boxes of 8 rows (one CTA's half of a stage).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -917,7 +931,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static int make_weight_map(const void *blob, int box_rows, CUtensorMap *out)
 {
-    static EncodeTiledFn encode = nullptr;
+    static EncodeTiledFn encode = nullptr;   // process-wide driver entry point; callers hold g_fwd_mutex
     if (!encode) {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -934,6 +948,32 @@ static int make_weight_map(const void *blob, int box_rows, CUtensorMap *out)
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -1;
+}
+
+// tensor maps of `blob` on the current device (callers hold g_fwd_mutex); zero maps for a null blob
+static int weight_maps(FwdDeviceState &ds, const void *blob, CUtensorMap *stage, CUtensorMap *bias)
+{
+    if (!blob) {
+        memset(stage, 0, sizeof(*stage));
+        memset(bias, 0, sizeof(*bias));
+        return 0;
+    }
+    FwdMapEntry *victim = &ds.maps[0];
+    for (FwdMapEntry &e : ds.maps) {
+        if (e.blob == blob) {
+            e.used = ++ds.tick;
+            *stage = e.stage; *bias = e.bias;
+            return 0;
+        }
+        if (e.used < victim->used) victim = &e;
+    }
+    int rc = make_weight_map(blob, TM_BOX_ROWS, &victim->stage);
+    if (rc == 0) rc = make_weight_map(blob, TM_BIAS_BOX_ROWS, &victim->bias);
+    if (rc != 0) { victim->blob = nullptr; victim->used = 0; return rc; }
+    victim->blob = blob;
+    victim->used = ++ds.tick;
+    *stage = victim->stage; *bias = victim->bias;
+    return 0;
 }
 
 extern "C" int bk_debug_words(unsigned int *out8)
@@ -980,30 +1020,33 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
     a.g_whole = a.G; a.split = 1; a.n_sub = a.G; a.n_pairs = 0;
     a.dump = dump; a.dump_pass = dump_pass; a.prof = prof;
     a.diag = prof ? ((flags & 0x200) ? 1 : 0) | ((flags & 0x400) ? 2 : 0) : 0;
+    const int slot = bk_current_device_slot();
+    if (slot < 0) return -2;
+    std::lock_guard<std::mutex> lock(g_fwd_mutex);     // launches of one process are serialised here; the kernels are not
+    FwdDeviceState &ds = g_fwd_dev[slot];
     if (!g_dbg_host) {
-        if (cudaHostAlloc((void **)&g_dbg_host, 64, cudaHostAllocMapped) != cudaSuccess) g_dbg_host = nullptr;
+        if (cudaHostAlloc((void **)&g_dbg_host, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) g_dbg_host = nullptr;
         else memset(g_dbg_host, 0, 64);
     }
     a.dbg = nullptr;
     if (g_dbg_host) cudaHostGetDevicePointer((void **)&a.dbg, g_dbg_host, 0);
     cudaError_t e;
     if (flags & BK_FWD_SIMT) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        if (!ds.simt_attr) {
             e = cudaFuncSetAttribute(bk_forward_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SIMT_SMEM);
             if (e != cudaSuccess) return -3;
-            attr_done = true;
+            ds.simt_attr = true;
         }
         bk_forward_simt_kernel<<<B * a.n_nets, 128, SIMT_SMEM, stream>>>(a);
     } else {
-        static int n_sm = 0;
-        if (!n_sm) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (!ds.n_sm) {
+            int n_sm = 0;
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, slot);
             e = cudaFuncSetAttribute(bk_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-            if (e != cudaSuccess) { n_sm = 0; return -3; }
+            if (e != cudaSuccess || n_sm < 2) return -3;
+            ds.n_sm = n_sm;
         }
+        const int n_sm = ds.n_sm;
         // Schedule (see FwdArgs): CTA pairs take two groups of one net at a time.  The pairs of whole groups fill
         // complete rounds of the n_sm / 2 clusters; the groups left over for the last, partial round are split into
         // board ranges so that it spreads over the idle SMs (fewer M tiles per CTA).
@@ -1019,18 +1062,12 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
         a.n_sub = a.g_whole + (a.G - a.g_whole) * a.split;
         a.n_pairs = a.n_nets * ((a.n_sub + 1) / 2);
         const int grid = 2 * (a.n_pairs < n_clusters ? a.n_pairs : n_clusters);
-        static const void *cached_blob[2] = {nullptr, nullptr};   // the maps depend on the blob addresses only
-        static CUtensorMap cached_map[2], cached_bias_map[2];
+        CUtensorMap map[2], bias_map[2];
         for (int i = 0; i < 2; ++i) {
-            if (cached_blob[i] != a.blob[i] || !a.blob[i]) {
-                int rc = make_weight_map(a.blob[i], TM_BOX_ROWS, &cached_map[i]);
-                if (rc == 0) rc = make_weight_map(a.blob[i], TM_BIAS_BOX_ROWS, &cached_bias_map[i]);
-                if (rc != 0) return rc;
-                cached_blob[i] = a.blob[i];
-            }
+            const int rc = weight_maps(ds, a.blob[i], &map[i], &bias_map[i]);
+            if (rc != 0) return rc;
         }
-        bk_forward_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, stream>>>(a, cached_map[0], cached_map[1], cached_bias_map[0],
-                                                                     cached_bias_map[1]);
+        bk_forward_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, stream>>>(a, map[0], map[1], bias_map[0], bias_map[1]);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

@@ -64,4 +64,11 @@
 #define BK_FWD_SIMT 4        /* validation path: plain CUDA-core kernel instead of tcgen05 */
 #define BK_FWD_NOSPLIT 8     /* measurement only: do not split the items of the last partial round */
 
+
+/* per-device launch state (kernel attributes, SM count, tensor maps) is kept in arrays of this size, guarded by a mutex */
+#define BK_MAX_DEVICES 64
+#ifdef __cplusplus
+int bk_current_device_slot(void);   /* bk_api.cu: index of the current CUDA device, -1 if none / out of range */
+#endif
+
 #endif

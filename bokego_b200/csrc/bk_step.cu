@@ -15,11 +15,15 @@
 //       device, independent of how games are sharded over GPUs.
 //       The move is played with Game.play_move semantics (go.py:123-182) including the lazy liberty cache
 //       refresh that precedes the board update (go.py:160).
+//       With `feats_conv` the kernel goes on to encode the position AFTER the move (nnet.features with the carried liberty
+//       cache, bk_encode_core.cuh) into the conv operand of the next policy evaluation: "sample, play, capture, re-encode"
+//       is one launch, and a playout move is two launches (policy forward, this kernel) instead of three.
 //   bk_score_kernel  Game.score() (go.py:202-218) and the +-1 reward of Go_MCTS.reward (mcts.py:330-338).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "bk_bitboard.cuh"
+#include "bk_encode_core.cuh"
 
 namespace {
 
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(96)
 bk_step_kernel(int8_t *__restrict__ boards, int16_t *__restrict__ ko_arr, int16_t *__restrict__ last_arr,
                int16_t *__restrict__ turn_arr, uint8_t *__restrict__ libs, uint8_t *__restrict__ done,
                const float *__restrict__ probs, const float *__restrict__ q_inj, int q_vecs, uint64_t seed,
-               uint32_t game0, int mode, int max_turn, int16_t *__restrict__ moves_out, int B)
+               uint32_t game0, int mode, int max_turn, int16_t *__restrict__ moves_out, uint4 *__restrict__ feats_conv, int B)
 {
     __shared__ BKGroups grp;
     __shared__ float s_v[3];
@@ -192,11 +196,22 @@ bk_step_kernel(int8_t *__restrict__ boards, int16_t *__restrict__ ko_arr, int16_
         return;
     }
     if (active) bd[p] = bb_test(black, p) ? 1 : (bb_test(white, p) ? -1 : 0);
+    const bool over = mode == 0 ? (turn > max_turn || last == BK_PASS) : (turn > max_turn + 1);
     if (threadIdx.x == 0) {
         ko_arr[b] = (int16_t)ko; last_arr[b] = (int16_t)last; turn_arr[b] = (int16_t)turn;
-        const bool over = mode == 0 ? (turn > max_turn || last == BK_PASS) : (turn > max_turn + 1);
         if (over) done[b] = 1;
     }
+    if (!feats_conv || over) return;        // block-uniform
+
+    // ---- re-encode: nnet.features of the new position with the carried cache (what the next policy call sees) -------
+    __syncthreads();                         // every thread is done with the old table; the cache refresh above is visible
+    bk_groups_build(grp, black, white, p);
+    uint8_t *lb = libs + (size_t)b * BK_NSQ;
+    const bool stale2 = last >= 0 && lb[last] == 0;
+    __syncthreads();                         // table complete; lb[last] has been read by everyone before lb[] is rewritten
+    if (!active) return;
+    bk_encode_square(grp, black, white, (turn & 1) == 0, ko, last, true, stale2, (int)lb[p], p, (size_t)b,
+                     bk_conv_base(feats_conv, b), nullptr, nullptr, nullptr, libs);
 }
 
 __global__ void __launch_bounds__(128)
@@ -277,8 +292,20 @@ extern "C" int bk_playout_step(int8_t *boards, int16_t *ko, int16_t *last, int16
                               int max_turn, int16_t *moves_out, int B, cudaStream_t stream)
 {
     if (B <= 0) return 0;
+    if (!boards || !ko || !last || !turn || !done || !probs) return -1;
     bk_step_kernel<<<B, 96, 0, stream>>>(boards, ko, last, turn, libs, done, probs, q_inj, q_vecs, seed, game0,
-                                                    mode, max_turn, moves_out, B);
+                                                    mode, max_turn, moves_out, nullptr, B);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+extern "C" int bk_playout_step_encode(int8_t *boards, int16_t *ko, int16_t *last, int16_t *turn, uint8_t *libs, uint8_t *done,
+                                     const float *probs, const float *q_inj, int q_vecs, uint64_t seed, uint32_t game0,
+                                     int mode, int max_turn, int16_t *moves_out, void *feats_conv, int B, cudaStream_t stream)
+{
+    if (B <= 0) return 0;
+    if (!boards || !ko || !last || !turn || !done || !probs || !libs || !feats_conv) return -1;
+    bk_step_kernel<<<B, 96, 0, stream>>>(boards, ko, last, turn, libs, done, probs, q_inj, q_vecs, seed, game0,
+                                                    mode, max_turn, moves_out, (uint4 *)feats_conv, B);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

@@ -21,7 +21,10 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/bokego_b200.h"
+#include "bk_layout.h"
 #include "bk_train_args.h"
 
 namespace {
@@ -613,10 +616,15 @@ Ws ws_layout(int P)
     return w;
 }
 
-bool attrs_set = false;
+// kernel attributes are per device: one flag per device, guarded by a mutex (several host threads / devices per process)
+std::mutex attrs_mutex;
+bool attrs_set[BK_MAX_DEVICES] = {};
 int set_attrs()
 {
-    if (attrs_set) return 0;
+    const int slot = bk_current_device_slot();
+    if (slot < 0) return -2;
+    std::lock_guard<std::mutex> lock(attrs_mutex);
+    if (attrs_set[slot]) return 0;
     cudaError_t e = cudaSuccess;
 #define BK_SET(k, n) if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, n)
     BK_SET(bk_train_conv_kernel<0>, CONV_SMEM);
@@ -627,7 +635,7 @@ int set_attrs()
     BK_SET(bk_train_wgrad_kernel<2>, WGRAD_SMEM);
 #undef BK_SET
     if (e != cudaSuccess || bk_tc_set_attrs() != 0) return -3;
-    attrs_set = true;
+    attrs_set[slot] = true;
     return 0;
 }
 

@@ -253,13 +253,19 @@ def prefill_caches(tree_cls, nodes, policy_net, value_net=None, device=None):
         libs = np.stack([np.frombuffer(bytes(n._libs), dtype=np.uint8) for n in part]) if carried else None
         pos = Positions.from_numpy(bd, ko, last, [int(n.turn) for n in part], dev, libs)
         out = features_batch(pos, want=("conv", "f32", "libs"))
-        _, probs, vals = policy_value_batch(out["conv"], len(part), pnet, vnet, want_logits=False)
-        f32, libs_out, probs = out["f32"].cpu(), out["libs"].cpu().numpy(), probs.cpu()
+        logits, _, vals = policy_value_batch(out["conv"], len(part), pnet, vnet, want_logits=True)
+        # the distribution exactly as policy_dist builds it (nnet.py:265-275: SOFT of the logits, then Categorical's
+        # renormalisation, both on the device) and as Go_MCTS.dist stores it (probabilities moved to the CPU, mcts.py:381)
+        probs = SOFT(logits)
+        probs = (probs / probs.sum(-1, keepdim=True)).cpu()
+        f32, libs_out = out["f32"].cpu(), out["libs"].cpu().numpy()
         vals = None if vals is None else vals.cpu()
         for i, n in enumerate(part):
             n._libs = bytearray(libs_out[i].tobytes())
             tree_cls._fts_cache[n] = f32[i]
-            tree_cls._dist_cache[n] = Categorical(probs[i])
+            dist = Categorical(probs[i])
+            dist.probs = probs[i]
+            tree_cls._dist_cache[n] = dist
             if vals is not None:
-                tree_cls._val_cache[n] = float(vals[i])
+                tree_cls._val_cache[n] = vals[i].item()
     return len(todo)

@@ -1,8 +1,8 @@
 """Whole playouts and self-play games on the device, sharded over ranks (SURVEY 8b `playout_batch`, 8e).
 
-One move step for every board of a batch = three kernel launches, boards resident in HBM:
-    bk_encode (carried liberty cache, in place)  ->  bk_forward (policy only)  ->  bk_playout_step
-which is exactly the loop of the reference's `MCTS._simulate` (/root/reference/bokego/mcts.py:195-206: `find_random_child`
+One move step for every board of a batch = two kernel launches, boards resident in HBM:
+    bk_forward (policy only)  ->  bk_playout_step_encode (sample, play, capture, re-encode the new position in place)
+after one bk_encode of the starting positions -- which is exactly the loop of the reference's `MCTS._simulate` (/root/reference/bokego/mcts.py:195-206: `find_random_child`
 until terminal, then `reward`) and of `bin/selfplay.py:18-33` (`playout`: `legal_sample` for pi_1 / pi_2 alternately), run for
 all boards at once.  The steps of a whole game are captured once in a CUDA graph and replayed (the per-step work is small
 at self-play batch sizes, so launch latency matters).
@@ -84,14 +84,23 @@ def run_playouts(pos, policy, mode=MODE_MCTS, max_turn=None, seed=0, game0=0, po
     bufs = {"conv": torch.empty(L.bk_feats_conv_bytes(B), dtype=torch.uint8, device=dev), "libs": pos.libs}
     probs = torch.empty(B, 81, dtype=torch.float32, device=dev)
 
+    training = any(hasattr(n, "play_probs") for n in (policy, policy_odd) if n is not None)
+    encoded = [False]      # bufs["conv"] holds the planes of the current positions (written by the previous move's launch)
+
     def step(k, fresh):
         net = policy if (policy_odd is None or (first_turn + k) % 2 == 0) else policy_odd
         if hasattr(net, "play_probs"):     # a net being trained (reinforce.PolicyTrainer): train-mode forward, positions recorded
             net.play_probs(pos, fresh, bufs, probs)
+            encoded[0] = False
         else:
-            features_batch(pos, fresh_libs=fresh, want=("conv", "libs"), out=bufs)
+            if not encoded[0]:
+                features_batch(pos, fresh_libs=fresh, want=("conv", "libs"), out=bufs)
             policy_value_batch(bufs["conv"], B, net, None, want_logits=False, probs_out=probs)
-        playout_step(pos, probs, mode, max_turn, seed=seed, game0=game0, moves_out=moves[k])
+        # with a net in training in the loop the trainer encodes for itself (it needs the byte planes), so only fuse otherwise
+        fuse = not training
+        playout_step(pos, probs, mode, max_turn, seed=seed, game0=game0, moves_out=moves[k],
+                     encode_into=bufs["conv"] if fuse else None)
+        encoded[0] = fuse
 
     k0 = 0
     if fresh_first and n_steps > 0:
@@ -139,17 +148,17 @@ class PlayoutGraph:
 
         def body():
             pos.boards.zero_(); pos.ko.fill_(-1); pos.last.fill_(-2); pos.turn.zero_(); pos.done.zero_()
+            features_batch(pos, fresh_libs=True, want=("conv", "libs"), out=bufs)
             for k in range(self.n_steps):
                 net = policy if (policy_odd is None or k % 2 == 0) else policy_odd
-                features_batch(pos, fresh_libs=(k == 0), want=("conv", "libs"), out=bufs)
                 policy_value_batch(bufs["conv"], B, net, None, want_logits=False, probs_out=probs)
-                playout_step(pos, probs, mode, max_turn, seed=seed, game0=game0, moves_out=self.moves[k])
+                playout_step(pos, probs, mode, max_turn, seed=seed, game0=game0, moves_out=self.moves[k], encode_into=bufs["conv"])
             score_batch(pos.boards, komi, out=(self.score, self.reward))
 
         # one eager step first: the library sets its kernel attributes on first use, which must not happen under capture
         features_batch(pos, fresh_libs=True, want=("conv", "libs"), out=bufs)
         policy_value_batch(bufs["conv"], B, policy, None, want_logits=False, probs_out=probs)
-        self.launches = 5 + 3 * self.n_steps + 1
+        self.launches = 5 + 1 + 2 * self.n_steps + 1
         self.graph = torch.cuda.CUDAGraph()
         cap = torch.cuda.Stream(device=dev)
         cap.wait_stream(torch.cuda.current_stream(dev))

@@ -8,8 +8,10 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name says host; buffers are caller-allocated,
- *     contiguous, and owned by the caller; the library allocates nothing and keeps no global state
- *     apart from one-time kernel attributes;
+ *     contiguous, and owned by the caller; the library allocates no device memory.  Its only state is launch state kept PER
+ *     DEVICE behind a mutex (kernel attributes, SM count, tensor maps over the weight blobs it has seen), so the entry
+ *     points may be called from several host threads and for several devices of one process; the current device
+ *     (cudaSetDevice) selects where the work runs;
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
  *   - return value: 0 = ok, BK_ERR_ARG = bad argument, BK_ERR_DEVICE = not an sm_100 device,
  *     BK_ERR_LAUNCH = CUDA launch error (see cudaGetLastError);
@@ -87,6 +89,14 @@ int bk_forward(const void *feats_conv, const void *blob_policy, const void *blob
 int bk_playout_step(int8_t *boards, int16_t *ko, int16_t *last, int16_t *turn, uint8_t *libs,
                     uint8_t *done, const float *probs, const float *q_inj, int q_vecs, uint64_t seed,
                     uint32_t game0, int mode, int max_turn, int16_t *moves_out, int B, void *stream);
+/* bk_playout_step followed, in the same launch, by bk_encode of the position after the move (carried liberty cache, in place)
+ * into feats_conv -- the "sample, play, capture, re-encode" step of a playout loop (mcts.py:195-206, selfplay.py:18-33), so that
+ * a playout move is two launches: bk_forward (policy), bk_playout_step_encode.  libs must not be NULL; feats_conv must be the
+ * buffer a previous bk_encode of the same B boards wrote (its padding rows stay untouched); boards that are finished after the
+ * move keep their old planes. */
+int bk_playout_step_encode(int8_t *boards, int16_t *ko, int16_t *last, int16_t *turn, uint8_t *libs, uint8_t *done,
+                           const float *probs, const float *q_inj, int q_vecs, uint64_t seed, uint32_t game0, int mode,
+                           int max_turn, int16_t *moves_out, void *feats_conv, int B, void *stream);
 /* Go_MCTS.make_move (bokego/mcts.py:340-346) for C children: child c = copy of parent parent_idx[c] (an index into the
  * parent arrays) with moves[c] played by Game.play_move (go.py:123-182; -1 = play_pass go.py:109-121).  The lazy liberty
  * cache is refreshed on the parent position before the move (go.py:160) and handed to the child; libs == NULL means the

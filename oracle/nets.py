@@ -64,6 +64,33 @@ def value(sd, feats):
     return torch.tanh(F.linear(h, _t(sd["lin2.weight"]), _t(sd["lin2.bias"]))).reshape(-1)
 
 
+def folded(sd):
+    """BatchNorm(eval) folded into the seven convs in float64: w' = w * g / sqrt(var + eps), b' = (b - mean) * g / sqrt(var + eps) + beta"""
+    ws, bs = [], []
+    for i in CONV_IDX:
+        w, b = _t(sd[f"conv.{i}.weight"]).double(), _t(sd[f"conv.{i}.bias"]).double()
+        s = _t(sd[f"conv.{i + 1}.weight"]).double() / torch.sqrt(_t(sd[f"conv.{i + 1}.running_var"]).double() + 1e-5)
+        ws.append(w * s[:, None, None, None])
+        bs.append((b - _t(sd[f"conv.{i + 1}.running_mean"]).double()) * s + _t(sd[f"conv.{i + 1}.bias"]).double())
+    return ws, bs
+
+
+@torch.no_grad()
+def policy_logits_f16_operands(sd, feats):
+    """The arithmetic the north-star prescribes for the conv kernel, emulated on the CPU: BatchNorm folded, conv weights and
+    the activations handed from layer to layer rounded to fp16 (round-to-nearest-even), every sum in fp32, bias / ReLU / the
+    1x1 head in fp32.  NOT the reference's result: it is the yardstick that separates "error of 16-bit operands" (what this
+    function shows against policy_logits) from "error of the kernel" (what the kernel shows against this function)."""
+    h = lambda t: t.float().half().float()
+    ws, bs = folded(sd)
+    a = _t(feats).float()
+    for l in range(7):
+        y = F.conv2d(a, h(ws[l]), None, padding=ws[l].shape[-1] // 2) + bs[l].float()[None, :, None, None]
+        y = F.relu(y)
+        a = h(y) if l < 6 else y
+    return head81(sd, a)
+
+
 def planes_to_float(feats_u8):
     """uint8 [B,27,81] plane values -> float32 [B,27,9,9] exactly as nnet.features returns them."""
     return torch.from_numpy(np.asarray(feats_u8)).float().reshape(-1, 27, 9, 9)

@@ -71,3 +71,67 @@ def test_results_do_not_depend_on_sharding(env):
         assert torch.equal(p, whole.records())
     lo, hi, sim = po.simulate(64, p17, dev, seed=9, rank=1, world=2)
     assert (lo, hi) == (32, 64) and sim.moves.shape[0] == 32
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fused_step_encode_equals_step_then_encode(env, mode):
+    """bk_playout_step_encode == bk_playout_step followed by bk_encode (carried cache, in place): boards, ko / last / turn,
+    liberty cache, done flags, moves and every byte of the conv operand, move after move to the end of the games; and the
+    planes of the fused path decode to the oracle's features of the same positions"""
+    bk, po, dev, p17, p19 = env
+    B, seed = 203, 21
+    max_turn = 80 if mode == 0 else 70
+    a, b = bk.Positions.empty(B, dev), bk.Positions.empty(B, dev)
+    fa = bk.features_batch(a, fresh_libs=True, want=("conv", "libs"), out={"libs": a.libs})
+    fb = bk.features_batch(b, fresh_libs=True, want=("conv", "libs"), out={"libs": b.libs})
+    for k in range(po.n_steps_for(mode, max_turn)):
+        net = p17 if (mode == 0 or k % 2 == 0) else p19
+        _, probs, _ = bk.policy_value_batch(fa["conv"], B, net, None, want_logits=False)
+        ma = bk.playout_step(a, probs, mode, max_turn, seed=seed, game0=9, encode_into=fa["conv"])
+        live = b.done == 0
+        mb = bk.playout_step(b, probs, mode, max_turn, seed=seed, game0=9)
+        fresh = bk.features_batch(b, fresh_libs=False, want=("conv", "libs"), out={"libs": b.libs})
+        # boards that finished with this move keep their old planes in the fused path (nobody evaluates them again)
+        still = (b.done == 0)
+        conv_b = torch.where(_board_mask(still, fb["conv"].numel(), dev), fresh["conv"], fb["conv"])
+        fb["conv"] = conv_b
+        assert torch.equal(ma, mb), k
+        for x, y in ((a.boards, b.boards), (a.ko, b.ko), (a.last, b.last), (a.turn, b.turn), (a.done, b.done)):
+            assert torch.equal(x, y), k
+        assert torch.equal(a.libs[still], b.libs[still]), k
+        assert torch.equal(fa["conv"], fb["conv"]), k
+        if k in (0, 7, 40) and bool(still.any()):
+            idx = torch.nonzero(still).flatten()[:32]
+            sub = bk.Positions(a.boards[idx].contiguous(), a.ko[idx].contiguous(), a.last[idx].contiguous(), a.turn[idx].contiguous())
+            want, _, _ = ocpu.features_batch(*(t.cpu().numpy() for t in (sub.boards, sub.ko, sub.last, sub.turn)), None)
+            got = _decode_conv(fa["conv"], B)[idx.cpu().numpy()]
+            # planes 6..12 (liberties) depend on the carried cache; every other plane is a function of the position alone
+            keep = [c for c in range(27) if not 6 <= c <= 12]
+            assert np.array_equal(got[:, keep], want[:, keep]), k
+        if not bool(live.any()):
+            break
+    assert bool((a.done != 0).all())
+
+
+def _board_mask(board_flags, nbytes, dev):
+    """byte mask over the conv operand: True for the bytes of boards whose flag is set ([group][4 chunks][605 rows][16 B])"""
+    B = board_flags.numel()
+    G = (B + 4) // 5
+    flags = torch.zeros(G * 5, dtype=torch.bool, device=dev)
+    flags[:B] = board_flags
+    rows = flags.reshape(G, 5, 1).expand(G, 5, 121).reshape(G, 1, 605, 1).expand(G, 4, 605, 16)
+    return rows.reshape(-1)[:nbytes]
+
+
+def _decode_conv(conv, B):
+    """conv operand -> uint8 planes [B][27][81]"""
+    G = (B + 4) // 5
+    h = conv.view(torch.float16).reshape(G, 4, 605, 8).cpu().float().numpy()
+    out = np.zeros((G * 5, 27, 81), np.uint8)
+    for bi in range(5):
+        for x in range(9):
+            for y in range(9):
+                r = 121 * bi + 22 + 11 * x + y
+                v = h[:, :, r, :].reshape(G, 32)[:, :27]
+                out[bi::5][:, :, 9 * x + y] = v.astype(np.uint8)
+    return out[:B]
