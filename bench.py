@@ -6,7 +6,8 @@ pass of the hot path over one batch of synthetic legal 9x9 positions:
     boards -> bk_encode (27 feature planes) -> bk_forward (PolicyNet + ValueNet, softmax / tanh fused).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B]        our arm (CUDA kernels via the C ABI)
-    python bench.py --impl reference ...                                   the CPU arm (oracle port on host cores)
+    python bench.py --impl reference ...                                   the CPU arm: the unmodified reference from baseline/_ref
+                                                                           on the host cores (the oracle port if it is not installed)
 
 N > 1 is launched by the driver as torchrun, one rank per GPU; positions are independent, so every rank
 evaluates its own batch (weak scaling, no collective on the data path) and rank 0 reports the aggregate.
@@ -28,6 +29,46 @@ sys.path.insert(0, ROOT)
 
 FLOP_VALID = 266_838_272     # policy+value eval, zero-padding MACs excluded -- primary
 FLOP_DENSE = 314_700_032     # what nn.Conv2d executes with zero padding -- secondary
+
+
+WORKLOAD = "batched PolicyNet+ValueNet forward incl. feature encoding, batch 4096 synthetic legal 9x9 positions (BASELINE configs[1])"
+
+
+def bench_config(batch):
+    """the `config` object of BOTH arms (identical keys and values, so the driver can compare the lines)"""
+    return {"workload": WORKLOAD, "batch_per_gpu": batch, "weights": "policy_17 + stand-in ValueNet (policy_19 trunk, seeded head)",
+            "positions": "seeded uniformly-random legal play, depth ~ U{0..70}, evaluated as fresh positions",
+            "l2": "GPU arm: L2 flushed between timed iterations (256 MiB memset); CPU arm: not applicable"}
+
+
+def reference_root():
+    """the unmodified reference installed by tools/install_reference.sh (git-ignored, travels to the GPU box), or None"""
+    r = os.path.join(ROOT, "baseline", "_ref")
+    return r if os.path.isfile(os.path.join(r, "bokego", "nnet.py")) else None
+
+
+def import_reference():
+    """the reference's own modules (go, nnet, mcts, gtp) from baseline/_ref -- used by the CPU legs only"""
+    import importlib
+    r = reference_root()
+    if r is None:
+        return None
+    for k in [k for k in sys.modules if k == "bokego" or k.startswith("bokego.")]:
+        del sys.modules[k]
+    if r not in sys.path:
+        sys.path.insert(0, r)
+    mods = tuple(importlib.import_module("bokego." + m) for m in ("go", "nnet", "mcts", "gtp"))
+    assert os.path.abspath(mods[1].__file__).startswith(os.path.abspath(r)), "bokego.nnet is not the reference's"
+    return mods
+
+
+def reference_nets(nnet, sd17, sdv):
+    """the reference's nn.Modules with the bench weights (CPU, eval)"""
+    t = lambda sd: {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+    pi, v = nnet.PolicyNet(), nnet.ValueNet()
+    pi.load_state_dict(t(sd17))
+    v.load_state_dict(t(sdv))
+    return pi.eval(), v.eval()
 
 
 def load_nets():
@@ -206,6 +247,85 @@ def cpu_selfplay_rate(n_games, sd17, sd19, seed=1):
     return n_games / dt, cores, dt
 
 
+def cpu_simulate_rate(n_boards, sd17, seed=2):
+    """CPU arm of the --simulate line: MCTS-flavour playouts (Go_MCTS.find_random_child to the end, mcts.py:195-206) through the
+    oracle port -- C feature encoder + fp32 torch CPU policy forward + C stepping -- all boards of the sample in lock step"""
+    from oracle import cpu as ocpu
+    from oracle import nets as onets
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    net = {k: torch.from_numpy(np.asarray(v)) for k, v in sd17.items()}
+    bd = np.zeros((n_boards, 81), np.int8); ko = np.full(n_boards, -1, np.int16); last = np.full(n_boards, -2, np.int16)
+    turn = np.zeros(n_boards, np.int16); done = np.zeros(n_boards, np.uint8); libs = None
+    t0 = time.perf_counter()
+    for k in range(81):
+        f, _, libs = ocpu.features_batch(bd, ko, last, turn, libs)
+        probs = onets.policy_probs(net, onets.planes_to_float(f)).numpy()
+        ocpu.step_batch(bd, ko, last, turn, libs, done, probs, 0, 80, seed=seed, game0=0)
+        if done.all():
+            break
+    ocpu.score_batch(bd)
+    dt = time.perf_counter() - t0
+    return n_boards / dt, cores, dt
+
+
+def cpu_genmove_reference(sd17, sdv, n_rollouts):
+    """BASELINE configs[0] / the CPU side of configs[2]: the reference's own engine on the host CPU, unmodified --
+    GTP(Go_MCTS(), pi, v, no_sim=True, time_lim=0, n_rollouts=n).send("genmove b") (gtp.py:344-366; boke.py's `-r` is never
+    forwarded, SURVEY 3.1, so the engine is constructed directly).  One thread, as the reference runs it."""
+    mods = import_reference()
+    if mods is None:
+        return None
+    go, nnet, mcts, gtp = mods
+    torch.set_num_threads(1)
+    pi, v = reference_nets(nnet, sd17, sdv)
+    for c in (mcts.MCTS._val_cache, mcts.MCTS._dist_cache, mcts.MCTS._fts_cache):
+        c.clear()
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        g = gtp.GTP(mcts.Go_MCTS(), pi, v, no_sim=True, time_lim=0, n_rollouts=n_rollouts, pondering=False)
+        g.running = True
+        out = g.send("genmove b")
+        dt = time.perf_counter() - t0
+    return {"seconds": dt, "playouts_per_s": n_rollouts / dt, "move": out.strip("= \n"), "value_evals": len(mcts.MCTS._val_cache),
+            "policy_evals": len(mcts.MCTS._dist_cache), "cores": 1, "kind": "reference",
+            "sample": f"one genmove, {n_rollouts} rollouts from the empty board, nets on the CPU, torch threads 1"}
+
+
+def gpu_genmove_reference_callers(sd17, sdv, dev, n_rollouts, batched):
+    """The same engine -- the reference's gtp.py / mcts.py, unmodified, from baseline/_ref -- over the B200 mirror
+    (bokego_b200.dropin), nets on the GPU; `batched`: children of every expanded node evaluated in one launch pair through
+    the class-level caches (dropin.batch_expansions)."""
+    from bokego_b200 import _lib, dropin, nnet
+    if dropin.find_reference() is None:
+        return None
+    mcts, gtp, _ = dropin.reference_callers()
+    try:
+        t = lambda sd: {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+        pi, v = nnet.PolicyNet(), nnet.ValueNet()
+        pi.load_state_dict(t(sd17)); v.load_state_dict(t(sdv))
+        pi.eval().to(dev); v.eval().to(dev)
+        dropin.batch_expansions(mcts.MCTS, batched)
+        res = None
+        for rep in range(2):                     # the first pass warms the packed blobs and the kernels
+            for c in (mcts.MCTS._val_cache, mcts.MCTS._dist_cache, mcts.MCTS._fts_cache):
+                c.clear()
+            n0 = _lib.launch_count
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            g = gtp.GTP(mcts.Go_MCTS(), pi, v, no_sim=True, time_lim=0, n_rollouts=n_rollouts, pondering=False, device=dev)
+            g.running = True
+            out = g.send("genmove b")
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            res = {"seconds": dt, "playouts_per_s": n_rollouts / dt, "move": out.strip("= \n"), "kernel_launches": _lib.launch_count - n0,
+                   "value_evals": len(mcts.MCTS._val_cache), "batched_expansions": bool(batched)}
+        return res
+    finally:
+        dropin.batch_expansions(mcts.MCTS, False)
+        dropin.uninstall()
+
+
 FLOP_TRAIN = 2 * (2 * 66_706_944 + 6 * 10_240_000 + 10_368)   # forward + weight gradient + data gradient, valid taps, per position
 
 
@@ -294,32 +414,97 @@ def reinforce_leg(dev, sd17, sd19, with_cpu):
     return out
 
 
+_REF_WORKER = {}
+
+
+def _ref_worker_init(root):
+    """pool worker: import the reference once (CPU only)"""
+    sys.path.insert(0, root)
+    import bokego.go as go, bokego.nnet as nnet      # noqa: E401
+    torch.set_num_threads(1)
+    _REF_WORKER["go"], _REF_WORKER["nnet"] = go, nnet
+
+
+def _ref_worker_features(chunk):
+    """nnet.features (/root/reference/bokego/nnet.py:182-262) of a chunk of positions, each a fresh go.Game"""
+    go, nnet = _REF_WORKER["go"], _REF_WORKER["nnet"]
+    dec = {1: go.BLACK, -1: go.WHITE, 0: go.EMPTY}
+    out = []
+    for bd, ko, last, turn in chunk:
+        g = go.Game("".join(dec[int(v)] for v in bd), None if ko < 0 else int(ko), None if last == -2 else int(last), int(turn))
+        out.append(nnet.features(g).numpy())
+    return np.stack(out)
+
+
+class ReferenceEvaluator:
+    """The reference's own CPU implementation of the hot path, unmodified: nnet.features per position (one process per host
+    core) and PolicyNet / ValueNet fp32 forward over the batch with all torch threads (8d (ii))."""
+
+    def __init__(self, sd17, sdv):
+        import multiprocessing as mp
+        self.go, self.nnet, _, _ = import_reference()
+        self.cores = len(os.sched_getaffinity(0))
+        self.pi, self.v = reference_nets(self.nnet, sd17, sdv)
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_ref_worker_init, initargs=(reference_root(),))
+
+    def evaluate(self, bd, ko, last, turn):
+        n = len(bd)
+        step = max(1, (n + 4 * self.cores - 1) // (4 * self.cores))
+        chunks = [[(bd[i], int(ko[i]), int(last[i]), int(turn[i])) for i in range(lo, min(n, lo + step))] for lo in range(0, n, step)]
+        x = torch.from_numpy(np.concatenate(self.pool.map(_ref_worker_features, chunks)))
+        torch.set_num_threads(self.cores)
+        with torch.no_grad():
+            p = self.nnet.SOFT(self.pi(x))
+            v = self.v(x).reshape(-1)
+        return p, v
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
 def run_reference(args, rank, world):
+    """The CPU arm: the reference's own implementation on the host cores when baseline/_ref holds it (kind "reference"),
+    else the oracle port (kind "port").  Every step evaluates a bounded sample of the 4096-position batch."""
     if rank != 0:
         return
     sd17, _, sdv = load_nets()
-    # bounded sample: size it so that W+K steps end within a few minutes
-    probe, cores, _ = cpu_rate(256, sd17, sdv)
+    cores = len(os.sched_getaffinity(0))
+    ref = ReferenceEvaluator(sd17, sdv) if reference_root() is not None else None
+    if ref is not None:
+        kind = "reference"
+        how = f"unmodified reference from baseline/_ref: nnet.features in {cores} processes + PolicyNet/ValueNet fp32 torch forward, {cores} threads"
+        evaluate = ref.evaluate
+    else:
+        kind = "port"
+        how = f"C feature oracle (OpenMP) + fp32 torch CPU forward, {cores} threads"
+        torch.set_num_threads(cores)
+        sd17t = {k: torch.from_numpy(np.asarray(v)) for k, v in sd17.items()}
+        sdvt = {k: torch.from_numpy(np.asarray(v)) for k, v in sdv.items()}
+        evaluate = lambda *a: cpu_eval(*a, sd17t, sdvt)
+    # bounded sample: size it so that W + K steps end within about two minutes
+    bd, ko, last, turn = cpu_positions(args.batch, 1)
+    evaluate(bd[:64], ko[:64], last[:64], turn[:64])
+    t0 = time.perf_counter()
+    evaluate(bd[:256], ko[:256], last[:256], turn[:256])
+    probe = 256 / (time.perf_counter() - t0)
     budget_s = 120.0 / max(1, args.steps + args.warmup)
     sample = int(max(256, min(args.batch, probe * budget_s) // 256 * 256))
-    bd, ko, last, turn = cpu_positions(sample, 1)
-    torch.set_num_threads(cores)
-    sd17t = {k: torch.from_numpy(np.asarray(v)) for k, v in sd17.items()}
-    sdvt = {k: torch.from_numpy(np.asarray(v)) for k, v in sdv.items()}
+    bd, ko, last, turn = bd[:sample], ko[:sample], last[:sample], turn[:sample]
     for _ in range(args.warmup):
-        cpu_eval(bd, ko, last, turn, sd17t, sdvt)
+        evaluate(bd, ko, last, turn)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_eval(bd, ko, last, turn, sd17t, sdvt)
+        evaluate(bd, ko, last, turn)
     el = time.perf_counter() - t0
+    if ref is not None:
+        ref.close()
     val = sample * args.steps / el
     line = {"impl": "reference", "metric": "policy+value evals/sec", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "batched PolicyNet+ValueNet forward incl. feature encoding, batch 4096 synthetic legal 9x9 positions",
-                       "sample": f"{sample} positions per step (bounded sample of the 4096 batch)"},
-            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} positions/step x {args.steps} steps; C feature oracle (OpenMP) + fp32 torch CPU forward, {cores} threads"},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(args.batch),
+            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": kind,
+                             "sample": f"{sample} of the {args.batch} positions per step x {args.steps} steps; {how}"},
             "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -434,21 +619,42 @@ def run_ours(args, rank, world, local_rank):
                                   "kernel_launches_per_batch": sp.launches},
                      "simulate": {"boards_per_gpu": args.simulate_boards, "playouts_per_s": world * args.simulate_boards * 2 / (1e-3 * sim_tot),
                                   "ms_per_batch": sim_tot / 2, "scaling": "weak", "max_turn": 80}}
-            # BASELINE configs[2]: one genmove of the batched tree search, 1600 playouts from the empty board (rank 0's GPU)
-            from bokego_b200 import mcts as bmcts
-            bmcts.MCTS(None, pol, val, device=dev).rollout(10)
-            gm = {}
-            for name, kw in (("reference_parameters", {"expand_thresh": 100, "leaf_batch": 32}),
-                             ("expand_on_second_visit", {"expand_thresh": 1, "leaf_batch": 128})):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                tree = bmcts.MCTS(None, pol, val, device=dev, **kw)
-                tree.rollout(1600)
-                tree.choose()
-                torch.cuda.synchronize()
-                dt = time.perf_counter() - t0
-                gm[name] = dict(kw, seconds=dt, playouts_per_s=1600 / dt, net_evals=tree.n_evals, eval_batches=tree.n_eval_batches)
-            extra["mcts_genmove"] = dict(gm, playouts=1600, position="empty 9x9 board", timing="host wall clock around the search")
+            # weak-scaling self-play beside the strong-scaling line: args.selfplay_games games PER GPU
+            if world > 1:
+                spw = po.PlayoutGraph(args.selfplay_games, dev, pol, bk.MODE_SELFPLAY, seed=1, game0=rank * args.selfplay_games, policy_odd=pol19)
+                spw_tot, _ = timed(lambda: spw.replay(), 3, 1, flush_l2=False)
+                extra["selfplay"]["weak_scaling"] = {"games_per_gpu": args.selfplay_games,
+                                                     "games_per_s": world * args.selfplay_games * 3 / (1e-3 * spw_tot), "ms_per_batch": spw_tot / 3}
+                del spw
+            # BASELINE configs[2] and [0]: one genmove from the empty board -- rank 0 only (a host-side search per rank would only
+            # make the ranks fight for host cores); the other ranks wait at the barrier below
+            if rank == 0:
+                from bokego_b200 import mcts as bmcts
+                bmcts.MCTS(None, pol, val, device=dev).rollout(10)
+                gm = {}
+                for name, n_roll, kw in (("reference_parameters", 1600, {"expand_thresh": 100, "leaf_batch": 32}),
+                                         ("expand_on_second_visit", 1600, {"expand_thresh": 1, "leaf_batch": 128}),
+                                         ("simulate_mode", 1600, {"expand_thresh": 100, "leaf_batch": 64, "no_sim": False}),
+                                         ("config0_200_rollouts", 200, {"expand_thresh": 100, "leaf_batch": 1})):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    tree = bmcts.MCTS(None, pol, val, device=dev, **kw)
+                    tree.rollout(n_roll)
+                    tree.choose()
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    gm[name] = dict(kw, playouts=n_roll, seconds=dt, playouts_per_s=n_roll / dt, net_evals=tree.n_evals,
+                                    eval_batches=tree.n_eval_batches, device_playouts=tree.n_playouts)
+                extra["mcts_genmove"] = dict(gm, position="empty 9x9 board", timing="host wall clock around the search")
+                # the reference's own gtp.py / mcts.py over the mirror on the GPU (row b'), 200 rollouts = BASELINE configs[0]
+                rc = {}
+                for name, batched in (("one_position_per_call", False), ("batched_expansions", True)):
+                    r = gpu_genmove_reference_callers(sd17, sdv, dev, 200, batched)
+                    if r is not None:
+                        rc[name] = r
+                extra["genmove_reference_callers"] = rc if rc else {"unavailable": "no reference install in baseline/_ref"}
+            if dist:
+                dist.barrier()
         if world == 1 and not args.no_train:
             extra["reinforce"] = reinforce_leg(dev, sd17, sd19, not args.no_cpu)
     clocks = cs.summary()
@@ -464,9 +670,7 @@ def run_ours(args, rank, world, local_rank):
             "metric": "policy+value evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "batched PolicyNet+ValueNet forward incl. feature encoding, batch 4096 synthetic legal 9x9 positions (BASELINE configs[1])",
-                       "batch_per_gpu": B, "weights": "policy_17 + stand-in ValueNet (policy_19 trunk, seeded head)",
-                       "l2": "flushed between timed iterations (256 MiB memset)", "operands": "fp16, fp32 accumulate"},
+            "config": bench_config(B), "operands": "fp16 operands, fp32 accumulation (tcgen05 kind::f16)",
             "clocks": clocks,
             "e2e": {"value": world * B * args.steps / (1e-3 * pipe_tot), "unit": "evals/s", "h2d_bytes_per_step": ev_pipe.h2d_bytes,
                     "d2h_bytes_per_step": ev_pipe.d2h_bytes,
@@ -488,6 +692,16 @@ def run_ours(args, rank, world, local_rank):
                 sp_rate, sp_cores, sp_dt = cpu_selfplay_rate(args.cpu_selfplay_games, sd17, sd19)
                 extra["selfplay"]["cpu_baseline"] = {"value": sp_rate, "unit": "games/s", "cores": sp_cores, "kind": "port",
                                                      "sample": f"{args.cpu_selfplay_games} games x 72 moves in lock step ({sp_dt:.1f} s)"}
+            if "simulate" in extra:
+                sm_rate, sm_cores, sm_dt = cpu_simulate_rate(args.cpu_simulate_boards, sd17)
+                extra["simulate"]["cpu_baseline"] = {"value": sm_rate, "unit": "playouts/s", "cores": sm_cores, "kind": "port",
+                                                     "sample": f"{args.cpu_simulate_boards} boards played to the end in lock step ({sm_dt:.1f} s)"}
+            if "mcts_genmove" in extra:
+                g200, g1600 = cpu_genmove_reference(sd17, sdv, 200), cpu_genmove_reference(sd17, sdv, 1600)
+                if g1600 is not None:
+                    extra["mcts_genmove"]["cpu_baseline"] = dict(g1600, value=g1600["playouts_per_s"], unit="playouts/s")
+                    if isinstance(extra.get("genmove_reference_callers"), dict):
+                        extra["genmove_reference_callers"]["cpu_baseline"] = dict(g200, value=g200["playouts_per_s"], unit="playouts/s")
             line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_sample} positions x {len(ts)} passes ({sum(ts):.1f} s); C feature oracle (OpenMP) + fp32 torch CPU forward, {cores} threads"}
         line.update(extra)
@@ -511,6 +725,7 @@ def main():
     ap.add_argument("--selfplay-games", type=int, default=4096)
     ap.add_argument("--simulate-boards", type=int, default=65536)
     ap.add_argument("--cpu-selfplay-games", type=int, default=256)
+    ap.add_argument("--cpu-simulate-boards", type=int, default=256)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

@@ -48,9 +48,9 @@ def _sig(L):
     L.bk_make_moves.restype = i32
     L.bk_make_moves.argtypes = [vp] * 13 + [i32, vp]
     L.bk_tree_run.restype = i32
-    L.bk_tree_run.argtypes = [vp] * 7 + [i32, i32, i32, i32, C.c_double, vp, vp, vp, i32, vp]
+    L.bk_tree_run.argtypes = [vp] * 7 + [i32, i32, i32, i32, C.c_double, vp, vp, vp, i32, vp, vp, C.c_double, i32]
     L.bk_tree_finish.restype = i32
-    L.bk_tree_finish.argtypes = [vp] * 5 + [i32, i32, i32]
+    L.bk_tree_finish.argtypes = [vp] * 5 + [i32, i32, i32, vp, vp, i32]
     L.bk_score.restype = i32
     L.bk_score.argtypes = [vp, f32, vp, vp, i32, vp]
     L.bk_exp_draws.restype = i32

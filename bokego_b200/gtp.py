@@ -8,7 +8,12 @@ recorded from the unmodified reference (tests/golden/gtp_transcript.json) and co
 
 Differences, all on the search side: positions are bokego_b200.go.Game objects and the search is bokego_b200.mcts.MCTS
 (device-resident position pool, leaves evaluated in batches); it is created lazily, so every command that needs no search
-works without a GPU.  `analyze` (a streaming Sabaki extension) and `clear_cache` are accepted but answer `?`.
+works without a GPU.  Like the reference (whose N / V dicts keep every node, gtp.py:332-337, mcts.py:110-131) the tree is kept
+from move to move: the engine's own move re-roots with `choose`, an opponent move with `advance`, and only a move that is not in
+the tree (a pass, a position set by clear_board / undo / loadsgf) starts a new one; the resign test runs on the statistics the
+root already has, before the search (gtp.py:344-356).  `pondering` is accepted and stored but there is no background search: a
+rollout batch here is one blocking device round trip, so nothing is searched while waiting for input.  `analyze` (a streaming
+Sabaki extension) and `clear_cache` are accepted but answer `?`.
 """
 import copy
 import os
@@ -50,6 +55,8 @@ class GTP:
         self._undid = False
 
     # ---- engine side ---------------------------------------------------------------------------------------------------
+    MAX_TREE_NODES = 1 << 20        # a kept tree is dropped beyond this size (the node pool only grows)
+
     def _set_root(self, game):
         self.root = game
         self.tree = None
@@ -57,14 +64,20 @@ class GTP:
     def input_move(self, sq_c):
         node = _after(self.root, sq_c)
         self._last_root = self.root
-        self._set_root(node)
+        tree = self.tree
+        self.root = node
+        # keep the subtree of the move when the tree has it (gtp.py:332-337 -> set_root keeps the statistics)
+        if tree is not None and (tree.n > self.MAX_TREE_NODES or not tree.advance(sq_c)):
+            tree = None
+        self.tree = tree
         self._move_history.append(sq_c)
         self._undid = False
 
     def search(self):
         """run the configured amount of search from the current position and return the tree"""
         from . import mcts
-        self.tree = mcts.MCTS(self.root, self.policy_net, self.value_net, **self.search_kwargs)
+        if self.tree is None:
+            self.tree = mcts.MCTS(self.root, self.policy_net, self.value_net, **self.search_kwargs)
         if self.time_lim:
             t0 = default_timer()
             while default_timer() < t0 + self.time_lim:
@@ -75,12 +88,14 @@ class GTP:
 
     def genmove(self, resign=None):
         """move for the player to move (gtp.py:344-366); go.RESIGN when the position is lost (winrate < 0.1 after move 50)"""
-        tree = self.search()
-        give_up = resign if resign is not None else (tree.winrate() < 0.1 and self.root.turn > 50)
+        if resign is not None:
+            give_up = resign
+        else:                                            # `surrender` (gtp.py:339-342) on the statistics from before the search
+            give_up = self.tree is not None and self.tree.winrate() < 0.1 and self.root.turn > 50
         if give_up:
             self.running = False
             return go.RESIGN
-        mv = tree.best_move()
+        mv = self.search().best_move()
         self.input_move(mv)
         return mv
 

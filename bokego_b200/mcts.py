@@ -14,6 +14,16 @@ expansion, the descents / back-ups run in a native host-side core of the library
 every new leaf (descents that end in an already evaluated leaf are backed up at once).  With `leaf_batch=1` the visit counts
 are those of the sequential rule.
 
+`no_sim=False` is the reference's `--simulate` mode (mcts.py:133-151, 195-217, boke.py:24-25): every rollout also plays its
+leaf out to the end of the game with moves drawn from the policy net (Go_MCTS.find_random_child), the result -- Black's +-1
+from Game.score(), negated when White is to move at the leaf -- is summed into Q on the way up with alternating sign, and
+selection mixes the two estimates, ((1 - w) Q + w V) / N with w = value_net_weight (0.5; 0 without a value net).  Here the
+`leaf_batch` parked leaves of a batch are played out TOGETHER on the device (bokego_b200.playout.run_playouts from the leaf
+positions with their carried liberty caches: bk_forward + bk_playout_step_encode per move, bk_score at the end); the random
+stream of playout number r is keyed (seed, r, turn, try), so a search is reproducible.  One difference from the reference is
+deliberate: its get_move zeroes rejected moves in the CACHED distribution of the node (mcts.py:357), which leaks into later
+PUCT priors of own-eye moves and into later playouts through the same position; here priors are never mutated.
+
 Ties in the arg-max go to the lowest move index (the reference iterates a Python set, i.e. its tie-break is arbitrary).
 """
 import ctypes as C
@@ -22,51 +32,66 @@ import numpy as np
 import torch
 
 from . import _lib, go
-from .batched import NONE, PASS, Positions, features_batch, make_moves, policy_value_batch
+from .batched import MODE_MCTS, NONE, PASS, Positions, features_batch, make_moves, policy_value_batch
 
 MAX_TURNS = 80   # mcts.py:13
-
-
-def fake_nets(boards, turn):
-    """Deterministic stand-in for the two nets, a function of the position only (test hook: tests/golden/make_golden_mcts.py
-    drives the REFERENCE search with the same function, so the tree statistics can be compared exactly).
-    boards int8 [n,81], turn int16 [n] -> (probs float32 [n,81], value float32 [n])"""
-    import zlib
-    probs = np.zeros((len(boards), 81), np.float32)
-    val = np.zeros(len(boards), np.float32)
-    for i in range(len(boards)):
-        rng = np.random.RandomState(zlib.crc32(np.ascontiguousarray(boards[i], np.int8).tobytes() + bytes([int(turn[i]) & 0xFF])))
-        lg = (rng.standard_normal(81) * 1.5).astype(np.float32)
-        e = np.exp(lg - lg.max())
-        probs[i] = (e / e.sum()).astype(np.float32)
-        val[i] = np.float32(np.tanh(rng.standard_normal()))
-    return probs, val
 
 
 class MCTS:
     """root: a bokego_b200.go.Game (or None for the empty board).  policy_net / value_net: PackedNet (or the nnet mirror's
     PolicyNet / ValueNet, whose packed blobs are used).  kwargs as in the reference: expand_thresh (100),
-    exploration_weight (4.0); additionally leaf_batch (descents per evaluation batch, default 1), device, and `nets_override`
-    (test hook: a callable (boards int8 [n,81], turn int16 [n]) -> (probs, value) replacing the two nets; the encoder still
-    supplies legal moves and the liberty cache)."""
+    exploration_weight (4.0), no_sim (True), value_net_weight (0.5 in --simulate mode with a value net); additionally
+    leaf_batch (descents per evaluation batch, default 1), seed (random stream of the --simulate playouts) and device."""
 
     def __init__(self, root=None, policy_net=None, value_net=None, **kwargs):
         self.device = _lib.require_device(kwargs.get("device", "cuda"))
         self.expand_thresh = kwargs.get("expand_thresh", 100)
         self.exploration_weight = kwargs.get("exploration_weight", 4.0)
         self.leaf_batch = max(1, int(kwargs.get("leaf_batch", 1)))
-        self.nets_override = kwargs.get("nets_override")
-        self.policy = self.value = None
-        if self.nets_override is None:
-            if policy_net is None:
-                raise TypeError("Missing required keywork argument: 'policy_net'")
-            if value_net is None:
-                raise TypeError("Keyword argument 'value_net' is required for no simulation mode")
-            pk = lambda n: n._packed(self.device) if hasattr(n, "_packed") else n
-            self.policy, self.value = pk(policy_net), pk(value_net)
+        self.no_sim = kwargs.get("no_sim", True)
+        self.seed = int(kwargs.get("seed", 0))
+        self._bind_nets(policy_net, value_net)
+        if self.no_sim:                                   # mcts.py:66-71
+            self.value_net_weight = 1.0
+        elif not self.has_value:
+            self.value_net_weight = 0.0
+        else:
+            self.value_net_weight = kwargs.get("value_net_weight", 0.5)
+        self.n_playouts = 0     # --simulate playouts made so far (= the game id of the next playout's random stream)
         self.n_evals = 0        # positions sent through the nets
         self.n_eval_batches = 0
         self.set_root(root)
+
+    def _bind_nets(self, policy_net, value_net):
+        if policy_net is None:
+            raise TypeError("Missing required keywork argument: 'policy_net'")
+        if value_net is None and self.no_sim:
+            raise TypeError("Keyword argument 'value_net' is required for no simulation mode")
+        pk = lambda n: None if n is None else (n._packed(self.device) if hasattr(n, "_packed") else n)
+        self.policy, self.value = pk(policy_net), pk(value_net)
+        self.has_value = self.value is not None
+
+    def _net_outputs(self, sub):
+        """(probs float32 [n,81], value float64 [n], legal uint8 [n,81], libs uint8 tensor [n,81]) of the positions `sub`:
+        one encoder launch and one policy + value launch"""
+        out = features_batch(sub, want=("conv", "legal", "libs"))
+        _, probs, val = policy_value_batch(out["conv"], sub.B, self.policy, self.value, want_logits=False)
+        val = np.zeros(sub.B) if val is None else val.double().cpu().numpy()
+        return probs.cpu().numpy(), val, out["legal"].cpu().numpy(), out["libs"]
+
+    def _playout_results(self, leaves, first_id):
+        """--simulate: play the positions of the nodes `leaves` out to the end (mcts.py:195-206) and return Black's +-1 per
+        leaf (Go_MCTS.reward, mcts.py:330-338).  Playout j uses the random stream of game id first_id + j."""
+        from .playout import MCTS_MAX_TURN, n_steps_for, run_playouts
+        idx = torch.as_tensor(leaves, dtype=torch.long, device=self.device)
+        p = self.pool
+        pos = Positions(p.boards[idx].contiguous(), p.ko[idx].contiguous(), p.last[idx].contiguous(), p.turn[idx].contiguous(),
+                        p.libs[idx].contiguous())
+        pos.done = ((pos.turn > MAX_TURNS) | (pos.last == PASS)).to(torch.uint8)        # a terminal leaf is scored as it is
+        first_turn = int(min(self.turn[i] for i in leaves))
+        res = run_playouts(pos, self.policy, MODE_MCTS, MCTS_MAX_TURN, seed=self.seed, game0=first_id,
+                           n_steps=n_steps_for(MODE_MCTS, MCTS_MAX_TURN, first_turn), first_turn=first_turn, graph=False)
+        return res.reward.cpu().numpy().astype(np.float64)
 
     # ---- storage ---------------------------------------------------------------------------------------------------
     def _alloc(self, cap):
@@ -79,6 +104,7 @@ class MCTS:
         self.move = np.full(cap, NONE, np.int16)        # the move that led to the node
         self.N = np.zeros(cap, np.int64)
         self.V = np.zeros(cap, np.float64)
+        self.Q = np.zeros(cap, np.float64)              # --simulate: playout reward sums (mcts.py:46)
         self.child0 = np.full(cap, -1, np.int32)        # first child id, children are contiguous
         self.nchild = np.full(cap, -1, np.int32)        # -1 = not expanded
         self.val = np.full(cap, np.nan, np.float64)     # value net output (mover's perspective), nan = not evaluated
@@ -93,7 +119,7 @@ class MCTS:
             return
         cap = max(self.cap * 2, self.n + need)
         old, n = self.pool, self.n
-        keep = {k: getattr(self, k) for k in ("parent", "move", "N", "V", "child0", "nchild", "val", "turn", "last", "prior", "legal")}
+        keep = {k: getattr(self, k) for k in ("parent", "move", "N", "V", "Q", "child0", "nchild", "val", "turn", "last", "prior", "legal")}
         self._alloc(cap)
         self.n = n
         for k, v in keep.items():
@@ -133,19 +159,11 @@ class MCTS:
         fresh = ids == [0] and getattr(self, "_root_fresh", False) and self.parent[0] < 0
         sub = Positions(self.pool.boards[idx].contiguous(), self.pool.ko[idx].contiguous(), self.pool.last[idx].contiguous(),
                         self.pool.turn[idx].contiguous(), None if fresh else self.pool.libs[idx].contiguous())
-        if self.nets_override is None:
-            out = features_batch(sub, want=("conv", "legal", "libs"))
-            _, probs, val = policy_value_batch(out["conv"], sub.B, self.policy, self.value, want_logits=False)
-            probs, val = probs.cpu().numpy(), val.double().cpu().numpy()
-        else:
-            out = features_batch(sub, want=("legal", "libs"))
-            probs, val = self.nets_override(sub.boards.cpu().numpy(), sub.turn.cpu().numpy())
-            # what the reference's search sees: Categorical renormalises the probabilities in float32 (nnet.py:274)
-            probs = torch.distributions.Categorical(probs=torch.from_numpy(np.asarray(probs, np.float32))).probs.numpy()
-        self.pool.libs[idx] = out["libs"]
+        probs, val, legal, libs = self._net_outputs(sub)
+        self.pool.libs[idx] = libs
         self.prior[ids] = probs
         self.val[ids] = np.asarray(val, np.float64)
-        self.legal[ids] = out["legal"].cpu().numpy()
+        self.legal[ids] = legal
         self.n_evals += len(ids)
         self.n_eval_batches += 1
 
@@ -199,17 +217,28 @@ class MCTS:
         pend_nodes, pend_len = np.empty((K, D), np.int32), np.empty(K, np.int32)
         pend_expand, n_pend = np.empty(K, np.int32), C.c_int(0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
+        sim, have_value = not self.no_sim, int(self.has_value)
         done = 0
         while done < n:
+            # the arrays may have been re-allocated by an expansion: take the pointers afresh every round
             done += L.bk_tree_run(p(self.N), p(self.V), p(self.child0), p(self.nchild), p(self.move), p(self.prior), p(self.val),
                                   int(self.root), n - done, K, int(self.expand_thresh), C.c_double(self.exploration_weight),
-                                  p(pend_nodes), p(pend_len), p(pend_expand), D, C.byref(n_pend))
+                                  p(pend_nodes), p(pend_len), p(pend_expand), D, C.byref(n_pend),
+                                  p(self.Q) if sim else None, C.c_double(self.value_net_weight), have_value)
             k = n_pend.value
             if k == 0:
                 continue
-            self._evaluate([int(pend_nodes[j, pend_len[j] - 1]) for j in range(k)])
+            leaves = [int(pend_nodes[j, pend_len[j] - 1]) for j in range(k)]
+            self._evaluate(leaves)           # priors and legal moves are needed with or without a value net
             self._expand_many(list(dict.fromkeys(int(x) for x in pend_expand[:k] if x >= 0)))
-            L.bk_tree_finish(p(self.N), p(self.V), p(self.val), p(pend_nodes), p(pend_len), k, D, K)
+            reward = None
+            if sim:
+                # mcts.py:199-204: Black's result, seen by the player to move at the leaf
+                black = self._playout_results(leaves, self.n_playouts)
+                self.n_playouts += k
+                reward = np.ascontiguousarray(np.where(self.turn[leaves] % 2 == 0, black, -black), np.float64)
+            L.bk_tree_finish(p(self.N), p(self.V), p(self.val), p(pend_nodes), p(pend_len), k, D, K,
+                             p(self.Q) if sim else None, None if reward is None else p(reward), have_value)
             done += k
 
     def root_visits(self):
@@ -236,7 +265,21 @@ class MCTS:
         self._expand(best)
         return int(self.move[best])
 
+    def advance(self, mv):
+        """Re-root at the child of the root reached by move `mv`, keeping the statistics of its subtree (what the reference's
+        input_move -> set_root does, gtp.py:332-337: its N / V dicts keep every node).  False when the root has no such child
+        (a pass, or a root that was never expanded): the caller then starts a new tree."""
+        lo, c = self.child0[self.root], max(0, self.nchild[self.root])
+        hit = np.flatnonzero(self.move[lo: lo + c] == mv)
+        if len(hit) == 0:
+            return False
+        self.root = lo + int(hit[0])
+        self._evaluate([self.root])
+        self._expand(self.root)
+        return True
+
     def winrate(self, node=None):
-        """(V/N + 1) / 2 from the perspective of the player to move at the node (mcts.py:159-170)"""
+        """(((1 - w) Q + w V) / N + 1) / 2 from the perspective of the player to move at the node (mcts.py:159-170)"""
         i = self.root if node is None else node
-        return (self.V[i] / self.N[i] + 1) / 2 if self.N[i] > 0 else 0
+        w = self.value_net_weight
+        return (((1 - w) * self.Q[i] + w * self.V[i]) / self.N[i] + 1) / 2 if self.N[i] > 0 else 0

@@ -388,7 +388,11 @@ def reinforce(pi, pi_opp, optimizer, train_color, **kwargs):
         coef = torch.where(played, coef, torch.zeros_like(coef))
         # running statistics: the self-play calls game by game, then the replay calls on the same positions (all ranks' games)
         stats_rows = gather_games(trainer._rec_stats, bs, group).reshape(n_mine * bs, 7, 2, 128)
-        trainer.update_running(stats_rows, torch.cat([order, order]))
+        # only the calls the reference makes: no net call follows the end of a game (legal_sample returns None, selfplay.py:44-45,
+        # and the replay is bounded by len(g), selfplay.py:91-100), so rows of finished games are left out of the filter
+        played_all = gather_games(mine.unsqueeze(-1), bs, group)[..., 0] >= 0            # [step][game], all ranks' games
+        seq = order[played_all.t().reshape(-1)]
+        trainer.update_running(stats_rows, torch.cat([seq, seq]))
         # positions are independent under per-position BatchNorm, so games with a zero coefficient are skipped
         reinforce_step(trainer, trainer._rec_planes[:, sel].reshape(-1, 27, 81).contiguous(),
                        mine[:, sel].reshape(-1).clamp(min=0).contiguous(), coef[:, sel].reshape(-1).contiguous(), group=group,

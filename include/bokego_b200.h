@@ -119,9 +119,15 @@ int bk_exp_draws(uint64_t seed, uint32_t game0, uint32_t move, uint32_t tr, floa
  * caller has evaluated / expanded, bk_tree_finish removes the virtual losses and backs the values up. */
 int bk_tree_run(int64_t *N, double *V, const int32_t *child0, const int32_t *nchild, const int16_t *move, const float *prior,
                 const double *val, int root, int n_rollouts, int leaf_batch, int expand_thresh, double c_puct,
-                int32_t *pend_nodes, int32_t *pend_len, int32_t *pend_expand, int max_depth, int *n_pending);
+                int32_t *pend_nodes, int32_t *pend_len, int32_t *pend_expand, int max_depth, int *n_pending,
+                double *Q, double value_weight, int have_value);
 int bk_tree_finish(int64_t *N, double *V, const double *val, const int32_t *pend_nodes, const int32_t *pend_len,
-                   int n_pending, int max_depth, int leaf_batch);
+                   int n_pending, int max_depth, int leaf_batch, double *Q, const double *reward, int have_value);
+/* --simulate mode (MCTS(no_sim=False), mcts.py:133-151, 195-217): pass Q (playout reward sums, one per node) and
+ * value_weight (value_net_weight of mcts.py:66-71: selection uses ((1 - w) Q + w V) / N); every descent is then parked, the
+ * caller plays every parked leaf out on the device (bk_forward + bk_playout_step_encode until the boards are done, bk_score)
+ * and hands bk_tree_finish reward[j] = +-1 as seen by the player to move at leaf j.  Q == NULL is the no_sim search.
+ * have_value = 0: no value net (val is ignored, V stays 0). */
 
 /* ---- REINFORCE step (bin/selfplay.py:59-122): train-mode PolicyNet forward, policy-gradient loss, backward, AdamW ---------
  * All pointers are device pointers.  Parameters, gradients and the Adam moments are flat float32 buffers of

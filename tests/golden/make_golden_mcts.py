@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Golden tree statistics of the REFERENCE search (bokego/mcts.py, unmodified, imported from /root/reference) driven by a
-deterministic stand-in for the two nets (bokego_b200.mcts.fake_nets: a function of the position only).  With the nets taken out
+deterministic stand-in for the two nets (tests/fake_nets.py: a function of the position only).  With the nets taken out
 of the picture the visit counts are an exact, reproducible function of the search rule, so the array-based search of
 bokego_b200.mcts can be compared count for count.  Runs only in the build container:
 
@@ -21,7 +21,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import bokego.go as go            # noqa: E402  (the reference)
 import bokego.mcts as mcts        # noqa: E402
 
-from bokego_b200.mcts import fake_nets   # noqa: E402  (pure numpy helper, no device needed)
+sys.path.insert(0, os.path.dirname(HERE))
+from fake_nets import fake_nets   # noqa: E402  (tests/fake_nets.py: pure numpy helper, no device needed)
 
 ENC = {go.BLACK: 1, go.WHITE: -1, go.EMPTY: 0}
 DEC = {1: go.BLACK, -1: go.WHITE, 0: go.EMPTY}

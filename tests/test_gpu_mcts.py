@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 import torch
 
+from fake_nets import fake_net_tree
 from oracle import cpu as ocpu
 
 pytestmark = pytest.mark.gpu
@@ -55,7 +56,7 @@ def test_sequential_search_equals_reference_tree(env):
         board = "".join(DEC[int(v)] for v in g["board"][i])
         last = None if g["last"][i] == -2 else int(g["last"][i])
         root = go.Game(board=board, ko=None, last_move=last, turn=int(g["turn"][i]))
-        tree = mcts.MCTS(root, nets_override=mcts.fake_nets, expand_thresh=int(g["expand_thresh"][i]), device=dev)
+        tree = fake_net_tree(mcts)(root, expand_thresh=int(g["expand_thresh"][i]), device=dev)
         tree.rollout(int(g["n_rollouts"][i]))
         assert np.array_equal(tree.root_visits(), g["visits"][i]), i
         lo, c = tree.child0[tree.root], tree.nchild[tree.root]
@@ -86,3 +87,53 @@ def test_batched_search_with_virtual_loss(env):
     assert 0.0 < bat.winrate() < 1.0
     mv = bat.choose()
     assert 0 <= mv < 81 and bat.nchild[bat.root] > 0
+
+
+def test_simulate_search_equals_reference_tree(env):
+    """--simulate mode (MCTS(no_sim=False), mcts.py:133-151, 195-217) against tree statistics of the unmodified reference
+    search (tests/golden/mcts_sim.npz, make_golden_mcts_sim.py: fake nets, keyed draws): per root child N, Q and V, the root's
+    own sums, node count, winrate and chosen move; playouts run through bk_playout_step on the device"""
+    from fake_nets import fake_net_sim_tree
+    bk, go, mcts, dev, _, _ = env
+    g = dict(np.load(os.path.join(GOLDEN, "mcts_sim.npz")))
+    Tree = fake_net_sim_tree(mcts, int(g["seed"]))
+    for i in range(len(g["turn"])):
+        board = "".join(DEC[int(v)] for v in g["board"][i])
+        last = None if g["last"][i] == -2 else int(g["last"][i])
+        root = go.Game(board=board, ko=None, last_move=last, turn=int(g["turn"][i]))
+        tree = Tree(root, None, None if g["with_value"][i] else False, no_sim=False, expand_thresh=int(g["expand_thresh"][i]),
+                    value_net_weight=float(g["w"][i]), device=dev)
+        tree.rollout(int(g["n_rollouts"][i]))
+        lo, c = tree.child0[tree.root], tree.nchild[tree.root]
+        got = np.zeros((3, 81))
+        got[0, tree.move[lo: lo + c]], got[1, tree.move[lo: lo + c]], got[2, tree.move[lo: lo + c]] = \
+            tree.N[lo: lo + c], tree.Q[lo: lo + c], tree.V[lo: lo + c]
+        assert np.array_equal(got[:2], g["stats"][i][:2]), i
+        assert np.allclose(got[2], g["stats"][i][2], rtol=0, atol=1e-9), i
+        rs = g["root_stats"][i]
+        assert tree.N[tree.root] == rs[0] and tree.Q[tree.root] == rs[1] and abs(tree.V[tree.root] - rs[2]) < 1e-9, i
+        assert tree.n == g["n_nodes"][i], (i, tree.n, g["n_nodes"][i])
+        assert abs(tree.winrate() - g["winrate"][i]) < 1e-12, i
+        # most visited child; the reference breaks ties in the order of a Python set, the batched tree by the lowest move
+        assert got[0, tree.best_move()] == got[0].max() == g["stats"][i][0, int(g["best"][i])], i
+
+
+def test_simulate_search_on_the_device(env):
+    """--simulate with the real nets: leaf batches are played out together by run_playouts; bookkeeping invariants, and a
+    search is reproducible for a given seed"""
+    bk, go, mcts, dev, pol, val = env
+    runs = []
+    for _ in range(2):
+        t = mcts.MCTS(None, pol, val, no_sim=False, expand_thresh=4, leaf_batch=16, seed=5, device=dev)
+        t.rollout(160)
+        assert t.N[t.root] == 160 and t.n_playouts == 160 and abs(t.Q[t.root]) <= 160
+        assert t.value_net_weight == 0.5 and 0.0 < t.winrate() < 1.0
+        for i in np.flatnonzero(t.nchild[: t.n] > 0)[:40]:
+            lo, c = t.child0[i], t.nchild[i]
+            assert t.N[lo: lo + c].sum() <= t.N[i] and abs(t.Q[i]) <= t.N[i]
+        runs.append((t.root_visits().copy(), t.Q[: t.n].copy()))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    # policy only (no value net): w = 0, selection on playout results alone
+    t = mcts.MCTS(None, pol, None, no_sim=False, expand_thresh=4, leaf_batch=8, device=dev)
+    t.rollout(64)
+    assert t.value_net_weight == 0.0 and t.N[t.root] == 64 and not t.V[: t.n].any()

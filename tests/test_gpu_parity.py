@@ -10,12 +10,12 @@ from oracle import nets as onets
 
 pytestmark = pytest.mark.gpu
 
-# Tolerances vs the fp32 CPU reference for fp16 operands with fp32 accumulation.  The survey's
-# emulation of exactly this arithmetic measured logits 2.8e-2, probs 9.2e-4, value 3.1e-4 (max over 400
-# positions); on the B200 the kernels measure 2.8e-2 / 1.06e-3 / 4.9e-4 over the 256 golden positions.  That is
-# the rounding floor of 16-bit operands (tf32 has the same 10-bit mantissa, bf16 is 8x worse), so the probability
-# bound is stated as 1.5e-3 rather than the survey's rounder 1e-3; the argmax must be identical.
-TOL_LOGIT, TOL_PROB, TOL_VALUE = 5e-2, 1.5e-3, 1e-3
+# Tolerances vs the fp32 CPU reference for fp16 operands with fp32 accumulation: hard limits for the WORST
+# square of the WORST position of a test.  They come from the measured error distribution of tests/test_gpu_precision.py
+# (4,496 reference positions, profiles/r02_precision_report.json): probabilities mean 2.1e-4, p99 8e-4, p99.9 1.3e-3, worst
+# 3.9e-3 (the CPU emulation of the same arithmetic: 3.4e-3); logits p99.9 3.7e-2, worst 5.2e-2; value worst 9.3e-4.  The
+# distribution itself is asserted there; here a generous cap catches kernel bugs (a wrong tap or a lost row is off by 1e-1).
+TOL_LOGIT, TOL_PROB, TOL_VALUE = 8e-2, 5e-3, 1e-3
 
 
 @pytest.fixture(scope="module")
@@ -131,7 +131,7 @@ def test_forward_golden(bk, dev, positions, nets_golden, sd17, sd_value, simt):
     agree = float((logits.argmax(1) == want_l.argmax(1)).float().mean())
     print("argmax agreement", agree)
     assert el <= TOL_LOGIT and ep <= TOL_PROB and ev <= TOL_VALUE
-    assert agree >= 0.999 or (logits.argmax(1) != want_l.argmax(1)).sum() <= 1
+    assert agree == 1.0          # identical arg-max move on every golden position (near-ties are examined in test_gpu_precision.py)
     assert float((probs.sum(1) - 1).abs().max()) < 1e-5
 
 
@@ -220,6 +220,16 @@ def test_forward_schedule_boundaries(bk, dev, sd17, sd_value, n):
     torch.cuda.synchronize()
     assert float((l_t - l_s).abs().max()) < TOL_LOGIT and float((v_t - v_s).abs().max()) < TOL_VALUE
     assert float((p_t.sum(1) - 1).abs().max()) < 1e-5
+    # ... and against the ORACLE (fp32 CPU restatement of the reference nets) on every row: the 123 distinct positions are
+    # evaluated once on the CPU and compared with all n rows of the batch
+    fo, _, _ = ocpu.features_batch(bd, ko, last, turn)
+    x = onets.planes_to_float(fo)
+    torch.set_num_threads(8)
+    wl, wv = onets.policy_logits(sd17, x), onets.value(sd_value, x)
+    assert float((l_t.cpu() - wl[idx]).abs().max()) <= TOL_LOGIT
+    assert float((p_t.cpu() - torch.softmax(wl, 1)[idx]).abs().max()) <= TOL_PROB
+    assert float((v_t.cpu() - wv[idx]).abs().max()) <= TOL_VALUE
+    assert bool((l_t.cpu().argmax(1) == wl.argmax(1)[idx]).all())
     small = _pos(bk, dev, bd, ko, last, turn)
     l_0, _, v_0 = bk.policy_value_batch(bk.features_batch(small, want=("conv",))["conv"], 123, pol, val)
     it = torch.from_numpy(idx).to(dev)

@@ -135,3 +135,44 @@ def _decode_conv(conv, B):
                 v = h[:, :, r, :].reshape(G, 32)[:, :27]
                 out[bi::5][:, :, 9 * x + y] = v.astype(np.uint8)
     return out[:B]
+
+
+def test_simulate_65536_boards_subset_vs_oracle(env):
+    """BASELINE configs[3] at its full size: 65,536 concurrent --simulate playouts.  The CUDA-graph run equals the launch-by-launch
+    run record for record; and 96 boards spread over the batch are replayed by the oracle, move for move, from the
+    probabilities the device computed for them (bit-exact playouts given identical probabilities and draws), down to the
+    final boards, scores and rewards."""
+    bk, po, dev, p17, _ = env
+    B, seed, game0 = 65536, 31, 1000
+    a = po.run_playouts(bk.Positions.empty(B, dev, track_libs=False), p17, bk.MODE_MCTS, seed=seed, game0=game0, graph=True)
+    rec_a = a.records()
+    pick = np.unique(np.concatenate([np.arange(0, B, 701), [B - 1, B - 2, 4, 5, 739, 740]]))[:96]
+    pt = torch.from_numpy(pick).to(dev)
+    pos = bk.Positions.empty(B, dev)
+    bufs = bk.features_batch(pos, fresh_libs=True, want=("conv", "libs"), out={"libs": pos.libs})
+    probs = torch.empty(B, 81, dtype=torch.float32, device=dev)
+    n = len(pick)
+    bd = np.zeros((n, 81), np.int8); ko = np.full(n, -1, np.int16); last = np.full(n, -2, np.int16)
+    turn = np.zeros(n, np.int16); done = np.zeros(n, np.uint8)
+    _, _, libs = ocpu.features_batch(bd, ko, last, turn, None)
+    moves = []
+    for k in range(po.n_steps_for(bk.MODE_MCTS, 80)):
+        bk.policy_value_batch(bufs["conv"], B, p17, None, want_logits=False, probs_out=probs)
+        sub = probs[pt].cpu().numpy()
+        mv = bk.playout_step(pos, probs, bk.MODE_MCTS, 80, seed=seed, game0=game0, encode_into=bufs["conv"])
+        moves.append(mv.clone())
+        # the oracle plays the picked boards with the device's probabilities; its random stream is keyed by the GLOBAL game id
+        mo = np.empty(n, np.int16)
+        for j, gid in enumerate(pick):
+            sl = slice(j, j + 1)
+            mo[j] = ocpu.step_batch(bd[sl], ko[sl], last[sl], turn[sl], libs[sl], done[sl], sub[sl], 0, 80, seed=seed,
+                                    game0=game0 + int(gid))[0]
+        assert np.array_equal(mv[pt].cpu().numpy(), mo), k
+        _, _, libs = ocpu.features_batch(bd, ko, last, turn, libs)
+    assert bool(pos.done.all()) and done.all()
+    assert np.array_equal(pos.boards[pt].cpu().numpy(), bd) and np.array_equal(pos.turn[pt].cpu().numpy(), turn)
+    score, reward = bk.score_batch(pos.boards)
+    assert np.array_equal(score[pt].cpu().numpy().astype(np.float64), ocpu.score_batch(bd))
+    b_rec = po.PlayoutResult(torch.stack(moves, 1), pos.turn, score, reward).records()
+    assert torch.equal(rec_a, b_rec)
+    assert set(np.unique(reward.cpu().numpy())) <= {-1, 1}
