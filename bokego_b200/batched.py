@@ -293,6 +293,29 @@ def playout_step(pos, probs, mode, max_turn, seed=0, game0=0, q_inj=None, moves_
     return moves_out
 
 
+def playout_run(pos, feats_conv, policy, n_steps, mode, max_turn, seed=0, game0=0, policy_odd=None, first_turn=0, moves_out=None):
+    """n_steps playout moves for every board in ONE kernel launch (bk_playout_run): the conv kernel keeps each group of five
+    boards on its SM for the whole playout.  feats_conv: "conv" planes of the current positions (features_batch), pos.libs their
+    liberty cache.  Updates `pos` in place; returns moves int16 [n_steps, B]."""
+    L = _lib.lib()
+    dev, B = pos.device, pos.B
+    if pos.libs is None:
+        raise ValueError("playout_run needs the carried liberty cache pos.libs")
+    if feats_conv.device != dev or feats_conv.numel() < L.bk_feats_conv_bytes(B):
+        raise ValueError("feats_conv: wrong device or too small for B")
+    if moves_out is None:
+        moves_out = torch.empty(n_steps, B, dtype=torch.int16, device=dev)
+    _want(moves_out, torch.int16, (n_steps, B), "moves_out", dev)
+    with torch.cuda.device(dev):
+        rc = L.bk_playout_run(_lib.ptr(pos.boards), _lib.ptr(pos.ko), _lib.ptr(pos.last), _lib.ptr(pos.turn), _lib.ptr(pos.libs),
+                              _lib.ptr(pos.done), _lib.ptr(feats_conv), _lib.ptr(policy.blob),
+                              _lib.ptr(policy_odd.blob if policy_odd is not None else None), C.c_uint64(seed), C.c_uint32(game0),
+                              mode, max_turn, first_turn, n_steps, _lib.ptr(moves_out), B, _lib.stream_ptr(dev))
+    _lib.check(rc, "bk_playout_run")
+    _lib.count_launch()
+    return moves_out
+
+
 def make_moves(pos, parent_idx, moves):
     """Go_MCTS.make_move for a batch (mcts.py:340-346): child c = position parent_idx[c] of `pos` with moves[c] played.
     parent_idx int32 [C], moves int16 [C] (device tensors).  Returns (Positions of the C children, status uint8 [C]);

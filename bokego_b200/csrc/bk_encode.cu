@@ -89,7 +89,7 @@ bk_encode_kernel(const int8_t *__restrict__ boards, const int16_t *__restrict__ 
 
     // ---- per-square evaluation (bk_encode_core.cuh) ---------------------------------------------------
     bk_encode_square(grp, black, white, blk, ko, last, carried, stale, carried ? (int)libs_in[(size_t)b * BK_NSQ + p] : 0, p,
-                     (size_t)b, conv_base, feats_f32, planes_u8, legal_out, libs_out);
+                     (size_t)b, conv_base, BK_F_ROWS_G, feats_f32, planes_u8, legal_out, libs_out);
 }
 
 // float32 planes [B][27][81] (what nnet.features returns) -> the conv kernel's fp16 operand layout.

@@ -23,9 +23,11 @@ __device__ __forceinline__ uint4 *bk_conv_base(uint4 *feats_conv, int slot)
 // Planes of square p of board b from the group table `grp` of the position (black, white, ko, last, turn parity `blk`).
 // carried = the position has a liberty cache (Game._libs): lib_carried is its entry for p, `stale` = last >= 0 and the
 // cache entry of `last` is 0 (go.py:226); otherwise exact liberties (fresh Game).  Every output pointer may be null.
+// conv_base = first uint4 of this board's rows in the conv operand, chunk_stride = distance between channel chunks in uint4
+// (BK_F_ROWS_G in global memory; the row count of the shared-memory copy inside the conv kernel).
 __device__ __forceinline__ void bk_encode_square(const BKGroups &grp, BB black, BB white, bool blk, int ko, int last, bool carried,
-                                                 bool stale, int lib_carried, int p, size_t b, uint4 *conv_base, float *feats_f32,
-                                                 uint8_t *planes_u8, uint8_t *legal_out, uint8_t *libs_out)
+                                                 bool stale, int lib_carried, int p, size_t b, uint4 *conv_base, int chunk_stride,
+                                                 float *feats_f32, uint8_t *planes_u8, uint8_t *legal_out, uint8_t *libs_out)
 {
     const BB own = blk ? black : white, opp = blk ? white : black;
     const bool mine = bb_test(own, p), theirs = bb_test(opp, p);
@@ -79,7 +81,7 @@ __device__ __forceinline__ void bk_encode_square(const BKGroups &grp, BB black, 
             o.y = bk_pack2(v[8 * c + 2], v[8 * c + 3]);
             o.z = bk_pack2(v[8 * c + 4], v[8 * c + 5]);
             o.w = bk_pack2(v[8 * c + 6], v[8 * c + 7]);
-            conv_base[c * BK_F_ROWS_G + r] = o;
+            conv_base[c * chunk_stride + r] = o;
         }
     }
 }

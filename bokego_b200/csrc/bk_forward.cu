@@ -26,6 +26,13 @@
 // Items that do not fill a whole round of the grid are split into smaller board ranges (fewer M tiles each)
 // so that the last round, and small batches, spread over more SMs.
 //
+// PLAYOUT instantiation (bk_playout_run): the same kernel keeps its <= 5 boards for a WHOLE playout.  After the policy head of
+// move k the probabilities stay in shared memory; three epilogue warps per board sample the move, play it, refresh the liberty
+// cache and encode the new position (bk_step_core.cuh, the code of the stepping kernel) straight into the shared-memory
+// feature operand of move k + 1 -- no launch, no grid-wide dependency and no HBM round trip between the moves of a game
+// (/root/reference/bokego/mcts.py:195-206, bin/selfplay.py:18-33).  Boards, ko / last / turn, the liberty cache and the
+// move record stay in global memory (L2); the two policy nets of a self-play game alternate by move parity.
+//
 // A plain CUDA-core kernel over the same packed operands (BK_FWD_SIMT) exists to validate the packing and
 // the tensor-core path against each other on the GPU; it is not a fallback and is never selected implicitly.
 #include <cuda.h>
@@ -37,6 +44,7 @@
 #include <mutex>
 
 #include "bk_layout.h"
+#include "bk_step_core.cuh"
 
 namespace {
 
@@ -66,6 +74,10 @@ constexpr int OFF_TMEM = OFF_BAR + 192;
 constexpr int OFF_LOGIT = OFF_TMEM + 16;           // float[5][81]: head output per square
 constexpr int SMEM_BYTES = OFF_LOGIT + 1664;       // 232,016
 static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KiB");
+// PLAYOUT: between the last layer of move k and layer 0 of move k + 1 the activation buffer is dead; the step phase keeps its
+// per-board scratch (group table, arg-max slots) at its start and zeroes it again (padding rows must read as zero)
+constexpr int STEP_SCRATCH = (int)((sizeof(BkStepScratch) + 15) / 16 * 16);
+static_assert(BK_GROUP * STEP_SCRATCH <= A_BYTES, "step scratch");
 static_assert(OFF_W % 128 == 0 && OFF_ONES % 128 == 0 && OFF_BIASW % 128 == 0, "operand alignment");
 
 // WFULL (leader): both CTAs' halves of a stage have landed -- each CTA's tensor-map copy (cta_group::2) reports its
@@ -274,6 +286,12 @@ struct FwdArgs {
     int diag;                  // diagnostic bits: 1 = producer signals stages without copying, 2 = aligned A windows
     long long *prof;           // diagnostic: clock64 stamps of CTA 0, 4 per pass
     unsigned int *dbg;         // host-mapped words written before a bounded wait traps
+    // PLAYOUT only: whole games inside the kernel.  blob[0] / blob[1] are then the policy nets of the moves made at even / odd
+    // (first_turn + k); moves_out is [n_steps][B]
+    int8_t *boards; int16_t *ko, *last, *turn; uint8_t *libs, *done; int16_t *moves_out;
+    int n_steps, mode, max_turn, first_turn;
+    unsigned long long seed;
+    uint32_t game0;
 };
 
 struct Item { int g, net, lo, nb; };
@@ -438,6 +456,7 @@ __device__ __forceinline__ void finish_board(const float *logit, int net, const 
 // ------------------------------------------------------------------------------------------------------
 // the tcgen05 kernel
 // ------------------------------------------------------------------------------------------------------
+template <bool PLAYOUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1)
 bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant__ CUtensorMap tm_policy,
                      const __grid_constant__ CUtensorMap tm_value, const __grid_constant__ CUtensorMap tb_policy,
@@ -450,6 +469,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
     float *logit = reinterpret_cast<float *>(smem + OFF_LOGIT);
     const int rank = (int)cluster_ctarank();           // 0 = leader (issues the pair's MMAs), 1 = peer
     const int pair0 = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_steps = PLAYOUT ? args.n_steps : 1;     // moves every item is kept for (1 = plain forward)
     if (threadIdx.x == 0 && args.dbg) g_dbg = args.dbg;
 
     // ---- one-time setup: zero the operand buffers (pad rows must read as 0), the ones operand, barriers, TMEM
@@ -527,21 +547,26 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                 }
             };
             Item it, nx;
-            int pair_nb, nx_nb, n_done = 0;
+            int pair_nb, nx_nb;
+            uint32_t n_femp = 0;    // FEMPTY phases consumed (one per item and move)
             if (pair0 < args.n_pairs && decode_pair(args, pair0, rank, it, pair_nb)) load_feats(it);
             for (int v = pair0; v < args.n_pairs; v += n_clusters) {
                 if (!decode_pair(args, v, rank, it, pair_nb)) continue;
-                const CUtensorMap *tm = it.net == 0 ? &tm_policy : &tm_value;
-                const CUtensorMap *tb = it.net == 0 ? &tb_policy : &tb_value;
-                stream(tm, tb, BK_W_L0_OFF, n_stages_of(0));
-                if (pair_nb == BK_GROUP) stream(tm, tb, BK_W_L0_OFF, n_stages_of(0));   // layer 0, second pass (tiles 3, 4)
-                stream(tm, tb, BK_W_L_OFF(1), n_stages_of(1));
-                if (v + n_clusters < args.n_pairs && decode_pair(args, v + n_clusters, rank, nx, nx_nb)) {   // prefetch planes
-                    mbar_wait(sBar + 8 * BAR_FEMPTY, n_done & 1u, 0x200u);
-                    load_feats(nx);
+                for (int k = 0; k < n_steps; ++k) {
+                    const int net = PLAYOUT ? ((args.first_turn + k) & 1) : it.net;
+                    const CUtensorMap *tm = net == 0 ? &tm_policy : &tm_value;
+                    const CUtensorMap *tb = net == 0 ? &tb_policy : &tb_value;
+                    stream(tm, tb, BK_W_L0_OFF, n_stages_of(0));
+                    if (pair_nb == BK_GROUP) stream(tm, tb, BK_W_L0_OFF, n_stages_of(0));   // layer 0, second pass (tiles 3, 4)
+                    stream(tm, tb, BK_W_L_OFF(1), n_stages_of(1));
+                    // layer 0 of this move has read the feature planes; the planes of the NEXT item may be fetched once the
+                    // item's last move is past that point (in between, the epilogue warps write the next move's planes)
+                    mbar_wait(sBar + 8 * BAR_FEMPTY, n_femp & 1u, 0x200u);
+                    ++n_femp;
+                    if (k == n_steps - 1 && v + n_clusters < args.n_pairs && decode_pair(args, v + n_clusters, rank, nx, nx_nb))
+                        load_feats(nx);
+                    for (int l = 2; l <= 6; ++l) stream(tm, tb, BK_W_L_OFF(l), n_stages_of(l));
                 }
-                for (int l = 2; l <= 6; ++l) stream(tm, tb, BK_W_L_OFF(l), n_stages_of(l));
-                ++n_done;
             }
         }
     } else if (warp == WARP_MMA && rank == 1) {
@@ -552,9 +577,11 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         int pair_nb;
         for (int v = pair0; v < args.n_pairs; v += n_clusters) {
             if (!decode_pair(args, v, rank, it, pair_nb)) continue;
-            mbar_wait(sBar + 8 * BAR_FFULL, n_done & 1u, 0x300u);
-            ++n_done;
-            if (lane == 0) mbar_arrive_cluster(leader_bar + 8 * BAR_PFFULL);
+            for (int k = 0; k < n_steps; ++k) {
+                mbar_wait(sBar + 8 * BAR_FFULL, n_done & 1u, 0x300u);
+                ++n_done;
+                if (lane == 0) mbar_arrive_cluster(leader_bar + 8 * BAR_PFFULL);
+            }
         }
     } else if (warp == WARP_MMA) {
         // =========================== leader: MMA issuer (whole warp runs the loop, one elected lane issues) ===========
@@ -600,11 +627,14 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         int pair_nb;
         for (int v = pair0; v < args.n_pairs; v += n_clusters) {
             if (!decode_pair(args, v, rank, it, pair_nb)) continue;
-            mbar_wait(sBar + 8 * BAR_FFULL, n_done & 1u, 0x300u);
-            mbar_wait(sBar + 8 * BAR_PFFULL, n_done & 1u, 0x380u);
-            ++n_done;
             const int np = n_passes(pair_nb);
+            for (int k = 0; k < n_steps; ++k)
             for (int ps = 0; ps < np; ++ps, ++pass) {
+                if (ps == 0) {        // the feature planes of this move are in place in both CTAs (bulk copy, or the step phase)
+                    mbar_wait(sBar + 8 * BAR_FFULL, n_done & 1u, 0x300u);
+                    mbar_wait(sBar + 8 * BAR_PFFULL, n_done & 1u, 0x380u);
+                    ++n_done;
+                }
                 const Pass pi = pass_info(pair_nb, ps);
                 n_tiles = pi.n_tiles;
                 if (pass > 0) mbar_wait(sBar + 8 * BAR_ACT, (pass - 1) & 1u, 0x400u + pass);   // operands written, TMEM drained
@@ -670,9 +700,11 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         int pair_nb;
         for (int v = pair0; v < args.n_pairs; v += n_clusters) {
             if (!decode_pair(args, v, rank, it, pair_nb)) continue;
-            const uint8_t *blob = args.blob[it.net];
             const int np = n_passes(pair_nb);
+            for (int k = 0; k < n_steps; ++k)
             for (int ps = 0; ps < np; ++ps, ++pass) {
+                const int net = PLAYOUT ? ((args.first_turn + k) & 1) : it.net;
+                const uint8_t *blob = args.blob[net];
                 const Pass pi = pass_info(pair_nb, ps);
                 mbar_wait(sBar + 8 * BAR_ACC, pass & 1u, 0x600u + pass);
                 tc_fence_after();
@@ -726,11 +758,38 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     // logit[] holds nb boards x 81 head outputs; it is next written seven passes from now, and
                     // every pass in between needs all 16 warps to have arrived, so no trailing barrier
                     named_bar_sync(1, N_EPI_WARPS * 32);
-                    if (warp < it.nb) {
-                        const int b = it.g * BK_GROUP + it.lo + warp;
-                        finish_board(logit + warp * 81, it.net, blob, args.logits ? args.logits + (size_t)b * 81 : nullptr,
-                                     args.probs ? args.probs + (size_t)b * 81 : nullptr,
-                                     args.value ? args.value + b : nullptr, lane);
+                    if (!PLAYOUT) {
+                        if (warp < it.nb) {
+                            const int b = it.g * BK_GROUP + it.lo + warp;
+                            finish_board(logit + warp * 81, it.net, blob, args.logits ? args.logits + (size_t)b * 81 : nullptr,
+                                         args.probs ? args.probs + (size_t)b * 81 : nullptr,
+                                         args.value ? args.value + b : nullptr, lane);
+                        }
+                    } else {
+                        // ---- step phase: three warps per board (warp 15 idles) sample the move from the policy's
+                        // probabilities, play it and write the planes of the new position into the feature operand of the
+                        // next move.  The activation buffer is dead here and lends its first bytes as scratch.
+                        const int bi = warp / 3, sub = warp - 3 * bi;
+                        const bool last_move = k == n_steps - 1;
+                        if (bi < it.nb) {
+                            const int b = it.g * BK_GROUP + it.lo + bi;
+                            float *pr = logit + bi * 81;
+                            BkStepScratch &sc = *reinterpret_cast<BkStepScratch *>(smem + OFF_A + bi * STEP_SCRATCH);
+                            const BkSyncNamed sy{2 + bi};
+                            if (sub == 0) finish_board(pr, 0, blob, nullptr, pr, nullptr, lane);       // softmax in place
+                            sy.sync();
+                            uint4 *planes = last_move ? nullptr
+                                                      : reinterpret_cast<uint4 *>(smem + OFF_F) + F_MARGIN + BK_F_ROWS_B * (it.lo + bi);
+                            bk_step_board(sy, sc, 32 * sub + lane, b, args.boards + (size_t)b * BK_NSQ, args.ko, args.last, args.turn,
+                                          args.libs + (size_t)b * BK_NSQ, args.done, pr, nullptr, 0, args.seed, args.game0 + (uint32_t)b,
+                                          args.mode, args.max_turn, args.moves_out + (size_t)k * args.B + b, planes, F_ROWS);
+                            sy.sync();                    // the trio is done with the scratch: zero it again
+                            uint4 *z = reinterpret_cast<uint4 *>(&sc);
+                            for (int i = 32 * sub + lane; i < STEP_SCRATCH / 16; i += 96) z[i] = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                        fence_proxy_async();              // planes and zeroed scratch are visible to the tensor core
+                        named_bar_sync(1, N_EPI_WARPS * 32);
+                        if (!last_move && threadIdx.x == 0) mbar_arrive(sBar + 8 * BAR_FFULL);   // planes of move k + 1 are in place
                     }
                 }
             }
@@ -1042,7 +1101,9 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
         if (!ds.n_sm) {
             int n_sm = 0;
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, slot);
-            e = cudaFuncSetAttribute(bk_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+            e = cudaFuncSetAttribute(bk_forward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(bk_forward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
             if (e != cudaSuccess || n_sm < 2) return -3;
             ds.n_sm = n_sm;
         }
@@ -1067,7 +1128,56 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
             const int rc = weight_maps(ds, a.blob[i], &map[i], &bias_map[i]);
             if (rc != 0) return rc;
         }
-        bk_forward_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, stream>>>(a, map[0], map[1], bias_map[0], bias_map[1]);
+        bk_forward_tc_kernel<false><<<grid, N_THREADS, SMEM_BYTES, stream>>>(a, map[0], map[1], bias_map[0], bias_map[1]);
     }
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+// Whole playouts in ONE launch (see the PLAYOUT note at the top): B boards, n_steps moves each.
+extern "C" int bk_playout_run(int8_t *boards, int16_t *ko, int16_t *last, int16_t *turn, uint8_t *libs, uint8_t *done,
+                              const void *feats_conv, const void *blob_even, const void *blob_odd, uint64_t seed, uint32_t game0,
+                              int mode, int max_turn, int first_turn, int n_steps, int16_t *moves_out, int B, cudaStream_t stream)
+{
+    if (B <= 0 || n_steps <= 0) return 0;
+    if (!boards || !ko || !last || !turn || !libs || !done || !feats_conv || !blob_even || !moves_out) return -1;
+    if (mode != 0 && mode != 1) return -1;
+    FwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.feats = static_cast<const uint8_t *>(feats_conv);
+    a.blob[0] = static_cast<const uint8_t *>(blob_even);
+    a.blob[1] = static_cast<const uint8_t *>(blob_odd ? blob_odd : blob_even);
+    a.B = B; a.G = (B + BK_GROUP - 1) / BK_GROUP;
+    a.n_nets = 1; a.first_net = 0;
+    a.g_whole = a.G; a.split = 1; a.n_sub = a.G;           // whole groups only: an item keeps its boards for the whole game
+    a.n_pairs = (a.n_sub + 1) / 2;
+    a.dump_pass = -1;
+    a.boards = boards; a.ko = ko; a.last = last; a.turn = turn; a.libs = libs; a.done = done; a.moves_out = moves_out;
+    a.n_steps = n_steps; a.mode = mode; a.max_turn = max_turn; a.first_turn = first_turn; a.seed = seed; a.game0 = game0;
+    const int slot = bk_current_device_slot();
+    if (slot < 0) return -2;
+    std::lock_guard<std::mutex> lock(g_fwd_mutex);
+    FwdDeviceState &ds = g_fwd_dev[slot];
+    if (!g_dbg_host) {
+        if (cudaHostAlloc((void **)&g_dbg_host, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) g_dbg_host = nullptr;
+        else memset(g_dbg_host, 0, 64);
+    }
+    if (g_dbg_host) cudaHostGetDevicePointer((void **)&a.dbg, g_dbg_host, 0);
+    if (!ds.n_sm) {
+        int n_sm = 0;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, slot);
+        cudaError_t e = cudaFuncSetAttribute(bk_forward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(bk_forward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess || n_sm < 2) return -3;
+        ds.n_sm = n_sm;
+    }
+    const int n_clusters = ds.n_sm / 2;
+    const int grid = 2 * (a.n_pairs < n_clusters ? a.n_pairs : n_clusters);
+    CUtensorMap map[2], bias_map[2];
+    for (int i = 0; i < 2; ++i) {
+        const int rc = weight_maps(ds, a.blob[i], &map[i], &bias_map[i]);
+        if (rc != 0) return rc;
+    }
+    bk_forward_tc_kernel<true><<<grid, N_THREADS, SMEM_BYTES, stream>>>(a, map[0], map[1], bias_map[0], bias_map[1]);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

@@ -24,194 +24,25 @@
 
 #include "bk_bitboard.cuh"
 #include "bk_encode_core.cuh"
+#include "bk_step_core.cuh"
 
 namespace {
 
-__device__ __forceinline__ void load_boards(const int8_t *bd, int lane, BB &black, BB &white)
-{
-    uint32_t bl[3], wh[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int p = lane + 32 * k;
-        const int v = p < BK_NSQ ? (int)bd[p] : 0;
-        bl[k] = __ballot_sync(0xffffffffu, v == 1);
-        wh[k] = __ballot_sync(0xffffffffu, v == -1);
-    }
-    black.w[0] = bl[0] & BK_M27;
-    black.w[1] = ((bl[0] >> 27) | (bl[1] << 5)) & BK_M27;
-    black.w[2] = ((bl[1] >> 22) | (bl[2] << 10)) & BK_M27;
-    white.w[0] = wh[0] & BK_M27;
-    white.w[1] = ((wh[0] >> 27) | (wh[1] << 5)) & BK_M27;
-    white.w[2] = ((wh[1] >> 22) | (wh[2] << 10)) & BK_M27;
-}
-
-// warp-wide (max value, lowest index) -- the "first maximum" of a sequential argmax
-__device__ __forceinline__ void warp_argmax(float &v, int &i)
-{
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
-    }
-}
-
-// block-wide (max value, lowest index): warp shuffles, then the three warps' candidates through shared memory
-__device__ __forceinline__ void block_argmax(float &v, int &i, float *sv, int *si, int wsq, int lane)
-{
-    warp_argmax(v, i);
-    __syncthreads();                       // the previous round's readers are done with sv / si
-    if (lane == 0) { sv[wsq] = v; si[wsq] = i; }
-    __syncthreads();
-    v = sv[0]; i = si[0];
-#pragma unroll
-    for (int w = 1; w < 3; ++w)
-        if (sv[w] > v || (sv[w] == v && si[w] < i)) { v = sv[w]; i = si[w]; }
-}
-
-// One block of three warps per board, thread t = square t (as in bk_encode_kernel); the group table answers every
-// "what if a stone is put here" question by look-up.
+// One block of three warps per board, thread t = square t (as in bk_encode_kernel); the move itself is bk_step_board
+// (bk_step_core.cuh), shared with the persistent playout kernel.
 __global__ void __launch_bounds__(96)
 bk_step_kernel(int8_t *__restrict__ boards, int16_t *__restrict__ ko_arr, int16_t *__restrict__ last_arr,
                int16_t *__restrict__ turn_arr, uint8_t *__restrict__ libs, uint8_t *__restrict__ done,
                const float *__restrict__ probs, const float *__restrict__ q_inj, int q_vecs, uint64_t seed,
                uint32_t game0, int mode, int max_turn, int16_t *__restrict__ moves_out, uint4 *__restrict__ feats_conv, int B)
 {
-    __shared__ BKGroups grp;
-    __shared__ float s_v[3];
-    __shared__ int s_i[3];
-    __shared__ uint8_t s_ok[BK_NSQ + 15];
+    __shared__ BkStepScratch sc;
     const int b = (int)blockIdx.x;
-    const int lane = threadIdx.x & 31, wsq = threadIdx.x >> 5;
-    const int p = threadIdx.x;                       // this thread's square (81..95 idle)
-    const bool active = p < BK_NSQ;
     if (b >= B) return;
-    if (done[b]) {
-        if (threadIdx.x == 0 && moves_out) moves_out[b] = -3;
-        return;
-    }
-    int8_t *bd = boards + (size_t)b * BK_NSQ;
-    int ko = ko_arr[b], last = last_arr[b], turn = turn_arr[b];
-    BB black, white;
-    load_boards(bd, lane, black, white);
-    const bool blk = (turn & 1) == 0;
-    const BB own = blk ? black : white, opp = blk ? white : black;
-    const int me = blk ? 1 : -1;
-    bk_groups_build(grp, black, white, p);
-    const bool stale = libs && last >= 0 && libs[(size_t)b * BK_NSQ + last] == 0;
-    __syncthreads();
-
-    // probability and accept flag of this thread's square: Game.is_legal (go.py:184-200, early exit kept) and, in the
-    // mcts flavour, not an own eye (mcts.py:354)
-    float pr = 0.0f;
-    bool ok = false;
-    if (active) {
-        pr = probs[(size_t)b * BK_NSQ + p];
-        if (!bb_test(own, p) && !bb_test(opp, p)) {
-            int nb[4];
-            const int n = bb_nbr_list(p, nb);
-            const BB occ = bb_or(own, opp);
-            int empties = 0;
-            bool early = false;
-            for (int k = 0; k < n; ++k) {
-                if (empties > 1) { early = true; break; }
-                if (!bb_test(occ, nb[k])) ++empties;
-            }
-            ok = early || (p != ko && bk_groups_candidate(grp, own, opp, p, nullptr).libs_after > 0);
-            if (mode == 0 && ok) ok = bb_possible_eye(black, white, p) != me;
-        }
-        s_ok[p] = ok;
-    }
-    __syncthreads();
-
-    int mv = BK_NONE;
-    int t = 0;
-    for (;;) {
-        if (t > 0) {
-            if (!__syncthreads_or(pr > 0.0f)) { mv = BK_PASS; break; }
-            if (q_inj && t >= q_vecs) { mv = -4; break; }
-        }
-        float bv = -1.0f;
-        int bi = 0x7fffffff;
-        if (active) {
-            const float q = q_inj ? q_inj[((size_t)b * q_vecs + t) * BK_NSQ + p]
-                                  : bk_exp_draw(seed, game0 + (uint32_t)b, (uint32_t)turn, (uint32_t)t, p);
-            bv = __fdiv_rn(pr, q);
-            bi = p;
-        }
-        block_argmax(bv, bi, s_v, s_i, wsq, lane);
-        ++t;
-        const bool accept = s_ok[bi] != 0;
-        if (mode == 1) {
-            if (accept) { mv = bi; break; }
-            // highest-probability legal move, lowest index on ties
-            float fv = (active && ok) ? pr : -1.0f;
-            int fi = (active && ok) ? p : 0x7fffffff;
-            block_argmax(fv, fi, s_v, s_i, wsq, lane);
-            mv = fi == 0x7fffffff ? BK_NONE : fi;
-            break;
-        }
-        if (accept) { mv = bi; break; }
-        if (t - 1 >= BK_NSQ) { mv = BK_PASS; break; }   // tries >= 81 (mcts.py:354)
-        if (p == bi) pr = 0.0f;
-    }
-
-    if (threadIdx.x == 0 && moves_out) moves_out[b] = (int16_t)mv;
-    if (mv == BK_NONE || mv == -4) {
-        if (threadIdx.x == 0) done[b] = 1;
-        return;
-    }
-
-    // lazy liberty cache on the position BEFORE the move (go.py:160); a PASS does not touch it
-    if (libs && mv >= 0 && active) {
-        uint8_t *lb = libs + (size_t)b * BK_NSQ;
-        lb[p] = (uint8_t)bk_groups_lazy_lib(grp, black, white, last, stale, p, (int)lb[p]);   // `stale` was read before the barrier
-    }
-
-    // Game.play_move (go.py:123-182) from the table: every thread derives the same outcome
-    int st = 0;
-    if (mv == BK_PASS) {
-        turn += 1; ko = -1; last = BK_PASS;
-    } else if (mv == ko) {
-        st = 1;
-    } else if (bb_test(black, mv) || bb_test(white, mv)) {
-        st = 2;
-    } else {
-        const int pk = bb_possible_ko(black, white, mv);
-        BB dead;
-        const Cand c = bk_groups_candidate(grp, own, opp, mv, &dead);
-        if (c.libs_after == 0) {
-            st = 3;
-        } else {
-            ko = (c.caps == 1 && pk == (blk ? -1 : 1)) ? c.single_cap : -1;
-            const BB own2 = bb_or(own, bb_bit(mv)), opp2 = bb_andn(opp, dead);
-            black = blk ? own2 : opp2;
-            white = blk ? opp2 : own2;
-            last = mv;
-            turn += 1;
-        }
-    }
-    if (st != 0) {   // cannot happen for a position reached by legal play; flag instead of corrupting state
-        if (threadIdx.x == 0) { done[b] = 1; if (moves_out) moves_out[b] = (int16_t)(-10 - st); }
-        return;
-    }
-    if (active) bd[p] = bb_test(black, p) ? 1 : (bb_test(white, p) ? -1 : 0);
-    const bool over = mode == 0 ? (turn > max_turn || last == BK_PASS) : (turn > max_turn + 1);
-    if (threadIdx.x == 0) {
-        ko_arr[b] = (int16_t)ko; last_arr[b] = (int16_t)last; turn_arr[b] = (int16_t)turn;
-        if (over) done[b] = 1;
-    }
-    if (!feats_conv || over) return;        // block-uniform
-
-    // ---- re-encode: nnet.features of the new position with the carried cache (what the next policy call sees) -------
-    __syncthreads();                         // every thread is done with the old table; the cache refresh above is visible
-    bk_groups_build(grp, black, white, p);
-    uint8_t *lb = libs + (size_t)b * BK_NSQ;
-    const bool stale2 = last >= 0 && lb[last] == 0;
-    __syncthreads();                         // table complete; lb[last] has been read by everyone before lb[] is rewritten
-    if (!active) return;
-    bk_encode_square(grp, black, white, (turn & 1) == 0, ko, last, true, stale2, (int)lb[p], p, (size_t)b,
-                     bk_conv_base(feats_conv, b), nullptr, nullptr, nullptr, libs);
+    bk_step_board(BkSyncBlock(), sc, (int)threadIdx.x, b, boards + (size_t)b * BK_NSQ, ko_arr, last_arr, turn_arr,
+                  libs ? libs + (size_t)b * BK_NSQ : nullptr, done, probs + (size_t)b * BK_NSQ,
+                  q_inj ? q_inj + (size_t)b * q_vecs * BK_NSQ : nullptr, q_vecs, seed, game0 + (uint32_t)b, mode, max_turn,
+                  moves_out ? moves_out + b : nullptr, feats_conv ? bk_conv_base(feats_conv, b) : nullptr, BK_F_ROWS_G);
 }
 
 __global__ void __launch_bounds__(128)
@@ -222,7 +53,7 @@ bk_score_kernel(const int8_t *__restrict__ boards, float komi, float *__restrict
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
     BB black, white;
-    load_boards(boards + (size_t)b * BK_NSQ, lane, black, white);
+    bk_load_boards(boards + (size_t)b * BK_NSQ, lane, black, white);
     if (lane == 0) {
         const float sc = (float)bb_score_diff(black, white) - komi;
         if (score_out) score_out[b] = sc;
@@ -250,7 +81,7 @@ bk_make_moves_kernel(const int8_t *__restrict__ boards, const int16_t *__restric
     const int mv = moves[c];
     int ko = ko_arr[par], last = last_arr[par], turn = turn_arr[par];
     BB black, white;
-    load_boards(boards + (size_t)par * BK_NSQ, lane, black, white);
+    bk_load_boards(boards + (size_t)par * BK_NSQ, lane, black, white);
     if (libs_out) {
         const uint8_t *lb = libs ? libs + (size_t)par * BK_NSQ : nullptr;
         const bool stale = lb && mv >= 0 && last >= 0 && lb[last] == 0;

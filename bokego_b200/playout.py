@@ -1,8 +1,12 @@
 """Whole playouts and self-play games on the device, sharded over ranks (SURVEY 8b `playout_batch`, 8e).
 
-One move step for every board of a batch = two kernel launches, boards resident in HBM:
+Whole playouts are ONE kernel launch (bk_playout_run, `persistent=True`, the default): the conv kernel keeps each group of five
+boards on its SM for the whole game -- policy forward, then sample / play / capture / re-encode by three warps per board
+straight into the shared-memory operand of the next move -- after one bk_encode of the starting positions and before one
+bk_score.  The launch-per-move form (`persistent=False`) does the same with two launches per move, boards resident in HBM:
     bk_forward (policy only)  ->  bk_playout_step_encode (sample, play, capture, re-encode the new position in place)
-after one bk_encode of the starting positions -- which is exactly the loop of the reference's `MCTS._simulate` (/root/reference/bokego/mcts.py:195-206: `find_random_child`
+and is what a net in training uses (reinforce.PolicyTrainer records planes and statistics move by move).  Both give the same
+games, bit for bit.  It is exactly the loop of the reference's `MCTS._simulate` (/root/reference/bokego/mcts.py:195-206: `find_random_child`
 until terminal, then `reward`) and of `bin/selfplay.py:18-33` (`playout`: `legal_sample` for pi_1 / pi_2 alternately), run for
 all boards at once.  The steps of a whole game are captured once in a CUDA graph and replayed (the per-step work is small
 at self-play batch sizes, so launch latency matters).
@@ -13,7 +17,8 @@ keyed by the GLOBAL id, so results do not depend on R.  The only communication i
 import torch
 
 from . import _lib
-from .batched import (MODE_MCTS, MODE_SELFPLAY, Positions, features_batch, playout_step, policy_value_batch, score_batch)
+from .batched import (MODE_MCTS, MODE_SELFPLAY, Positions, features_batch, playout_run, playout_step, policy_value_batch,
+                      score_batch)
 
 MCTS_MAX_TURN = 80        # mcts.py:13  (terminal iff turn > 80 or the move was PASS, mcts.py:362-364)
 SELFPLAY_MAX_TURN = 70    # bin/selfplay.py:16 (checked every two moves => 72 moves, selfplay.py:21-33)
@@ -60,7 +65,7 @@ def n_steps_for(mode, max_turn, first_turn=0):
 
 
 def run_playouts(pos, policy, mode=MODE_MCTS, max_turn=None, seed=0, game0=0, policy_odd=None, n_steps=None,
-                 first_turn=0, komi=5.5, graph=True):
+                 first_turn=0, komi=5.5, graph=True, persistent=True):
     """Play every board of `pos` to the end with moves drawn from the policy net(s).
 
     policy:     PackedNet used for every move, or for the moves made at even `turn` when policy_odd is given
@@ -68,6 +73,8 @@ def run_playouts(pos, policy, mode=MODE_MCTS, max_turn=None, seed=0, game0=0, po
     policy_odd: PackedNet for the moves at odd turn (self-play of two nets; needs every board at the same turn parity,
                 `first_turn` states it)
     mode:       MODE_MCTS (Go_MCTS.find_random_child, mcts.py:319-364) or MODE_SELFPLAY (legal_sample, selfplay.py:35-47)
+    persistent: all moves in one launch of the persistent playout kernel (ignored when a net is being trained);
+                otherwise two launches per move, replayed from a CUDA graph when `graph`
     Updates `pos` in place (pos.libs is allocated when absent: the first encode then takes exact liberties, like a fresh
     Game) and returns a PlayoutResult.  Stream-ordered; does not synchronise.
     """
@@ -85,6 +92,12 @@ def run_playouts(pos, policy, mode=MODE_MCTS, max_turn=None, seed=0, game0=0, po
     probs = torch.empty(B, 81, dtype=torch.float32, device=dev)
 
     training = any(hasattr(n, "play_probs") for n in (policy, policy_odd) if n is not None)
+    if persistent and not training and n_steps > 0:
+        features_batch(pos, fresh_libs=fresh_first, want=("conv", "libs"), out=bufs)
+        playout_run(pos, bufs["conv"], policy, n_steps, mode, max_turn, seed=seed, game0=game0, policy_odd=policy_odd,
+                    first_turn=first_turn, moves_out=moves)
+        score, reward = score_batch(pos.boards, komi)
+        return PlayoutResult(moves.t().contiguous(), pos.turn.clone(), score, reward)
     encoded = [False]      # bufs["conv"] holds the planes of the current positions (written by the previous move's launch)
 
     def step(k, fresh):
@@ -132,7 +145,7 @@ class PlayoutGraph:
     the form used when the same batch of games is played repeatedly (benchmarks, fixed-size self-play workers).
     Seed and first game id are kernel arguments and therefore fixed at capture."""
 
-    def __init__(self, B, device, policy, mode, max_turn=None, seed=0, game0=0, policy_odd=None, komi=5.5):
+    def __init__(self, B, device, policy, mode, max_turn=None, seed=0, game0=0, policy_odd=None, komi=5.5, persistent=True):
         dev = _lib.require_device(device)
         if max_turn is None:
             max_turn = MCTS_MAX_TURN if mode == MODE_MCTS else SELFPLAY_MAX_TURN
@@ -149,16 +162,20 @@ class PlayoutGraph:
         def body():
             pos.boards.zero_(); pos.ko.fill_(-1); pos.last.fill_(-2); pos.turn.zero_(); pos.done.zero_()
             features_batch(pos, fresh_libs=True, want=("conv", "libs"), out=bufs)
-            for k in range(self.n_steps):
-                net = policy if (policy_odd is None or k % 2 == 0) else policy_odd
-                policy_value_batch(bufs["conv"], B, net, None, want_logits=False, probs_out=probs)
-                playout_step(pos, probs, mode, max_turn, seed=seed, game0=game0, moves_out=self.moves[k], encode_into=bufs["conv"])
+            if persistent:
+                playout_run(pos, bufs["conv"], policy, self.n_steps, mode, max_turn, seed=seed, game0=game0, policy_odd=policy_odd,
+                            moves_out=self.moves)
+            else:
+                for k in range(self.n_steps):
+                    net = policy if (policy_odd is None or k % 2 == 0) else policy_odd
+                    policy_value_batch(bufs["conv"], B, net, None, want_logits=False, probs_out=probs)
+                    playout_step(pos, probs, mode, max_turn, seed=seed, game0=game0, moves_out=self.moves[k], encode_into=bufs["conv"])
             score_batch(pos.boards, komi, out=(self.score, self.reward))
 
         # one eager step first: the library sets its kernel attributes on first use, which must not happen under capture
         features_batch(pos, fresh_libs=True, want=("conv", "libs"), out=bufs)
         policy_value_batch(bufs["conv"], B, policy, None, want_logits=False, probs_out=probs)
-        self.launches = 5 + 1 + 2 * self.n_steps + 1
+        self.launches = 5 + 1 + (1 if persistent else 2 * self.n_steps) + 1
         self.graph = torch.cuda.CUDAGraph()
         cap = torch.cuda.Stream(device=dev)
         cap.wait_stream(torch.cuda.current_stream(dev))

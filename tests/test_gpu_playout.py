@@ -176,3 +176,51 @@ def test_simulate_65536_boards_subset_vs_oracle(env):
     b_rec = po.PlayoutResult(torch.stack(moves, 1), pos.turn, score, reward).records()
     assert torch.equal(rec_a, b_rec)
     assert set(np.unique(reward.cpu().numpy())) <= {-1, 1}
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("B", [1, 7, 203, 745, 1485])
+def test_persistent_playout_kernel_equals_launch_per_move(env, mode, B):
+    """bk_playout_run (whole games inside one launch of the conv kernel: policy forward, then three warps per board sample,
+    play and re-encode into the shared-memory operand of the next move) against the launch-per-move loop: every move, the
+    final boards / ko / last / turn / liberty caches / done flags, scores and rewards must be identical.  B = 7 and 203 end in a
+    partial group, 745 in a CTA pair whose second CTA has no boards, 1485 needs more than one round of the 74 CTA pairs."""
+    bk, po, dev, p17, p19 = env
+    odd = p19 if mode == 1 else None
+    a_pos, b_pos = bk.Positions.empty(B, dev, track_libs=False), bk.Positions.empty(B, dev, track_libs=False)
+    a = po.run_playouts(a_pos, p17, mode, seed=13, game0=77, policy_odd=odd, persistent=True)
+    b = po.run_playouts(b_pos, p17, mode, seed=13, game0=77, policy_odd=odd, persistent=False, graph=False)
+    torch.cuda.synchronize()
+    assert torch.equal(a.moves, b.moves)
+    for x, y in ((a_pos.boards, b_pos.boards), (a_pos.ko, b_pos.ko), (a_pos.last, b_pos.last), (a_pos.turn, b_pos.turn),
+                 (a_pos.done, b_pos.done), (a_pos.libs, b_pos.libs), (a.score, b.score), (a.reward, b.reward)):
+        assert torch.equal(x, y)
+    assert bool(a_pos.done.all())
+
+
+def test_persistent_playout_from_midgame_positions_and_repeats(env):
+    """playouts that start from arbitrary positions with a carried liberty cache (the leaves of a --simulate search), odd
+    first turn, repeated launches with cold and warm L2: identical to the launch-per-move loop every time"""
+    bk, po, dev, p17, p19 = env
+    B = 333
+    base = bk.Positions.empty(B, dev)
+    uni = torch.full((B, 81), 1.0 / 81, dtype=torch.float32, device=dev)
+    for _ in range(23):                                   # 23 random legal moves: White to move, captures and kos on the boards
+        bk.features_batch(base, fresh_libs=False, want=("libs",), out={"libs": base.libs})
+        bk.playout_step(base, uni, bk.MODE_MCTS, 1000, seed=4, game0=0)
+    keep = [t.clone() for t in (base.boards, base.ko, base.last, base.turn, base.libs)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    want = None
+    for rep in range(6):
+        pos = bk.Positions(*(t.clone() for t in keep))
+        pos.done = ((pos.turn > 80) | (pos.last == -1)).to(torch.uint8)
+        if rep % 2:
+            flush.zero_()
+        res = po.run_playouts(pos, p17, bk.MODE_MCTS, seed=3, game0=5, first_turn=23, n_steps=po.n_steps_for(bk.MODE_MCTS, 80, 23),
+                              persistent=rep > 0, graph=False)
+        torch.cuda.synchronize()
+        got = (res.moves.clone(), pos.boards.clone(), pos.libs.clone(), res.score.clone())
+        if want is None:
+            want = got
+        for x, y in zip(got, want):
+            assert torch.equal(x, y), rep

@@ -34,8 +34,10 @@ def main():
     p19 = bk.PackedNet(dict(np.load(os.path.join(g, "weights_policy_19.npz"))), dev)
     sizes = [int(x) for x in sys.argv[1:]] or [512, 1024, 2048, 4096]
     for B in sizes:
-        sp = po.PlayoutGraph(B, dev, p17, bk.MODE_SELFPLAY, seed=1, policy_odd=p19)
+        sp = po.PlayoutGraph(B, dev, p17, bk.MODE_SELFPLAY, seed=1, policy_odd=p19, persistent=False)
         ms = timed(sp.replay, n=5, warm=2)
+        spk = po.PlayoutGraph(B, dev, p17, bk.MODE_SELFPLAY, seed=1, policy_odd=p19, persistent=True)
+        ms_k = timed(spk.replay, n=5, warm=2)
         # a mid-game position set for the per-kernel timings
         pos = bk.Positions.empty(B, dev)
         bufs = bk.features_batch(pos, fresh_libs=True, want=("conv", "libs"), out={"libs": pos.libs})
@@ -62,7 +64,9 @@ def main():
         t_se = timed(step_enc, n=50) - t_restore
         t_s = timed(step_only, n=50) - t_restore
         t_e = timed(lambda: bk.features_batch(pos, fresh_libs=False, want=("conv", "libs"), out=bufs), n=50)
-        print(json.dumps({"boards": B, "selfplay_ms_per_batch": ms, "us_per_move": 1e3 * ms / 72, "games_per_s": B / (1e-3 * ms),
+        print(json.dumps({"boards": B, "persistent_kernel": {"selfplay_ms_per_batch": ms_k, "us_per_move": 1e3 * ms_k / 72,
+                                                             "games_per_s": B / (1e-3 * ms_k)},
+                          "selfplay_ms_per_batch": ms, "us_per_move": 1e3 * ms / 72, "games_per_s": B / (1e-3 * ms),
                           "launches_per_move": 2, "forward_policy_us": 1e3 * fwd, "step_encode_us": 1e3 * t_se,
                           "step_only_us": 1e3 * t_s, "encode_only_us": 1e3 * t_e}), flush=True)
 
