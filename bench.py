@@ -616,14 +616,16 @@ def run_ours(args, rank, world, local_rank):
             extra = {"selfplay": {"games": args.selfplay_games, "games_per_s": args.selfplay_games * 3 / (1e-3 * sp_tot),
                                   "ms_per_batch": sp_tot / 3, "moves_per_game": 72, "scaling": "strong",
                                   "nets": "policy_17 (black) vs policy_19 (white)", "gather": "nccl all_gather of records" if world > 1 else "none",
-                                  "kernel_launches_per_batch": sp.launches},
+                                  "kernel_launches_per_batch": sp.launches, "boards_per_gpu": hi - lo, "us_per_move": 1e3 * sp_tot / 3 / 72,
+                                  "engine": "persistent playout kernel (bk_playout_run: whole games in one launch)" if sp.persistent
+                                  else "two launches per move (bk_forward + bk_playout_step_encode), CUDA graph"},
                      "simulate": {"boards_per_gpu": args.simulate_boards, "playouts_per_s": world * args.simulate_boards * 2 / (1e-3 * sim_tot),
                                   "ms_per_batch": sim_tot / 2, "scaling": "weak", "max_turn": 80}}
             # weak-scaling self-play beside the strong-scaling line: args.selfplay_games games PER GPU
             if world > 1:
                 spw = po.PlayoutGraph(args.selfplay_games, dev, pol, bk.MODE_SELFPLAY, seed=1, game0=rank * args.selfplay_games, policy_odd=pol19)
                 spw_tot, _ = timed(lambda: spw.replay(), 3, 1, flush_l2=False)
-                extra["selfplay"]["weak_scaling"] = {"games_per_gpu": args.selfplay_games,
+                extra["selfplay"]["weak_scaling"] = {"games_per_gpu": args.selfplay_games, "persistent_kernel": spw.persistent,
                                                      "games_per_s": world * args.selfplay_games * 3 / (1e-3 * spw_tot), "ms_per_batch": spw_tot / 3}
                 del spw
             # BASELINE configs[2] and [0]: one genmove from the empty board -- rank 0 only (a host-side search per rank would only

@@ -46,7 +46,9 @@ def _sig(L):
     L.bk_playout_step_encode.restype = i32
     L.bk_playout_step_encode.argtypes = [vp] * 8 + [i32, u64, u32, i32, i32, vp, vp, i32, vp]
     L.bk_playout_run.restype = i32
-    L.bk_playout_run.argtypes = [vp] * 9 + [u64, u32, i32, i32, i32, i32, vp, i32, vp]
+    L.bk_playout_run.argtypes = [vp] * 8 + [u64, u32, i32, i32, i32, i32, i32, vp, i32, vp]
+    L.bk_playout_run_debug.restype = i32
+    L.bk_playout_run_debug.argtypes = [vp] * 8 + [u64, u32, i32, i32, i32, i32, i32, vp, i32, vp, vp]
     L.bk_make_moves.restype = i32
     L.bk_make_moves.argtypes = [vp] * 13 + [i32, vp]
     L.bk_tree_run.restype = i32

@@ -293,24 +293,27 @@ def playout_step(pos, probs, mode, max_turn, seed=0, game0=0, q_inj=None, moves_
     return moves_out
 
 
-def playout_run(pos, feats_conv, policy, n_steps, mode, max_turn, seed=0, game0=0, policy_odd=None, first_turn=0, moves_out=None):
-    """n_steps playout moves for every board in ONE kernel launch (bk_playout_run): the conv kernel keeps each group of five
-    boards on its SM for the whole playout.  feats_conv: "conv" planes of the current positions (features_batch), pos.libs their
-    liberty cache.  Updates `pos` in place; returns moves int16 [n_steps, B]."""
+def playout_run(pos, policy, n_steps, mode, max_turn, seed=0, game0=0, policy_odd=None, first_turn=0, fresh_libs=None,
+                moves_out=None):
+    """n_steps playout moves for every board in ONE kernel launch (bk_playout_run): the conv kernel keeps each item of <= 5
+    boards on its SM for the whole playout, positions resident on chip.  fresh_libs: True -> the positions are fresh Games
+    (exact liberties); False -> pos.libs is their carried cache; None -> fresh iff pos.libs is None.
+    Updates `pos` in place (pos.libs is allocated when absent); returns moves int16 [n_steps, B]."""
     L = _lib.lib()
     dev, B = pos.device, pos.B
+    fresh = pos.libs is None if fresh_libs is None else fresh_libs
     if pos.libs is None:
-        raise ValueError("playout_run needs the carried liberty cache pos.libs")
-    if feats_conv.device != dev or feats_conv.numel() < L.bk_feats_conv_bytes(B):
-        raise ValueError("feats_conv: wrong device or too small for B")
+        if not fresh:
+            raise ValueError("fresh_libs=False needs pos.libs")
+        pos.libs = torch.zeros(B, 81, dtype=torch.uint8, device=dev)
     if moves_out is None:
         moves_out = torch.empty(n_steps, B, dtype=torch.int16, device=dev)
     _want(moves_out, torch.int16, (n_steps, B), "moves_out", dev)
     with torch.cuda.device(dev):
         rc = L.bk_playout_run(_lib.ptr(pos.boards), _lib.ptr(pos.ko), _lib.ptr(pos.last), _lib.ptr(pos.turn), _lib.ptr(pos.libs),
-                              _lib.ptr(pos.done), _lib.ptr(feats_conv), _lib.ptr(policy.blob),
-                              _lib.ptr(policy_odd.blob if policy_odd is not None else None), C.c_uint64(seed), C.c_uint32(game0),
-                              mode, max_turn, first_turn, n_steps, _lib.ptr(moves_out), B, _lib.stream_ptr(dev))
+                              _lib.ptr(pos.done), _lib.ptr(policy.blob), _lib.ptr(policy_odd.blob if policy_odd is not None else None),
+                              C.c_uint64(seed), C.c_uint32(game0), mode, max_turn, first_turn, n_steps, int(bool(fresh)),
+                              _lib.ptr(moves_out), B, _lib.stream_ptr(dev))
     _lib.check(rc, "bk_playout_run")
     _lib.count_launch()
     return moves_out

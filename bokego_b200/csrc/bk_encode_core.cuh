@@ -23,9 +23,10 @@ __device__ __forceinline__ uint4 *bk_conv_base(uint4 *feats_conv, int slot)
 // Planes of square p of board b from the group table `grp` of the position (black, white, ko, last, turn parity `blk`).
 // carried = the position has a liberty cache (Game._libs): lib_carried is its entry for p, `stale` = last >= 0 and the
 // cache entry of `last` is 0 (go.py:226); otherwise exact liberties (fresh Game).  Every output pointer may be null.
+// Returns the new liberty-cache entry of p (what libs_out receives).
 // conv_base = first uint4 of this board's rows in the conv operand, chunk_stride = distance between channel chunks in uint4
 // (BK_F_ROWS_G in global memory; the row count of the shared-memory copy inside the conv kernel).
-__device__ __forceinline__ void bk_encode_square(const BKGroups &grp, BB black, BB white, bool blk, int ko, int last, bool carried,
+__device__ __forceinline__ int bk_encode_square(const BKGroups &grp, BB black, BB white, bool blk, int ko, int last, bool carried,
                                                  bool stale, int lib_carried, int p, size_t b, uint4 *conv_base, int chunk_stride,
                                                  float *feats_f32, uint8_t *planes_u8, uint8_t *legal_out, uint8_t *libs_out)
 {
@@ -84,4 +85,5 @@ __device__ __forceinline__ void bk_encode_square(const BKGroups &grp, BB black, 
             conv_base[c * chunk_stride + r] = o;
         }
     }
+    return lib;
 }

@@ -72,12 +72,14 @@ constexpr int OFF_ONES = OFF_BIASW + CTA_BIAS_BYTES;
 constexpr int OFF_BAR = OFF_ONES + ONES_BYTES;     // barriers, 8 B each
 constexpr int OFF_TMEM = OFF_BAR + 192;
 constexpr int OFF_LOGIT = OFF_TMEM + 16;           // float[5][81]: head output per square
-constexpr int SMEM_BYTES = OFF_LOGIT + 1664;       // 232,016
+constexpr int OFF_RES = OFF_LOGIT + 1664;          // PLAYOUT: resident positions of the item's boards (BkResident[5])
+constexpr int SMEM_BYTES = OFF_RES + 240;          // 232,256
 static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KiB");
 // PLAYOUT: between the last layer of move k and layer 0 of move k + 1 the activation buffer is dead; the step phase keeps its
 // per-board scratch (group table, arg-max slots) at its start and zeroes it again (padding rows must read as zero)
 constexpr int STEP_SCRATCH = (int)((sizeof(BkStepScratch) + 15) / 16 * 16);
 static_assert(BK_GROUP * STEP_SCRATCH <= A_BYTES, "step scratch");
+static_assert(BK_GROUP * sizeof(BkResident) <= 240, "resident positions");
 static_assert(OFF_W % 128 == 0 && OFF_ONES % 128 == 0 && OFF_BIASW % 128 == 0, "operand alignment");
 
 // WFULL (leader): both CTAs' halves of a stage have landed -- each CTA's tensor-map copy (cta_group::2) reports its
@@ -290,6 +292,8 @@ struct FwdArgs {
     // (first_turn + k); moves_out is [n_steps][B]
     int8_t *boards; int16_t *ko, *last, *turn; uint8_t *libs, *done; int16_t *moves_out;
     int n_steps, mode, max_turn, first_turn;
+    int play_group;            // boards per item (1..5): the smallest that puts every board on an SM in one round
+    int fresh_libs;            // the starting positions have no liberty cache (exact liberties, like fresh Games)
     unsigned long long seed;
     uint32_t game0;
 };
@@ -315,6 +319,16 @@ __device__ __forceinline__ void decode_sub(const FwdArgs &a, int u, Item &it)
     it.lo = min(lo, in_group);
     it.nb = min(hi, in_group) - it.lo;
 }
+// PLAYOUT: sub-item u = boards [u * play_group, (u + 1) * play_group) of the batch (it.g = first board, it.lo = 0)
+__device__ __forceinline__ void decode_play(const FwdArgs &a, int u, Item &it)
+{
+    it.net = 0; it.lo = 0;
+    it.g = u * a.play_group;
+    it.nb = u < a.n_sub ? min(a.play_group, a.B - it.g) : 0;
+    if (it.nb < 0) it.nb = 0;
+}
+template <bool PLAYOUT>
+__device__ __forceinline__ bool decode_pair_t(const FwdArgs &a, int v, int rank, Item &mine, int &pair_nb);
 // pair v -> this CTA's item and the board count that fixes the pass structure of the pair; false = nothing to do
 __device__ __forceinline__ bool decode_pair(const FwdArgs &a, int v, int rank, Item &mine, int &pair_nb)
 {
@@ -323,6 +337,17 @@ __device__ __forceinline__ bool decode_pair(const FwdArgs &a, int v, int rank, I
     decode_sub(a, 2 * j + rank, mine);
     decode_sub(a, 2 * j + (rank ^ 1), other);
     mine.net = a.first_net + (v - j * a.n_nets);
+    pair_nb = max(mine.nb, other.nb);
+    return pair_nb > 0;
+}
+
+template <bool PLAYOUT>
+__device__ __forceinline__ bool decode_pair_t(const FwdArgs &a, int v, int rank, Item &mine, int &pair_nb)
+{
+    if (!PLAYOUT) return decode_pair(a, v, rank, mine, pair_nb);
+    Item other;
+    decode_play(a, 2 * v + rank, mine);
+    decode_play(a, 2 * v + (rank ^ 1), other);
     pair_nb = max(mine.nb, other.nb);
     return pair_nb > 0;
 }
@@ -549,9 +574,9 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
             Item it, nx;
             int pair_nb, nx_nb;
             uint32_t n_femp = 0;    // FEMPTY phases consumed (one per item and move)
-            if (pair0 < args.n_pairs && decode_pair(args, pair0, rank, it, pair_nb)) load_feats(it);
+            if (pair0 < args.n_pairs && decode_pair_t<PLAYOUT>(args, pair0, rank, it, pair_nb) && !PLAYOUT) load_feats(it);
             for (int v = pair0; v < args.n_pairs; v += n_clusters) {
-                if (!decode_pair(args, v, rank, it, pair_nb)) continue;
+                if (!decode_pair_t<PLAYOUT>(args, v, rank, it, pair_nb)) continue;
                 for (int k = 0; k < n_steps; ++k) {
                     const int net = PLAYOUT ? ((args.first_turn + k) & 1) : it.net;
                     const CUtensorMap *tm = net == 0 ? &tm_policy : &tm_value;
@@ -563,8 +588,8 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     // item's last move is past that point (in between, the epilogue warps write the next move's planes)
                     mbar_wait(sBar + 8 * BAR_FEMPTY, n_femp & 1u, 0x200u);
                     ++n_femp;
-                    if (k == n_steps - 1 && v + n_clusters < args.n_pairs && decode_pair(args, v + n_clusters, rank, nx, nx_nb))
-                        load_feats(nx);
+                    // (PLAYOUT: the planes never come from global memory -- the epilogue warps encode every position in place)
+                    if (!PLAYOUT && v + n_clusters < args.n_pairs && decode_pair(args, v + n_clusters, rank, nx, nx_nb)) load_feats(nx);
                     for (int l = 2; l <= 6; ++l) stream(tm, tb, BK_W_L_OFF(l), n_stages_of(l));
                 }
             }
@@ -576,7 +601,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         Item it;
         int pair_nb;
         for (int v = pair0; v < args.n_pairs; v += n_clusters) {
-            if (!decode_pair(args, v, rank, it, pair_nb)) continue;
+            if (!decode_pair_t<PLAYOUT>(args, v, rank, it, pair_nb)) continue;
             for (int k = 0; k < n_steps; ++k) {
                 mbar_wait(sBar + 8 * BAR_FFULL, n_done & 1u, 0x300u);
                 ++n_done;
@@ -597,7 +622,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         int n_tiles = 0;
         // one stage: up to four K steps with A windows a[0..nk-1], B = the 2 KiB K steps of ring slot `st` in both CTAs
         long long tw = 0, tp = 0, ti = 0;                  // diagnostic: cycles waiting for weights / bias rows, issuing
-        const bool profiling = args.prof != nullptr && blockIdx.x == 0;
+        const bool profiling = !PLAYOUT && args.prof != nullptr && blockIdx.x == 0;
         auto stage = [&](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int nk, uint32_t accum0) {
             long long c0 = 0, c1 = 0;
             if (profiling) c0 = clock64();
@@ -626,7 +651,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         Item it;
         int pair_nb;
         for (int v = pair0; v < args.n_pairs; v += n_clusters) {
-            if (!decode_pair(args, v, rank, it, pair_nb)) continue;
+            if (!decode_pair_t<PLAYOUT>(args, v, rank, it, pair_nb)) continue;
             const int np = n_passes(pair_nb);
             for (int k = 0; k < n_steps; ++k)
             for (int ps = 0; ps < np; ++ps, ++pass) {
@@ -634,12 +659,13 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     mbar_wait(sBar + 8 * BAR_FFULL, n_done & 1u, 0x300u);
                     mbar_wait(sBar + 8 * BAR_PFFULL, n_done & 1u, 0x380u);
                     ++n_done;
+                    if (PLAYOUT && args.prof && blockIdx.x == 0 && v == pair0 && k < 32 && lane == 0) args.prof[16 * k + 11] = clock64();
                 }
                 const Pass pi = pass_info(pair_nb, ps);
                 n_tiles = pi.n_tiles;
                 if (pass > 0) mbar_wait(sBar + 8 * BAR_ACT, (pass - 1) & 1u, 0x400u + pass);   // operands written, TMEM drained
                 tc_fence_after();
-                if (args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) args.prof[pass * 4 + 0] = clock64();
+                if (!PLAYOUT && args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) args.prof[pass * 4 + 0] = clock64();
                 if (pi.layer == 0) {
                     // stage s = taps 2s, 2s+1; a tap is two K steps (channel chunks 0,1 / 2,3); the last stage holds tap 24 only
                     const uint32_t fb = f_lo0 + (uint32_t)(128 * pi.tile0);
@@ -681,7 +707,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     umma_commit_pair(sBar + 8 * BAR_ACC);                      // accumulators of this pass complete
                 }
                 __syncwarp();
-                if (args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) {
+                if (!PLAYOUT && args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) {
                     args.prof[pass * 4 + 1] = clock64();
                     args.prof[256 + pass * 4 + 0] = tw; args.prof[256 + pass * 4 + 1] = tp; args.prof[256 + pass * 4 + 2] = ti;
                     tw = tp = ti = 0;
@@ -699,8 +725,30 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         Item it;
         int pair_nb;
         for (int v = pair0; v < args.n_pairs; v += n_clusters) {
-            if (!decode_pair(args, v, rank, it, pair_nb)) continue;
+            if (!decode_pair_t<PLAYOUT>(args, v, rank, it, pair_nb)) continue;
             const int np = n_passes(pair_nb);
+            // PLAYOUT: three warps per board (warp 15 idles) own one board of the item for the whole playout: its position is
+            // resident in shared memory (BkResident) plus one register per thread (the liberty-cache entry of the thread's square)
+            const int bi = warp / 3, sub = warp - 3 * bi;
+            const bool has_board = PLAYOUT && bi < it.nb;
+            const int gb = it.g + bi;                         // PLAYOUT: global index of the trio's board
+            BkStepScratch &sc = *reinterpret_cast<BkStepScratch *>(smem + OFF_A + (bi < BK_GROUP ? bi : 0) * STEP_SCRATCH);
+            BkResident &res = reinterpret_cast<BkResident *>(smem + OFF_RES)[bi < BK_GROUP ? bi : 0];
+            uint4 *const planes = reinterpret_cast<uint4 *>(smem + OFF_F) + F_MARGIN + BK_F_ROWS_B * (bi < BK_GROUP ? bi : 0);
+            const BkSyncNamed sy{2 + bi};
+            int my_lib = 0;
+            if (PLAYOUT) {
+                // ---- the starting positions: load, refresh the liberty cache, write the planes of move 0 (nnet.features)
+                if (has_board) {
+                    bk_resident_load(sy, sc, res, 32 * sub + lane, my_lib, gb, args.boards + (size_t)gb * BK_NSQ, args.ko, args.last,
+                                     args.turn, args.libs + (size_t)gb * BK_NSQ, args.done, args.fresh_libs != 0, planes, F_ROWS);
+                    uint4 *z = reinterpret_cast<uint4 *>(&sc);       // the scratch lives in the activation buffer: leave zeros
+                    for (int i = 32 * sub + lane; i < STEP_SCRATCH / 16; i += 96) z[i] = make_uint4(0u, 0u, 0u, 0u);
+                }
+                fence_proxy_async();
+                named_bar_sync(1, N_EPI_WARPS * 32);
+                if (threadIdx.x == 0) mbar_arrive(sBar + 8 * BAR_FFULL);
+            }
             for (int k = 0; k < n_steps; ++k)
             for (int ps = 0; ps < np; ++ps, ++pass) {
                 const int net = PLAYOUT ? ((args.first_turn + k) & 1) : it.net;
@@ -708,9 +756,13 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                 const Pass pi = pass_info(pair_nb, ps);
                 mbar_wait(sBar + 8 * BAR_ACC, pass & 1u, 0x600u + pass);
                 tc_fence_after();
-                const bool prof = args.prof && blockIdx.x == 0 && pass < 64 && threadIdx.x == 0;
+                const bool prof = !PLAYOUT && args.prof && blockIdx.x == 0 && pass < 64 && threadIdx.x == 0;
                 if (prof) args.prof[pass * 4 + 2] = clock64();
                 const bool dump = args.dump && blockIdx.x == 0 && first && ps == args.dump_pass;
+                if (PLAYOUT && args.prof && blockIdx.x == 0 && first && k < 32 && threadIdx.x == 0) {
+                    if (ps == 0) args.prof[16 * k + 10] = clock64();               // accumulators of the move's first pass ready
+                    if (pi.layer == 6) args.prof[16 * k + 9] = clock64();          // accumulators of the last layer ready
+                }
                 if (wq < pi.n_tiles) {
                     // one thread per GEMM row: all 128 output channels of row r (accumulator slot wq holds tile tile0 + wq)
                     const int r = 128 * (pi.tile0 + wq) + 32 * quad + lane;
@@ -766,30 +818,33 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                                          args.value ? args.value + b : nullptr, lane);
                         }
                     } else {
-                        // ---- step phase: three warps per board (warp 15 idles) sample the move from the policy's
-                        // probabilities, play it and write the planes of the new position into the feature operand of the
-                        // next move.  The activation buffer is dead here and lends its first bytes as scratch.
-                        const int bi = warp / 3, sub = warp - 3 * bi;
+                        // ---- step phase: the board's three warps sample the move from the policy's probabilities, play it
+                        // and write the planes of the new position into the feature operand of the next move.  The activation
+                        // buffer is dead here and lends its first bytes as scratch (zeroed again afterwards).
                         const bool last_move = k == n_steps - 1;
-                        if (bi < it.nb) {
-                            const int b = it.g * BK_GROUP + it.lo + bi;
+                        // diagnostic (bk_playout_run_debug): clock64 stamps per move of CTA 0's first item, taken by thread 0
+                        long long *stamps = (args.prof && blockIdx.x == 0 && first && k < 32) ? args.prof + 16 * k : nullptr;
+                        if (stamps && threadIdx.x == 0) stamps[6] = clock64();
+                        if (has_board) {
                             float *pr = logit + bi * 81;
-                            BkStepScratch &sc = *reinterpret_cast<BkStepScratch *>(smem + OFF_A + bi * STEP_SCRATCH);
-                            const BkSyncNamed sy{2 + bi};
                             if (sub == 0) finish_board(pr, 0, blob, nullptr, pr, nullptr, lane);       // softmax in place
                             sy.sync();
-                            uint4 *planes = last_move ? nullptr
-                                                      : reinterpret_cast<uint4 *>(smem + OFF_F) + F_MARGIN + BK_F_ROWS_B * (it.lo + bi);
-                            bk_step_board(sy, sc, 32 * sub + lane, b, args.boards + (size_t)b * BK_NSQ, args.ko, args.last, args.turn,
-                                          args.libs + (size_t)b * BK_NSQ, args.done, pr, nullptr, 0, args.seed, args.game0 + (uint32_t)b,
-                                          args.mode, args.max_turn, args.moves_out + (size_t)k * args.B + b, planes, F_ROWS);
+                            if (stamps && threadIdx.x == 0) stamps[0] = clock64();
+                            bk_resident_move(sy, sc, res, 32 * sub + lane, my_lib, pr, args.seed, args.game0 + (uint32_t)gb, args.mode,
+                                             args.max_turn, args.moves_out + (size_t)k * args.B + gb, last_move ? nullptr : planes, F_ROWS,
+                                             bi == 0 ? stamps : nullptr);
+                            if (stamps && threadIdx.x == 0) stamps[7] = clock64();
                             sy.sync();                    // the trio is done with the scratch: zero it again
                             uint4 *z = reinterpret_cast<uint4 *>(&sc);
                             for (int i = 32 * sub + lane; i < STEP_SCRATCH / 16; i += 96) z[i] = make_uint4(0u, 0u, 0u, 0u);
+                            if (last_move)                // the playout ends here: the position goes back to global memory
+                                bk_resident_store(res, 32 * sub + lane, my_lib, gb, args.boards + (size_t)gb * BK_NSQ, args.ko, args.last,
+                                                  args.turn, args.libs + (size_t)gb * BK_NSQ, args.done);
                         }
                         fence_proxy_async();              // planes and zeroed scratch are visible to the tensor core
                         named_bar_sync(1, N_EPI_WARPS * 32);
                         if (!last_move && threadIdx.x == 0) mbar_arrive(sBar + 8 * BAR_FFULL);   // planes of move k + 1 are in place
+                        if (stamps && threadIdx.x == 0) stamps[8] = clock64();
                     }
                 }
             }
@@ -1133,26 +1188,47 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
+static int playout_impl(int8_t *boards, int16_t *ko, int16_t *last, int16_t *turn, uint8_t *libs, uint8_t *done,
+                        const void *blob_even, const void *blob_odd, uint64_t seed, uint32_t game0, int mode, int max_turn,
+                        int first_turn, int n_steps, int fresh_libs, int16_t *moves_out, int B, cudaStream_t stream, long long *prof);
+
 // Whole playouts in ONE launch (see the PLAYOUT note at the top): B boards, n_steps moves each.
 extern "C" int bk_playout_run(int8_t *boards, int16_t *ko, int16_t *last, int16_t *turn, uint8_t *libs, uint8_t *done,
-                              const void *feats_conv, const void *blob_even, const void *blob_odd, uint64_t seed, uint32_t game0,
-                              int mode, int max_turn, int first_turn, int n_steps, int16_t *moves_out, int B, cudaStream_t stream)
+                              const void *blob_even, const void *blob_odd, uint64_t seed, uint32_t game0, int mode, int max_turn,
+                              int first_turn, int n_steps, int fresh_libs, int16_t *moves_out, int B, cudaStream_t stream)
+{
+    return playout_impl(boards, ko, last, turn, libs, done, blob_even, blob_odd, seed, game0, mode, max_turn, first_turn, n_steps,
+                        fresh_libs, moves_out, B, stream, nullptr);
+}
+
+// diagnostics: prof = room for 32 moves x 16 clock64 stamps of CTA 0's first item (tools/prof_playout.py)
+extern "C" int bk_playout_run_debug(int8_t *boards, int16_t *ko, int16_t *last, int16_t *turn, uint8_t *libs, uint8_t *done,
+                                    const void *blob_even, const void *blob_odd, uint64_t seed, uint32_t game0, int mode,
+                                    int max_turn, int first_turn, int n_steps, int fresh_libs, int16_t *moves_out, int B,
+                                    cudaStream_t stream, long long *prof)
+{
+    return playout_impl(boards, ko, last, turn, libs, done, blob_even, blob_odd, seed, game0, mode, max_turn, first_turn, n_steps,
+                        fresh_libs, moves_out, B, stream, prof);
+}
+
+static int playout_impl(int8_t *boards, int16_t *ko, int16_t *last, int16_t *turn, uint8_t *libs, uint8_t *done,
+                        const void *blob_even, const void *blob_odd, uint64_t seed, uint32_t game0, int mode, int max_turn,
+                        int first_turn, int n_steps, int fresh_libs, int16_t *moves_out, int B, cudaStream_t stream, long long *prof)
 {
     if (B <= 0 || n_steps <= 0) return 0;
-    if (!boards || !ko || !last || !turn || !libs || !done || !feats_conv || !blob_even || !moves_out) return -1;
+    if (!boards || !ko || !last || !turn || !libs || !done || !blob_even || !moves_out) return -1;
     if (mode != 0 && mode != 1) return -1;
     FwdArgs a;
     memset(&a, 0, sizeof(a));
-    a.feats = static_cast<const uint8_t *>(feats_conv);
     a.blob[0] = static_cast<const uint8_t *>(blob_even);
     a.blob[1] = static_cast<const uint8_t *>(blob_odd ? blob_odd : blob_even);
     a.B = B; a.G = (B + BK_GROUP - 1) / BK_GROUP;
     a.n_nets = 1; a.first_net = 0;
-    a.g_whole = a.G; a.split = 1; a.n_sub = a.G;           // whole groups only: an item keeps its boards for the whole game
-    a.n_pairs = (a.n_sub + 1) / 2;
     a.dump_pass = -1;
+    a.prof = prof;
     a.boards = boards; a.ko = ko; a.last = last; a.turn = turn; a.libs = libs; a.done = done; a.moves_out = moves_out;
     a.n_steps = n_steps; a.mode = mode; a.max_turn = max_turn; a.first_turn = first_turn; a.seed = seed; a.game0 = game0;
+    a.fresh_libs = fresh_libs;
     const int slot = bk_current_device_slot();
     if (slot < 0) return -2;
     std::lock_guard<std::mutex> lock(g_fwd_mutex);
@@ -1171,7 +1247,17 @@ extern "C" int bk_playout_run(int8_t *boards, int16_t *ko, int16_t *last, int16_
         if (e != cudaSuccess || n_sm < 2) return -3;
         ds.n_sm = n_sm;
     }
+    // Boards per item: an item keeps its boards for the whole playout, so the playout's duration is (moves) x (time of one
+    // item's policy evaluation), and that grows with the item's M tiles.  Take the smallest item size that still gives every
+    // board an SM in ONE round (512 boards on 148 SMs: 4 boards -- layer 0 then fits one pass); with more boards than
+    // 5 x SMs the items are full groups of 5 (best throughput per board) and the CTAs play several items one after the other.
     const int n_clusters = ds.n_sm / 2;
+    int grp = (B + 2 * n_clusters - 1) / (2 * n_clusters);
+    if (grp > BK_GROUP) grp = BK_GROUP;
+    a.play_group = grp;
+    a.n_sub = (B + grp - 1) / grp;
+    a.g_whole = a.n_sub; a.split = 1;
+    a.n_pairs = (a.n_sub + 1) / 2;
     const int grid = 2 * (a.n_pairs < n_clusters ? a.n_pairs : n_clusters);
     CUtensorMap map[2], bias_map[2];
     for (int i = 0; i < 2; ++i) {

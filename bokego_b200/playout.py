@@ -1,9 +1,9 @@
 """Whole playouts and self-play games on the device, sharded over ranks (SURVEY 8b `playout_batch`, 8e).
 
-Whole playouts are ONE kernel launch (bk_playout_run, `persistent=True`, the default): the conv kernel keeps each group of five
-boards on its SM for the whole game -- policy forward, then sample / play / capture / re-encode by three warps per board
-straight into the shared-memory operand of the next move -- after one bk_encode of the starting positions and before one
-bk_score.  The launch-per-move form (`persistent=False`) does the same with two launches per move, boards resident in HBM:
+Whole playouts are ONE kernel launch (bk_playout_run, `persistent=True`; the default while every board gets an SM in one round): the conv kernel keeps each item of up to
+five boards on its SM for the whole game, positions resident on chip -- three warps per board encode the starting position,
+and after every policy forward they sample / play / capture / re-encode straight into the shared-memory operand of the next
+move -- followed by one bk_score.  The launch-per-move form (`persistent=False`) does the same with two launches per move, boards resident in HBM:
     bk_forward (policy only)  ->  bk_playout_step_encode (sample, play, capture, re-encode the new position in place)
 and is what a net in training uses (reinforce.PolicyTrainer records planes and statistics move by move).  Both give the same
 games, bit for bit.  It is exactly the loop of the reference's `MCTS._simulate` (/root/reference/bokego/mcts.py:195-206: `find_random_child`
@@ -58,6 +58,15 @@ def record_to_sgf(record, out_path, **kwargs):
     return go.write_sgf(moves, out_path, **kwargs)
 
 
+def persistent_pays(B, device):
+    """The persistent playout kernel keeps an item of boards on its SM for the whole game, so its step phase (sample, play,
+    re-encode: ~10 us per move) is serial with that item's policy evaluation, while the launch-per-move loop amortises one
+    stepping launch over all rounds of the grid.  Measured (profiles/r02f_playout_per_move.jsonl): the kernel wins while every
+    board gets an SM in ONE round (512 boards: 90 us per move against 103), and loses by ~5 % beyond (1,024 / 4,096 boards)."""
+    n_sm = torch.cuda.get_device_properties(device).multi_processor_count
+    return B <= 5 * n_sm
+
+
 def n_steps_for(mode, max_turn, first_turn=0):
     """number of move steps after which every board of the batch is finished"""
     last = max_turn + (1 if mode == MODE_MCTS else 2)
@@ -65,7 +74,7 @@ def n_steps_for(mode, max_turn, first_turn=0):
 
 
 def run_playouts(pos, policy, mode=MODE_MCTS, max_turn=None, seed=0, game0=0, policy_odd=None, n_steps=None,
-                 first_turn=0, komi=5.5, graph=True, persistent=True):
+                 first_turn=0, komi=5.5, graph=True, persistent=None):
     """Play every board of `pos` to the end with moves drawn from the policy net(s).
 
     policy:     PackedNet used for every move, or for the moves made at even `turn` when policy_odd is given
@@ -74,7 +83,8 @@ def run_playouts(pos, policy, mode=MODE_MCTS, max_turn=None, seed=0, game0=0, po
                 `first_turn` states it)
     mode:       MODE_MCTS (Go_MCTS.find_random_child, mcts.py:319-364) or MODE_SELFPLAY (legal_sample, selfplay.py:35-47)
     persistent: all moves in one launch of the persistent playout kernel (ignored when a net is being trained);
-                otherwise two launches per move, replayed from a CUDA graph when `graph`
+                otherwise two launches per move, replayed from a CUDA graph when `graph`; None = whichever is faster at this
+                batch size (persistent_pays)
     Updates `pos` in place (pos.libs is allocated when absent: the first encode then takes exact liberties, like a fresh
     Game) and returns a PlayoutResult.  Stream-ordered; does not synchronise.
     """
@@ -92,10 +102,11 @@ def run_playouts(pos, policy, mode=MODE_MCTS, max_turn=None, seed=0, game0=0, po
     probs = torch.empty(B, 81, dtype=torch.float32, device=dev)
 
     training = any(hasattr(n, "play_probs") for n in (policy, policy_odd) if n is not None)
+    if persistent is None:
+        persistent = persistent_pays(B, dev)
     if persistent and not training and n_steps > 0:
-        features_batch(pos, fresh_libs=fresh_first, want=("conv", "libs"), out=bufs)
-        playout_run(pos, bufs["conv"], policy, n_steps, mode, max_turn, seed=seed, game0=game0, policy_odd=policy_odd,
-                    first_turn=first_turn, moves_out=moves)
+        playout_run(pos, policy, n_steps, mode, max_turn, seed=seed, game0=game0, policy_odd=policy_odd, first_turn=first_turn,
+                    fresh_libs=fresh_first, moves_out=moves)
         score, reward = score_batch(pos.boards, komi)
         return PlayoutResult(moves.t().contiguous(), pos.turn.clone(), score, reward)
     encoded = [False]      # bufs["conv"] holds the planes of the current positions (written by the previous move's launch)
@@ -145,8 +156,11 @@ class PlayoutGraph:
     the form used when the same batch of games is played repeatedly (benchmarks, fixed-size self-play workers).
     Seed and first game id are kernel arguments and therefore fixed at capture."""
 
-    def __init__(self, B, device, policy, mode, max_turn=None, seed=0, game0=0, policy_odd=None, komi=5.5, persistent=True):
+    def __init__(self, B, device, policy, mode, max_turn=None, seed=0, game0=0, policy_odd=None, komi=5.5, persistent=None):
         dev = _lib.require_device(device)
+        if persistent is None:
+            persistent = persistent_pays(B, dev)
+        self.persistent = persistent
         if max_turn is None:
             max_turn = MCTS_MAX_TURN if mode == MODE_MCTS else SELFPLAY_MAX_TURN
         self.pos = Positions.empty(B, dev)
@@ -161,11 +175,11 @@ class PlayoutGraph:
 
         def body():
             pos.boards.zero_(); pos.ko.fill_(-1); pos.last.fill_(-2); pos.turn.zero_(); pos.done.zero_()
-            features_batch(pos, fresh_libs=True, want=("conv", "libs"), out=bufs)
             if persistent:
-                playout_run(pos, bufs["conv"], policy, self.n_steps, mode, max_turn, seed=seed, game0=game0, policy_odd=policy_odd,
+                playout_run(pos, policy, self.n_steps, mode, max_turn, seed=seed, game0=game0, policy_odd=policy_odd, fresh_libs=True,
                             moves_out=self.moves)
             else:
+                features_batch(pos, fresh_libs=True, want=("conv", "libs"), out=bufs)
                 for k in range(self.n_steps):
                     net = policy if (policy_odd is None or k % 2 == 0) else policy_odd
                     policy_value_batch(bufs["conv"], B, net, None, want_logits=False, probs_out=probs)
@@ -175,7 +189,7 @@ class PlayoutGraph:
         # one eager step first: the library sets its kernel attributes on first use, which must not happen under capture
         features_batch(pos, fresh_libs=True, want=("conv", "libs"), out=bufs)
         policy_value_batch(bufs["conv"], B, policy, None, want_logits=False, probs_out=probs)
-        self.launches = 5 + 1 + (1 if persistent else 2 * self.n_steps) + 1
+        self.launches = 5 + (1 if persistent else 1 + 2 * self.n_steps) + 1
         self.graph = torch.cuda.CUDAGraph()
         cap = torch.cuda.Stream(device=dev)
         cap.wait_stream(torch.cuda.current_stream(dev))

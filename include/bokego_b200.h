@@ -97,15 +97,18 @@ int bk_playout_step(int8_t *boards, int16_t *ko, int16_t *last, int16_t *turn, u
 int bk_playout_step_encode(int8_t *boards, int16_t *ko, int16_t *last, int16_t *turn, uint8_t *libs, uint8_t *done,
                            const float *probs, const float *q_inj, int q_vecs, uint64_t seed, uint32_t game0, int mode,
                            int max_turn, int16_t *moves_out, void *feats_conv, int B, void *stream);
-/* Whole playouts in ONE launch: the conv kernel keeps every group of 5 boards on its SM for n_steps moves -- policy forward
- * (blob_even for the moves made at even first_turn + k, blob_odd for the odd ones; blob_odd NULL = one net), then sample / play /
- * capture / re-encode by three warps per board straight into the shared-memory operand of the next move (the loop of
- * MCTS._simulate, mcts.py:195-206, and of selfplay.playout, bin/selfplay.py:18-33).  feats_conv = bk_encode of the starting
- * positions (libs must hold their liberty cache); boards / ko / last / turn / libs / done are updated in place exactly as n_steps
- * calls of bk_playout_step_encode would; moves_out int16 [n_steps][B].  Random stream: (seed, game0 + b, turn, try). */
+/* Whole playouts in ONE launch: the conv kernel keeps every item of <= 5 boards on its SM for n_steps moves.  Three warps per
+ * board hold the position in shared memory and registers: they encode the starting position (nnet.features; fresh_libs != 0:
+ * exact liberties like a fresh Game, else the carried cache in `libs`), and after every policy forward (blob_even for the moves
+ * made at even first_turn + k, blob_odd for the odd ones; blob_odd NULL = one net) they sample, play, capture, refresh the cache
+ * and write the planes of the new position straight into the shared-memory operand of the next move -- the loop of
+ * MCTS._simulate (mcts.py:195-206) and of selfplay.playout (bin/selfplay.py:18-33) without a launch, a grid-wide dependency or
+ * an HBM round trip between the moves.  boards / ko / last / turn / libs / done are read once and written once, and end exactly as
+ * after n_steps calls of bk_playout_step_encode; moves_out int16 [n_steps][B].  Random stream: (seed, game0 + b, turn, try).
+ * The item size adapts to B: the smallest that gives every board an SM in one round (a playout lasts as long as one item). */
 int bk_playout_run(int8_t *boards, int16_t *ko, int16_t *last, int16_t *turn, uint8_t *libs, uint8_t *done,
-                   const void *feats_conv, const void *blob_even, const void *blob_odd, uint64_t seed, uint32_t game0, int mode,
-                   int max_turn, int first_turn, int n_steps, int16_t *moves_out, int B, void *stream);
+                   const void *blob_even, const void *blob_odd, uint64_t seed, uint32_t game0, int mode, int max_turn,
+                   int first_turn, int n_steps, int fresh_libs, int16_t *moves_out, int B, void *stream);
 /* Go_MCTS.make_move (bokego/mcts.py:340-346) for C children: child c = copy of parent parent_idx[c] (an index into the
  * parent arrays) with moves[c] played by Game.play_move (go.py:123-182; -1 = play_pass go.py:109-121).  The lazy liberty
  * cache is refreshed on the parent position before the move (go.py:160) and handed to the child; libs == NULL means the

@@ -179,12 +179,13 @@ def test_simulate_65536_boards_subset_vs_oracle(env):
 
 
 @pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("B", [1, 7, 203, 745, 1485])
+@pytest.mark.parametrize("B", [1, 7, 203, 512, 745, 1485])
 def test_persistent_playout_kernel_equals_launch_per_move(env, mode, B):
     """bk_playout_run (whole games inside one launch of the conv kernel: policy forward, then three warps per board sample,
     play and re-encode into the shared-memory operand of the next move) against the launch-per-move loop: every move, the
-    final boards / ko / last / turn / liberty caches / done flags, scores and rewards must be identical.  B = 7 and 203 end in a
-    partial group, 745 in a CTA pair whose second CTA has no boards, 1485 needs more than one round of the 74 CTA pairs."""
+    final boards / ko / last / turn / liberty caches / done flags, scores and rewards must be identical.  The item size adapts
+    to B (1 board per item up to 148 boards, 2 at 203, 4 at 512, 5 from 741 on); 745 ends in a CTA pair whose second CTA has no
+    boards, 1485 needs more than one round of the 74 CTA pairs."""
     bk, po, dev, p17, p19 = env
     odd = p19 if mode == 1 else None
     a_pos, b_pos = bk.Positions.empty(B, dev, track_libs=False), bk.Positions.empty(B, dev, track_libs=False)
@@ -224,3 +225,24 @@ def test_persistent_playout_from_midgame_positions_and_repeats(env):
             want = got
         for x, y in zip(got, want):
             assert torch.equal(x, y), rep
+
+
+@pytest.mark.parametrize("n_steps", [1, 10])
+def test_persistent_playout_stopped_early_leaves_the_same_state(env, n_steps):
+    """a run that stops before the games are over: positions, liberty caches and done flags equal the launch-per-move loop's, so
+    either engine can continue from the other's state"""
+    bk, po, dev, p17, p19 = env
+    B = 300
+    a_pos, b_pos = bk.Positions.empty(B, dev, track_libs=False), bk.Positions.empty(B, dev, track_libs=False)
+    a = po.run_playouts(a_pos, p17, bk.MODE_SELFPLAY, seed=2, game0=0, policy_odd=p19, n_steps=n_steps, persistent=True)
+    b = po.run_playouts(b_pos, p17, bk.MODE_SELFPLAY, seed=2, game0=0, policy_odd=p19, n_steps=n_steps, persistent=False, graph=False)
+    assert torch.equal(a.moves, b.moves) and not bool(a_pos.done.any())
+    for x, y in ((a_pos.boards, b_pos.boards), (a_pos.ko, b_pos.ko), (a_pos.last, b_pos.last), (a_pos.turn, b_pos.turn),
+                 (a_pos.done, b_pos.done), (a_pos.libs, b_pos.libs)):
+        assert torch.equal(x, y)
+    # ... and continue crosswise to the end
+    a2 = po.run_playouts(a_pos, p17, bk.MODE_SELFPLAY, seed=2, game0=0, policy_odd=p19, first_turn=n_steps,
+                         n_steps=po.n_steps_for(bk.MODE_SELFPLAY, 70, n_steps), persistent=False, graph=False)
+    b2 = po.run_playouts(b_pos, p17, bk.MODE_SELFPLAY, seed=2, game0=0, policy_odd=p19, first_turn=n_steps,
+                         n_steps=po.n_steps_for(bk.MODE_SELFPLAY, 70, n_steps), persistent=True)
+    assert torch.equal(a2.moves, b2.moves) and torch.equal(a_pos.boards, b_pos.boards) and torch.equal(a2.score, b2.score)
