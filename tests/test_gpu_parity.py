@@ -379,3 +379,40 @@ def test_playout_steps_vs_oracle_random_stream(bk, dev, mode, sd17):
         if done.all():
             break
     assert done.all()
+
+
+def test_entry_points_are_reentrant_across_host_threads(bk, dev, positions, nets_golden, sd17, sd19, sd_value):
+    """the C ABI keeps its launch state per device behind a mutex (include/bokego_b200.h, "Conventions"): four host threads,
+    each on its own stream and with its own nets (so the tensor-map cache is hit from all sides), evaluate concurrently -- ctypes
+    releases the GIL during the calls -- and every result equals the single-threaded one bit for bit"""
+    import threading
+    conv, B = _forward_inputs(bk, dev, positions, nets_golden)
+    nets = [bk.PackedNet(sd17, dev), bk.PackedNet(sd19, dev), bk.PackedNet(sd_value, dev), bk.PackedNet(sd17, dev)]
+    want = []
+    for i in range(4):
+        pol, val = nets[i], nets[2]
+        l, p, v = bk.policy_value_batch(conv, B, pol if not pol.is_value else nets[0], val)
+        want.append((l.clone(), v.clone()))
+    torch.cuda.synchronize()
+    errors = []
+
+    def work(i):
+        try:
+            torch.cuda.set_device(dev)
+            st = torch.cuda.Stream(device=dev)
+            pol = nets[i] if not nets[i].is_value else nets[0]
+            with torch.cuda.stream(st):
+                for _ in range(200):
+                    l, p, v = bk.policy_value_batch(conv, B, pol, nets[2])
+                st.synchronize()
+            if not (torch.equal(l, want[i][0]) and torch.equal(v, want[i][1])):
+                errors.append(f"thread {i}: result differs")
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"thread {i}: {e!r}")
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
