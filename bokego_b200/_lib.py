@@ -57,6 +57,8 @@ def _sig(L):
     L.bk_tree_finish.argtypes = [vp] * 5 + [i32, i32, i32, vp, vp, i32]
     L.bk_score.restype = i32
     L.bk_score.argtypes = [vp, f32, vp, vp, i32, vp]
+    L.bk_pack_records.restype = i32
+    L.bk_pack_records.argtypes = [vp] * 5 + [i32, i32, vp]
     L.bk_exp_draws.restype = i32
     L.bk_exp_draws.argtypes = [u64, u32, u32, u32, vp, i32, vp]
     L.bk_train_param_count.restype = C.c_size_t

@@ -362,6 +362,27 @@ def score_batch(boards, komi=5.5, out=None):
     return score, reward
 
 
+def pack_records(moves_tb, turn, score, reward, out=None):
+    """per-game records int16 [B, T + 3] = (turn reached, reward, 2 * score, moves...) from the move log int16 [T, B] of a playout
+    loop, in one launch (the rows of the one result gather of a multi-GPU run)"""
+    L = _lib.lib()
+    dev = _lib.require_device(moves_tb.device)
+    T, B = moves_tb.shape
+    _want(moves_tb, torch.int16, (T, B), "moves_tb", dev)
+    _want(turn, torch.int16, (B,), "turn", dev)
+    _want(score, torch.float32, (B,), "score", dev)
+    _want(reward, torch.int8, (B,), "reward", dev)
+    if out is None:
+        out = torch.empty(B, T + 3, dtype=torch.int16, device=dev)
+    _want(out, torch.int16, (B, T + 3), "out", dev)
+    with torch.cuda.device(dev):
+        rc = L.bk_pack_records(_lib.ptr(moves_tb), _lib.ptr(turn), _lib.ptr(score), _lib.ptr(reward), _lib.ptr(out), T, B,
+                               _lib.stream_ptr(dev))
+    _lib.check(rc, "bk_pack_records")
+    _lib.count_launch()
+    return out
+
+
 def exp_draws(seed, game0, move, tr, B, device):
     """The counter-based Exp(1) stream as the kernels see it: float32 [B,81]."""
     L = _lib.lib()

@@ -108,6 +108,24 @@ bk_make_moves_kernel(const int8_t *__restrict__ boards, const int16_t *__restric
     }
 }
 
+// per-game records of a finished batch of playouts: rec int16 [B][T + 3] = { turn reached, reward, 2 * score, move 0 .. T-1 }
+// from the move log int16 [T][B] of the playout loop (bokego_b200/playout.py: the rows that cross ranks in the result gather)
+__global__ void bk_pack_records_kernel(const int16_t *__restrict__ moves, const int16_t *__restrict__ turn,
+                                       const float *__restrict__ score, const int8_t *__restrict__ reward,
+                                       int16_t *__restrict__ rec, int T, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int W = T + 3;
+    if (i >= B * W) return;
+    const int b = i / W, c = i - b * W;
+    int16_t v;
+    if (c == 0) v = turn[b];
+    else if (c == 1) v = (int16_t)reward[b];
+    else if (c == 2) v = (int16_t)__float2int_rn(score[b] * 2.0f);
+    else v = moves[(size_t)(c - 3) * B + b];
+    rec[i] = v;
+}
+
 __global__ void bk_exp_draws_kernel(uint64_t seed, uint32_t game0, uint32_t move, uint32_t tr, float *__restrict__ q, int B)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,5 +184,15 @@ extern "C" int bk_exp_draws(uint64_t seed, uint32_t game0, uint32_t move, uint32
     if (B <= 0) return 0;
     const int n = B * BK_NSQ;
     bk_exp_draws_kernel<<<(n + 255) / 256, 256, 0, stream>>>(seed, game0, move, tr, q, B);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+extern "C" int bk_pack_records(const int16_t *moves, const int16_t *turn, const float *score, const int8_t *reward,
+                               int16_t *rec, int T, int B, cudaStream_t stream)
+{
+    if (B <= 0) return 0;
+    if (!moves || !turn || !score || !reward || !rec || T < 0) return -1;
+    const int n = B * (T + 3);
+    bk_pack_records_kernel<<<(n + 255) / 256, 256, 0, stream>>>(moves, turn, score, reward, rec, T, B);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

@@ -17,8 +17,8 @@ keyed by the GLOBAL id, so results do not depend on R.  The only communication i
 import torch
 
 from . import _lib
-from .batched import (MODE_MCTS, MODE_SELFPLAY, Positions, features_batch, playout_run, playout_step, policy_value_batch,
-                      score_batch)
+from .batched import (MODE_MCTS, MODE_SELFPLAY, Positions, features_batch, pack_records, playout_run, playout_step,
+                      policy_value_batch, score_batch)
 
 MCTS_MAX_TURN = 80        # mcts.py:13  (terminal iff turn > 80 or the move was PASS, mcts.py:362-364)
 SELFPLAY_MAX_TURN = 70    # bin/selfplay.py:16 (checked every two moves => 72 moves, selfplay.py:21-33)
@@ -37,11 +37,16 @@ class PlayoutResult:
     """moves int16 [B, T] (BK_MOVE_* codes once a board is finished), n_moves int16 [B] (turn reached),
     score float32 [B] (Game.score()), reward int8 [B] (+1 black wins, -1 otherwise)"""
 
-    def __init__(self, moves, n_moves, score, reward):
+    def __init__(self, moves, n_moves, score, reward, records=None):
         self.moves, self.n_moves, self.score, self.reward = moves, n_moves, score, reward
+        self._records = records
 
     def records(self):
         """fixed-size per-game records int16 [B, T + 3]: n_moves, reward, 2*score, moves..."""
+        if self._records is not None:
+            return self._records
+        if self.moves.is_cuda:      # one launch (bk_pack_records) from the [T, B] move log
+            return pack_records(self.moves.t().contiguous(), self.n_moves.to(torch.int16).contiguous(), self.score, self.reward)
         head = torch.stack([self.n_moves.to(torch.int16), self.reward.to(torch.int16),
                             torch.round(self.score * 2).to(torch.int16)], dim=1)
         return torch.cat([head, self.moves], dim=1).contiguous()
@@ -172,6 +177,7 @@ class PlayoutGraph:
         probs = torch.empty(B, 81, dtype=torch.float32, device=dev)
         self.score = torch.empty(B, dtype=torch.float32, device=dev)
         self.reward = torch.empty(B, dtype=torch.int8, device=dev)
+        self.rec = torch.empty(B, self.n_steps + 3, dtype=torch.int16, device=dev)
 
         def body():
             pos.boards.zero_(); pos.ko.fill_(-1); pos.last.fill_(-2); pos.turn.zero_(); pos.done.zero_()
@@ -185,11 +191,12 @@ class PlayoutGraph:
                     policy_value_batch(bufs["conv"], B, net, None, want_logits=False, probs_out=probs)
                     playout_step(pos, probs, mode, max_turn, seed=seed, game0=game0, moves_out=self.moves[k], encode_into=bufs["conv"])
             score_batch(pos.boards, komi, out=(self.score, self.reward))
+            pack_records(self.moves, pos.turn, self.score, self.reward, out=self.rec)
 
         # one eager step first: the library sets its kernel attributes on first use, which must not happen under capture
         features_batch(pos, fresh_libs=True, want=("conv", "libs"), out=bufs)
         policy_value_batch(bufs["conv"], B, policy, None, want_logits=False, probs_out=probs)
-        self.launches = 5 + (1 if persistent else 1 + 2 * self.n_steps) + 1
+        self.launches = 5 + (1 if persistent else 1 + 2 * self.n_steps) + 2
         self.graph = torch.cuda.CUDAGraph()
         cap = torch.cuda.Stream(device=dev)
         cap.wait_stream(torch.cuda.current_stream(dev))
@@ -200,7 +207,7 @@ class PlayoutGraph:
 
     def replay(self):
         self.graph.replay()
-        return PlayoutResult(self.moves.t(), self.pos.turn, self.score, self.reward)
+        return PlayoutResult(self.moves.t(), self.pos.turn, self.score, self.reward, records=self.rec)
 
 
 def self_play(n_games, policy_black, policy_white, device, seed=0, rank=0, world=1, graph=True):
@@ -229,6 +236,11 @@ def gather_records(local, n_total, rank, world, group=None):
     import torch.distributed as dist
     sizes = [shard_range(n_total, r, world) for r in range(world)]
     width = local.shape[1]
+    if local.is_cuda and n_total % world == 0 and local.is_contiguous():
+        # equal shards on GPUs: ONE collective straight into the result (NCCL has no int16: the bytes travel as uint8)
+        out = torch.empty(n_total, width, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out.view(torch.uint8), local.view(torch.uint8), group=group)
+        return out
     most = max(hi - lo for lo, hi in sizes)
     pad = torch.zeros(most, width, dtype=torch.int32, device=local.device)   # int32 on the wire: gloo has no int16
     pad[: local.shape[0]] = local

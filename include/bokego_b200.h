@@ -119,6 +119,10 @@ int bk_make_moves(const int8_t *boards, const int16_t *ko, const int16_t *last, 
                   int16_t *turn_out, uint8_t *libs_out, uint8_t *status_out, int C, void *stream);
 /* Game.score (go.py:202-218) minus komi, and Go_MCTS.reward's +-1 (mcts.py:330-338) */
 int bk_score(const int8_t *boards, float komi, float *score_out, int8_t *reward_out, int B, void *stream);
+/* fixed-size result records of B finished playouts, the rows that cross ranks in the one gather of a multi-GPU run: rec int16
+ * [B][T + 3] = { turn reached, reward, 2 * score, move 0 .. T-1 } from the move log moves int16 [T][B] of the playout loop */
+int bk_pack_records(const int16_t *moves, const int16_t *turn, const float *score, const int8_t *reward, int16_t *rec, int T,
+                    int B, void *stream);
 /* the counter-based Exp(1) stream itself: q float32 [B][81] for (seed, game0 + b, move, try) */
 int bk_exp_draws(uint64_t seed, uint32_t game0, uint32_t move, uint32_t tr, float *q, int B, void *stream);
 

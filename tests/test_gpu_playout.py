@@ -25,6 +25,12 @@ def test_graph_replay_equals_stepwise(env, mode):
     b = po.run_playouts(bk.Positions.empty(B, dev, track_libs=False), p17, mode, seed=11, game0=5, policy_odd=odd, graph=False)
     torch.cuda.synchronize()
     assert torch.equal(a.records(), b.records())
+    # the record kernel (bk_pack_records) against the plain tensor formula
+    head = torch.stack([a.n_moves.to(torch.int16), a.reward.to(torch.int16), torch.round(a.score * 2).to(torch.int16)], dim=1)
+    assert torch.equal(a.records(), torch.cat([head, a.moves], dim=1))
+    g = po.PlayoutGraph(B, dev, p17, mode, seed=11, game0=5, policy_odd=odd).replay()
+    torch.cuda.synchronize()
+    assert torch.equal(g.records(), a.records())
     rec = a.records().cpu().numpy()
     if mode == 1:
         assert (rec[:, 0] == 72).all()                   # selfplay.py:21-33: always 72 moves
