@@ -37,6 +37,8 @@ def _sig(L):
     L.bk_repack_f32.argtypes = [vp, vp, i32, vp]
     L.bk_forward.restype = i32
     L.bk_forward.argtypes = [vp] * 6 + [i32, i32, vp]
+    L.bk_forward_positions.restype = i32
+    L.bk_forward_positions.argtypes = [vp] * 12 + [i32, i32, vp]
     L.bk_forward_debug.restype = i32
     L.bk_forward_debug.argtypes = [vp] * 6 + [i32, i32, vp, vp, i32, vp]
     L.bk_debug_words.restype = i32

@@ -73,13 +73,16 @@ constexpr int OFF_BAR = OFF_ONES + ONES_BYTES;     // barriers, 8 B each
 constexpr int OFF_TMEM = OFF_BAR + 192;
 constexpr int OFF_LOGIT = OFF_TMEM + 16;           // float[5][81]: head output per square
 constexpr int OFF_RES = OFF_LOGIT + 1664;          // PLAYOUT: resident positions of the item's boards (BkResident[5])
-constexpr int SMEM_BYTES = OFF_RES + 240;          // 232,256
+constexpr int SMEM_BYTES = OFF_RES + 240 + 128;    // 232,384 (ENCODE: logit area + resident area + tail = one group table, see below)
 static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KiB");
 // PLAYOUT: between the last layer of move k and layer 0 of move k + 1 the activation buffer is dead; the step phase keeps its
 // per-board scratch (group table, arg-max slots) at its start and zeroes it again (padding rows must read as zero)
 constexpr int STEP_SCRATCH = (int)((sizeof(BkStepScratch) + 15) / 16 * 16);
 static_assert(BK_GROUP * STEP_SCRATCH <= A_BYTES, "step scratch");
 static_assert(BK_GROUP * sizeof(BkResident) <= 240, "resident positions");
+// ENCODE: while the tensor pipe runs layers 1..5 of an item, three epilogue warps encode the boards of the NEXT item one at a time;
+// their group table lives in the logit area (written only by the last layer's epilogue) and the bytes behind it
+static_assert(sizeof(BKGroups) <= SMEM_BYTES - OFF_LOGIT, "encode scratch");
 static_assert(OFF_W % 128 == 0 && OFF_ONES % 128 == 0 && OFF_BIASW % 128 == 0, "operand alignment");
 
 // WFULL (leader): both CTAs' halves of a stage have landed -- each CTA's tensor-map copy (cta_group::2) reports its
@@ -292,6 +295,9 @@ struct FwdArgs {
     // (first_turn + k); moves_out is [n_steps][B]
     int8_t *boards; int16_t *ko, *last, *turn; uint8_t *libs, *done; int16_t *moves_out;
     int n_steps, mode, max_turn, first_turn;
+    // ENCODE only: positions in (boards / ko / last / turn above, libs = carried liberty cache or null for fresh Games), optional
+    // outputs of the encoder
+    uint8_t *legal_out, *libs_out;
     int play_group;            // boards per item (1..5): the smallest that puts every board on an SM in one round
     int fresh_libs;            // the starting positions have no liberty cache (exact liberties, like fresh Games)
     unsigned long long seed;
@@ -481,7 +487,10 @@ __device__ __forceinline__ void finish_board(const float *logit, int net, const 
 // ------------------------------------------------------------------------------------------------------
 // the tcgen05 kernel
 // ------------------------------------------------------------------------------------------------------
-template <bool PLAYOUT>
+// MODE 0: planes from global memory (bk_encode's operand, bulk copies); 1: PLAYOUT (whole games, positions resident on chip);
+// 2: ENCODE (planes from the positions: the epilogue warps run nnet.features for the NEXT item while the tensor pipe works on
+// the current one -- one launch from positions to probabilities and values)
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1)
 bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant__ CUtensorMap tm_policy,
                      const __grid_constant__ CUtensorMap tm_value, const __grid_constant__ CUtensorMap tb_policy,
@@ -494,6 +503,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
     float *logit = reinterpret_cast<float *>(smem + OFF_LOGIT);
     const int rank = (int)cluster_ctarank();           // 0 = leader (issues the pair's MMAs), 1 = peer
     const int pair0 = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    constexpr bool PLAYOUT = MODE == 1, ENCODE = MODE == 2;
     const int n_steps = PLAYOUT ? args.n_steps : 1;     // moves every item is kept for (1 = plain forward)
     if (threadIdx.x == 0 && args.dbg) g_dbg = args.dbg;
 
@@ -574,7 +584,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
             Item it, nx;
             int pair_nb, nx_nb;
             uint32_t n_femp = 0;    // FEMPTY phases consumed (one per item and move)
-            if (pair0 < args.n_pairs && decode_pair_t<PLAYOUT>(args, pair0, rank, it, pair_nb) && !PLAYOUT) load_feats(it);
+            if (pair0 < args.n_pairs && decode_pair_t<PLAYOUT>(args, pair0, rank, it, pair_nb) && MODE == 0) load_feats(it);
             for (int v = pair0; v < args.n_pairs; v += n_clusters) {
                 if (!decode_pair_t<PLAYOUT>(args, v, rank, it, pair_nb)) continue;
                 for (int k = 0; k < n_steps; ++k) {
@@ -589,7 +599,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     mbar_wait(sBar + 8 * BAR_FEMPTY, n_femp & 1u, 0x200u);
                     ++n_femp;
                     // (PLAYOUT: the planes never come from global memory -- the epilogue warps encode every position in place)
-                    if (!PLAYOUT && v + n_clusters < args.n_pairs && decode_pair(args, v + n_clusters, rank, nx, nx_nb)) load_feats(nx);
+                    if (MODE == 0 && v + n_clusters < args.n_pairs && decode_pair(args, v + n_clusters, rank, nx, nx_nb)) load_feats(nx);
                     for (int l = 2; l <= 6; ++l) stream(tm, tb, BK_W_L_OFF(l), n_stages_of(l));
                 }
             }
@@ -724,9 +734,43 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         bool first = true;
         Item it;
         int pair_nb;
+        // ENCODE: nnet.features of board j of item `e` into block j of the feature operand (and, for the first net's items, the
+        // encoder's other outputs), by the three warps `sub` = 0..2 on barrier `sy`, group table in `grp`
+        auto encode_board = [&](const Item &e, int j, BKGroups &grp, const BkSyncNamed &sy, int sub) {
+            const int b = e.g * BK_GROUP + e.lo + j;
+            const bool outs = e.net == args.first_net;
+            bk_encode_board(sy, grp, 32 * sub + lane, b, args.boards + (size_t)b * BK_NSQ, args.ko, args.last, args.turn,
+                            args.libs ? args.libs + (size_t)b * BK_NSQ : nullptr,
+                            reinterpret_cast<uint4 *>(smem + OFF_F) + F_MARGIN + BK_F_ROWS_B * j, F_ROWS,
+                            (outs && args.legal_out) ? args.legal_out + (size_t)b * BK_NSQ : nullptr,
+                            (outs && args.libs_out) ? args.libs_out + (size_t)b * BK_NSQ : nullptr);
+        };
+        if (ENCODE) {
+            // the planes of the CTA's first item: every board by its own three warps, tables in the (still unused) activation buffer
+            Item f;
+            int fnb;
+            if (pair0 < args.n_pairs && decode_pair(args, pair0, rank, f, fnb)) {
+                const int bi = warp / 3, sub = warp - 3 * bi;
+                if (bi < f.nb) {
+                    BkStepScratch &sc = *reinterpret_cast<BkStepScratch *>(smem + OFF_A + bi * STEP_SCRATCH);
+                    encode_board(f, bi, sc.grp, BkSyncNamed{2 + bi}, sub);
+                    uint4 *z = reinterpret_cast<uint4 *>(&sc);
+                    for (int i = 32 * sub + lane; i < STEP_SCRATCH / 16; i += 96) z[i] = make_uint4(0u, 0u, 0u, 0u);
+                }
+                fence_proxy_async();
+                named_bar_sync(1, N_EPI_WARPS * 32);
+                if (threadIdx.x == 0) mbar_arrive(sBar + 8 * BAR_FFULL);
+            }
+        }
         for (int v = pair0; v < args.n_pairs; v += n_clusters) {
             if (!decode_pair_t<PLAYOUT>(args, v, rank, it, pair_nb)) continue;
             const int np = n_passes(pair_nb);
+            // ENCODE: the item this CTA takes next; its boards are encoded by warps 0..2 at the top of the passes of layers 1..5
+            // (one board per pass): layer 0 has read the current planes by then, and the tensor pipe is busy for ~19 k cycles
+            Item nx;
+            int nx_nb = 0;
+            const bool have_next = ENCODE && v + n_clusters < args.n_pairs && decode_pair(args, v + n_clusters, rank, nx, nx_nb);
+            const int first_enc = pair_nb == BK_GROUP ? 2 : 1;
             // PLAYOUT: three warps per board (warp 15 idles) own one board of the item for the whole playout: its position is
             // resident in shared memory (BkResident) plus one register per thread (the liberty-cache entry of the thread's square)
             const int bi = warp / 3, sub = warp - 3 * bi;
@@ -754,6 +798,21 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                 const int net = PLAYOUT ? ((args.first_turn + k) & 1) : it.net;
                 const uint8_t *blob = args.blob[net];
                 const Pass pi = pass_info(pair_nb, ps);
+                // (warps 2, 3 and 6: schedulers 2 and 3 -- not the scheduler of the MMA-issuing warp 17 nor of the producer warp 16,
+                // whose instruction issue paces the tensor pipe)
+                const int enc_sub = warp == 2 ? 0 : (warp == 3 ? 1 : (warp == 6 ? 2 : -1));
+                if (ENCODE && have_next && enc_sub >= 0) {
+                    const int j = ps - first_enc, nj = nx.nb > 0 ? nx.nb : 1;
+                    if (j >= 0 && j < nj) {
+                        const BkSyncNamed sy{2};
+                        if (j < nx.nb) encode_board(nx, j, *reinterpret_cast<BKGroups *>(smem + OFF_LOGIT), sy, enc_sub);
+                        if (j == nj - 1) {                 // the next item's planes are complete (a CTA without boards just reports)
+                            fence_proxy_async();
+                            sy.sync();
+                            if (enc_sub == 0 && lane == 0) mbar_arrive(sBar + 8 * BAR_FFULL);
+                        }
+                    }
+                }
                 mbar_wait(sBar + 8 * BAR_ACC, pass & 1u, 0x600u + pass);
                 tc_fence_after();
                 const bool prof = !PLAYOUT && args.prof && blockIdx.x == 0 && pass < 64 && threadIdx.x == 0;
@@ -817,6 +876,8 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                                          args.probs ? args.probs + (size_t)b * 81 : nullptr,
                                          args.value ? args.value + b : nullptr, lane);
                         }
+                        // ENCODE: the logit area is the encode scratch of the next item's passes -- nobody may still be reading it
+                        if (ENCODE) named_bar_sync(1, N_EPI_WARPS * 32);
                     } else {
                         // ---- step phase: the board's three warps sample the move from the policy's probabilities, play it
                         // and write the planes of the new position into the feature operand of the next move.  The activation
@@ -1096,9 +1157,13 @@ extern "C" int bk_debug_words(unsigned int *out8)
     return g_dbg_host ? 0 : -1;
 }
 
+// positions for the ENCODE mode (planes computed inside the kernel); boards == nullptr: planes come from feats_conv
+struct FwdPositions {
+    const int8_t *boards; const int16_t *ko, *last, *turn; const uint8_t *libs_in; uint8_t *legal_out, *libs_out;
+};
 static int forward_impl(const void *feats_conv, const void *blob_policy, const void *blob_value, float *logits,
                         float *probs, float *value, int B, int flags, cudaStream_t stream, float *dump, int dump_pass,
-                        long long *prof);
+                        long long *prof, const FwdPositions *pos = nullptr);
 
 // diagnostics: dump = raw accumulators [640][128] of pass `dump_pass` of CTA 0's first item; prof = clock64 stamps of
 // CTA 0, four per pass {MMA issue start, MMA issue end, accumulators ready, epilogue done}, room for 64 passes
@@ -1115,15 +1180,37 @@ extern "C" int bk_forward(const void *feats_conv, const void *blob_policy, const
     return forward_impl(feats_conv, blob_policy, blob_value, logits, probs, value, B, flags, stream, nullptr, -1, nullptr);
 }
 
+// bk_forward_positions: nnet.features + both nets in ONE launch -- the ENCODE instantiation of the conv kernel computes the
+// planes of every item from the positions while the tensor pipe works on the item before (see MODE 2 at the kernel)
+extern "C" int bk_forward_positions(const int8_t *boards, const int16_t *ko, const int16_t *last, const int16_t *turn,
+                                    const uint8_t *libs_in, const void *blob_policy, const void *blob_value, float *logits,
+                                    float *probs, float *value, uint8_t *legal_out, uint8_t *libs_out, int B, int flags,
+                                    cudaStream_t stream)
+{
+    if (B <= 0) return 0;
+    if (!boards || !ko || !last || !turn || (flags & BK_FWD_SIMT)) return -1;
+    // with both nets every board is encoded twice (once per net, by different CTAs): an in-place cache update would let one of
+    // them read a half-updated cache
+    if (libs_out && libs_out == libs_in && (flags & BK_FWD_POLICY) && (flags & BK_FWD_VALUE)) return -1;
+    const FwdPositions pos = {boards, ko, last, turn, libs_in, legal_out, libs_out};
+    return forward_impl(nullptr, blob_policy, blob_value, logits, probs, value, B, flags, stream, nullptr, -1, nullptr, &pos);
+}
+
 static int forward_impl(const void *feats_conv, const void *blob_policy, const void *blob_value, float *logits,
                         float *probs, float *value, int B, int flags, cudaStream_t stream, float *dump, int dump_pass,
-                        long long *prof)
+                        long long *prof, const FwdPositions *pos)
 {
     if (B <= 0) return 0;
     const bool do_p = flags & BK_FWD_POLICY, do_v = flags & BK_FWD_VALUE;
     if (!do_p && !do_v) return -1;
-    if ((do_p && !blob_policy) || (do_v && (!blob_value || !value)) || !feats_conv) return -1;
+    if ((do_p && !blob_policy) || (do_v && (!blob_value || !value)) || (!feats_conv && !pos)) return -1;
     FwdArgs a;
+    memset(&a, 0, sizeof(a));
+    if (pos) {
+        a.boards = const_cast<int8_t *>(pos->boards); a.ko = const_cast<int16_t *>(pos->ko); a.last = const_cast<int16_t *>(pos->last);
+        a.turn = const_cast<int16_t *>(pos->turn); a.libs = const_cast<uint8_t *>(pos->libs_in);
+        a.legal_out = pos->legal_out; a.libs_out = pos->libs_out;
+    }
     a.feats = static_cast<const uint8_t *>(feats_conv);
     a.blob[0] = static_cast<const uint8_t *>(blob_policy);
     a.blob[1] = static_cast<const uint8_t *>(blob_value);
@@ -1156,9 +1243,11 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
         if (!ds.n_sm) {
             int n_sm = 0;
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, slot);
-            e = cudaFuncSetAttribute(bk_forward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+            e = cudaFuncSetAttribute(bk_forward_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
             if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(bk_forward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+                e = cudaFuncSetAttribute(bk_forward_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(bk_forward_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
             if (e != cudaSuccess || n_sm < 2) return -3;
             ds.n_sm = n_sm;
         }
@@ -1183,7 +1272,8 @@ static int forward_impl(const void *feats_conv, const void *blob_policy, const v
             const int rc = weight_maps(ds, a.blob[i], &map[i], &bias_map[i]);
             if (rc != 0) return rc;
         }
-        bk_forward_tc_kernel<false><<<grid, N_THREADS, SMEM_BYTES, stream>>>(a, map[0], map[1], bias_map[0], bias_map[1]);
+        if (pos) bk_forward_tc_kernel<2><<<grid, N_THREADS, SMEM_BYTES, stream>>>(a, map[0], map[1], bias_map[0], bias_map[1]);
+        else bk_forward_tc_kernel<0><<<grid, N_THREADS, SMEM_BYTES, stream>>>(a, map[0], map[1], bias_map[0], bias_map[1]);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
@@ -1241,9 +1331,11 @@ static int playout_impl(int8_t *boards, int16_t *ko, int16_t *last, int16_t *tur
     if (!ds.n_sm) {
         int n_sm = 0;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, slot);
-        cudaError_t e = cudaFuncSetAttribute(bk_forward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(bk_forward_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(bk_forward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+            e = cudaFuncSetAttribute(bk_forward_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(bk_forward_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess || n_sm < 2) return -3;
         ds.n_sm = n_sm;
     }
@@ -1264,6 +1356,6 @@ static int playout_impl(int8_t *boards, int16_t *ko, int16_t *last, int16_t *tur
         const int rc = weight_maps(ds, a.blob[i], &map[i], &bias_map[i]);
         if (rc != 0) return rc;
     }
-    bk_forward_tc_kernel<true><<<grid, N_THREADS, SMEM_BYTES, stream>>>(a, map[0], map[1], bias_map[0], bias_map[1]);
+    bk_forward_tc_kernel<1><<<grid, N_THREADS, SMEM_BYTES, stream>>>(a, map[0], map[1], bias_map[0], bias_map[1]);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

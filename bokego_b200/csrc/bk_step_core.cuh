@@ -234,6 +234,29 @@ __device__ __forceinline__ void bk_step_board(const Sync &sy, BkStepScratch &sc,
 #undef BK_STAMP
 }
 
+// nnet.features of ONE board by 96 threads (the body of bk_encode_kernel): group table into `grp`, then planes / legal moves /
+// refreshed liberty cache.  libs_in_row == null: a fresh Game (exact liberties).  Ends with a barrier: `grp` may be reused.
+template <class Sync>
+__device__ __forceinline__ void bk_encode_board(const Sync &sy, BKGroups &grp, int tid, int b, const int8_t *bd, const int16_t *ko_arr,
+                                                const int16_t *last_arr, const int16_t *turn_arr, const uint8_t *libs_in_row,
+                                                uint4 *planes, int chunk_stride, uint8_t *legal_row, uint8_t *libs_out_row)
+{
+    const int lane = tid & 31, p = tid;
+    const bool active = p < BK_NSQ;
+    const int ko = ko_arr[b], last = last_arr[b], turn = turn_arr[b];
+    BB black, white;
+    bk_load_boards(bd, lane, black, white);
+    const bool carried = libs_in_row != nullptr;
+    const bool stale = carried && last >= 0 && libs_in_row[last] == 0;
+    const int lib_c = (carried && active) ? (int)libs_in_row[p] : 0;
+    bk_groups_build(grp, black, white, p);
+    sy.sync();                               // table complete; every thread has read libs_in_row[last] (libs_out may alias libs_in)
+    if (active)
+        bk_encode_square(grp, black, white, (turn & 1) == 0, ko, last, carried, stale, lib_c, p, 0, planes, chunk_stride, nullptr,
+                         nullptr, legal_row, libs_out_row);
+    sy.sync();
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Resident form, for the persistent playout kernel: the position of a board lives in shared memory (bit-boards, ko / last /
 // turn / done, the liberty-cache entry of `last`) and in one register per thread (the liberty-cache entry of the thread's own

@@ -32,7 +32,7 @@ import numpy as np
 import torch
 
 from . import _lib, go
-from .batched import MODE_MCTS, NONE, PASS, Positions, features_batch, make_moves, policy_value_batch
+from .batched import MODE_MCTS, NONE, PASS, Positions, evaluate_positions, features_batch, make_moves, policy_value_batch  # noqa: F401
 
 MAX_TURNS = 80   # mcts.py:13
 
@@ -73,9 +73,8 @@ class MCTS:
 
     def _net_outputs(self, sub):
         """(probs float32 [n,81], value float64 [n], legal uint8 [n,81], libs uint8 tensor [n,81]) of the positions `sub`:
-        one encoder launch and one policy + value launch"""
-        out = features_batch(sub, want=("conv", "legal", "libs"))
-        _, probs, val = policy_value_batch(out["conv"], sub.B, self.policy, self.value, want_logits=False)
+        ONE launch (bk_forward_positions: planes on chip, policy + value)"""
+        _, probs, val, out = evaluate_positions(sub, self.policy, self.value, want=("legal", "libs"))
         val = np.zeros(sub.B) if val is None else val.double().cpu().numpy()
         return probs.cpu().numpy(), val, out["legal"].cpu().numpy(), out["libs"]
 

@@ -80,6 +80,16 @@ int bk_weights_pack(const float *w0, const float *w16, const float *bias, const 
 int bk_forward(const void *feats_conv, const void *blob_policy, const void *blob_value, float *logits,
                float *probs, float *value, int B, int flags, void *stream);
 
+/* bk_encode + bk_forward in ONE launch: positions in, probabilities / values out.  The conv kernel computes the planes of every
+ * item itself -- three of its epilogue warps run nnet.features (nnet.py:182-262) for the boards of the NEXT item, straight into
+ * the shared-memory operand of layer 0, while the tensor pipe works on the current item -- so the planes never exist in global
+ * memory and no encoder launch precedes the nets.  libs_in == NULL: fresh Games (exact liberties), else the carried Game._libs.
+ * legal_out / libs_out (may be NULL) as in bk_encode, except that libs_out may alias libs_in only when ONE net is evaluated
+ * (with both, every board is encoded once per net); the other arguments as in bk_forward (BK_FLAG_SIMT is not available here).  Results are bit-identical to bk_encode followed by bk_forward. */
+int bk_forward_positions(const int8_t *boards, const int16_t *ko, const int16_t *last, const int16_t *turn,
+                         const uint8_t *libs_in, const void *blob_policy, const void *blob_value, float *logits, float *probs,
+                         float *value, uint8_t *legal_out, uint8_t *libs_out, int B, int flags, void *stream);
+
 /* ---- (c) playout stepping ------------------------------------------------------------------------
  * mode 0: Go_MCTS.get_move + make_move + is_game_over (bokego/mcts.py:340-364)
  * mode 1: legal_sample + playout loop (bin/selfplay.py:18-47)

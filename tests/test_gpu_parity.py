@@ -416,3 +416,32 @@ def test_entry_points_are_reentrant_across_host_threads(bk, dev, positions, nets
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("n", [1, 4, 5, 7, 123, 741, 1480, 4096])
+def test_forward_from_positions_equals_encode_then_forward(bk, dev, positions, sd17, sd_value, n):
+    """bk_forward_positions (the conv kernel encodes the planes of every item on chip, the next item's while the tensor pipe
+    works on the current one) against bk_encode followed by bk_forward: logits, probabilities, values, legal moves and the
+    refreshed liberty cache must be identical bit for bit -- fresh positions and positions with a carried cache, both nets,
+    one net, ragged sizes, sizes with a split tail"""
+    p = positions
+    idx = np.arange(n) % len(p["board"])
+    pol, val = bk.PackedNet(sd17, dev), bk.PackedNet(sd_value, dev)
+    for carried in (False, True):
+        libs = p["libs_in"][idx] if carried else None
+        if carried:
+            idx = idx[p["fresh"][idx] == 0] if (p["fresh"][idx] == 0).any() else idx
+            libs = p["libs_in"][idx]
+        m = len(idx)
+        a = bk.Positions.from_numpy(p["board"][idx], p["ko"][idx], p["last"][idx], p["turn"][idx], dev, libs)
+        b = bk.Positions.from_numpy(p["board"][idx], p["ko"][idx], p["last"][idx], p["turn"][idx], dev, libs)
+        fa = bk.features_batch(a, want=("conv", "legal", "libs"))
+        l0, p0, v0 = bk.policy_value_batch(fa["conv"], m, pol, val)
+        l1, p1, v1, fb = bk.evaluate_positions(b, pol, val, want_logits=True, want=("legal", "libs"))
+        torch.cuda.synchronize()
+        assert torch.equal(l0, l1) and torch.equal(p0, p1) and torch.equal(v0, v1), (n, carried)
+        assert torch.equal(fa["legal"], fb["legal"]) and torch.equal(fa["libs"], fb["libs"]), (n, carried)
+        assert torch.equal(a.libs, b.libs)
+        _, p2, none_v, _ = bk.evaluate_positions(b, pol, None, fresh_libs=not carried)
+        none_l, none_p, v2, _ = bk.evaluate_positions(b, None, val, fresh_libs=not carried)
+        assert none_v is None and none_l is None and none_p is None and torch.equal(p2, p0) and torch.equal(v2, v0)

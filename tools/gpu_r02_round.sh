@@ -12,7 +12,7 @@ timeout 600 python tools/stress_forward.py --iters 2000 > gpurun_out/r02_stress_
 # ncu: launch list of the bench's timed step, then full captures (each after the same command has exited 0 without ncu)
 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu --no-playouts --no-train > gpurun_out/r02_plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-playouts --no-train > gpurun_out/r02_ncu_list.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:bk_forward_tc -s 3 -c 2 -o gpurun_out/prof_fwd python bench.py --steps 3 --warmup 3 --no-cpu --no-playouts --no-train > gpurun_out/r02_ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:bk_forward_tc -s 3 -c 3 -o gpurun_out/prof_fwd python bench.py --steps 3 --warmup 3 --no-cpu --no-playouts --no-train > gpurun_out/r02_ncu_full.log 2>&1
 timeout 300 python tools/run_playout_once.py 512 6 > gpurun_out/r02_playout_once.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_playout.csv python tools/run_playout_once.py 512 6 > gpurun_out/r02_ncu_list_playout.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"bk_forward_tc|bk_step_kernel" -c 4 -o gpurun_out/prof_playout python tools/run_playout_once.py 512 6 > gpurun_out/r02_ncu_full_playout.log 2>&1
