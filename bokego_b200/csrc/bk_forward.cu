@@ -79,6 +79,8 @@ static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KiB");
 // per-board scratch (group table, arg-max slots) at its start and zeroes it again (padding rows must read as zero)
 constexpr int STEP_SCRATCH = (int)((sizeof(BkStepScratch) + 15) / 16 * 16);
 static_assert(BK_GROUP * STEP_SCRATCH <= A_BYTES, "step scratch");
+constexpr int HALF_HEAD_OFF = 16384;               // PLAYOUT: 64 partial head sums of a half tile (dead activation buffer, re-zeroed)
+static_assert(BK_GROUP * STEP_SCRATCH <= HALF_HEAD_OFF && HALF_HEAD_OFF + 256 <= A_BYTES, "half-tile head scratch");
 static_assert(BK_GROUP * sizeof(BkResident) <= 240, "resident positions");
 // ENCODE: while the tensor pipe runs layers 1..5 of an item, three epilogue warps encode the boards of the NEXT item one at a time;
 // their group table lives in the logit area (written only by the last layer's epilogue) and the bytes behind it
@@ -220,14 +222,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
 }
 // D[tmem] (+)= A[smem] * B[smem] over the CTA pair: rows 0..127 from the leader's A, 128..255 from the peer's A at the
 // same shared-memory offset; output channels 0..63 from the leader's B half, 64..127 from the peer's
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accum)
+// instruction descriptor of the HALF tile: M = 128 over the pair = 64 rows of each CTA, at half the tensor time (32 cycles).
+// Its accumulator layout (tools/probes/tc_probe_m128x2.cu, profiles/r02_probe_m128x2.txt): row r (0..63) x channel n sits at TMEM
+// lane r + 64 * (n / 64), column n % 64 -- 64 columns used; the other 64 columns of the 128-column slot are clobbered.
+constexpr uint32_t IDESC_HALF = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accum, uint32_t idesc = IDESC);
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accum, uint32_t idesc)
 {
     const uint64_t adesc = ((uint64_t)DESC_HI << 32) | a_lo, bdesc = ((uint64_t)DESC_HI << 32) | b_lo;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accum)
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
 // completion of all MMAs issued so far -> one arrival on the barrier at this offset in BOTH CTAs of the pair
@@ -377,6 +384,15 @@ __device__ __forceinline__ Pass pass_info(int nb, int ps)
         p.l0_last = ps == 0;
     }
     return p;
+}
+// PLAYOUT: index of the pass's last tile when it may run as a HALF tile (64 rows per CTA, M = 128 MMAs at half the tensor
+// time), else -1.  Layers 1..6 of a 4-board item end at GEMM row 398 (tile 3 holds 15 real rows), of a 3-board item at row 298
+// (tile 2: 43 rows); 1, 2 and 5 boards fill more than half of their last tile.  Only the persistent playout kernel uses it:
+// there an item lasts as long as its passes, and the half tile takes 1/8 off the layers of a 4-board item.
+template <bool PLAYOUT>
+__device__ __forceinline__ int half_last_tile(int pair_nb, const Pass &pi)
+{
+    return (PLAYOUT && pi.layer >= 1 && (pair_nb == 3 || pair_nb == 4)) ? pi.n_tiles - 1 : -1;
 }
 __device__ __forceinline__ int n_stages_of(int layer) { return layer == 0 ? BK_L0_STAGES : BK_L_STAGES; }
 
@@ -630,6 +646,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         const uint32_t w_lo0 = desc_lo(sW, 1024);          // B half: [2 k-chunks][64 co][8 k] per K step
         const uint32_t b_lo0 = desc_lo(s_base + OFF_BIASW, 1024);
         int n_tiles = 0;
+        int half_tile = -1;        // PLAYOUT, layers 1..6 of 3- / 4-board items: the last tile holds <= 64 real rows -> M = 128 MMAs
         // one stage: up to four K steps with A windows a[0..nk-1], B = the 2 KiB K steps of ring slot `st` in both CTAs
         long long tw = 0, tp = 0, ti = 0;                  // diagnostic: cycles waiting for weights / bias rows, issuing
         const bool profiling = !PLAYOUT && args.prof != nullptr && blockIdx.x == 0;
@@ -649,7 +666,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                         for (int t = 0; t < 4; ++t)
                             if (t < n_tiles)
                                 umma_f16(tmem + (uint32_t)(t * 128), aw[j] + (uint32_t)t * 128u, w_lo + (uint32_t)j * (CTA_KSTEP_BYTES >> 4),
-                                         j == 0 ? accum0 : 1u);
+                                         j == 0 ? accum0 : 1u, t == half_tile ? IDESC_HALF : IDESC);
                     }
                 }
                 umma_commit_pair(sBar + 8 * (BAR_WEMPTY + st));   // stage consumed -> both producers may refill
@@ -673,6 +690,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                 }
                 const Pass pi = pass_info(pair_nb, ps);
                 n_tiles = pi.n_tiles;
+                half_tile = half_last_tile<PLAYOUT>(pair_nb, pi);
                 if (pass > 0) mbar_wait(sBar + 8 * BAR_ACT, (pass - 1) & 1u, 0x400u + pass);   // operands written, TMEM drained
                 tc_fence_after();
                 if (!PLAYOUT && args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) args.prof[pass * 4 + 0] = clock64();
@@ -707,7 +725,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     if (elect_one()) {
 #pragma unroll
                         for (int t = 0; t < 4; ++t)
-                            if (t < n_tiles) umma_f16(tmem + (uint32_t)(t * 128), one_lo, b_lo0, 1u);
+                            if (t < n_tiles) umma_f16(tmem + (uint32_t)(t * 128), one_lo, b_lo0, 1u, t == half_tile ? IDESC_HALF : IDESC);
                         umma_commit_pair(sBar + 8 * BAR_BEMPTY);
                     }
                     __syncwarp();
@@ -822,7 +840,42 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     if (ps == 0) args.prof[16 * k + 10] = clock64();               // accumulators of the move's first pass ready
                     if (pi.layer == 6) args.prof[16 * k + 9] = clock64();          // accumulators of the last layer ready
                 }
-                if (wq < pi.n_tiles) {
+                const int half_tile = half_last_tile<PLAYOUT>(pair_nb, pi);
+                if (PLAYOUT && wq == half_tile) {
+                    // HALF tile (M = 128 MMAs): 64 rows; lanes 0..63 hold channels 0..63 of row = lane, lanes 64..127 channels
+                    // 64..127 of row = lane - 64, in the first 64 columns of the slot -- two threads per row, 64 channels each
+                    const int hc = quad >> 1;                                   // which half of the channels
+                    const int r = 128 * (pi.tile0 + wq) + 32 * (quad & 1) + lane;
+                    int board = 0, sq = 0;
+                    const int dest = act_row_valid(r, it.nb, board, sq) ? r : -1;
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(t_lane + (uint32_t)(wq * 128), v0);
+                    tmem_ld32(t_lane + (uint32_t)(wq * 128 + 32), v1);
+                    tc_wait_ld();
+                    if (pi.layer < 6) {
+                        if (dest >= 0) {
+                            store_act32(smem, v0, hc * 8, dest);
+                            store_act32(smem, v1, hc * 8 + 4, dest);
+                        }
+                    } else {
+                        // the 1x1 head is ONE chain of 128 fused multiply-adds per row (channel order), as in the full tiles: the
+                        // thread with channels 0..63 starts it, hands the partial sum over, the other thread finishes it
+                        const float4 *hw4 = reinterpret_cast<const float4 *>(blob + BK_W_HEADW_OFF);
+                        float *hpart = reinterpret_cast<float *>(smem + OFF_A + HALF_HEAD_OFF);
+                        const int slot = 32 * (quad & 1) + lane;
+                        if (hc == 0) {
+                            float hsum = head_dot32(v0, hw4, 0.0f);
+                            hpart[slot] = head_dot32(v1, hw4 + 8, hsum);
+                        }
+                        named_bar_sync(8, 128);
+                        if (hc == 1) {
+                            float hsum = head_dot32(v0, hw4 + 16, hpart[slot]);
+                            hsum = head_dot32(v1, hw4 + 24, hsum);
+                            hpart[slot] = 0.0f;                                 // the activation buffer's padding must read as zero
+                            if (dest >= 0) logit[board * 81 + sq] = hsum + __ldg(reinterpret_cast<const float *>(blob + BK_W_HEADB_OFF) + sq);
+                        }
+                    }
+                } else if (wq < pi.n_tiles) {
                     // one thread per GEMM row: all 128 output channels of row r (accumulator slot wq holds tile tile0 + wq)
                     const int r = 128 * (pi.tile0 + wq) + 32 * quad + lane;
                     int dest, board = 0, sq = 0;
