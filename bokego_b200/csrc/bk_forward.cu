@@ -1392,13 +1392,20 @@ static int playout_impl(int8_t *boards, int16_t *ko, int16_t *last, int16_t *tur
         if (e != cudaSuccess || n_sm < 2) return -3;
         ds.n_sm = n_sm;
     }
-    // Boards per item: an item keeps its boards for the whole playout, so the playout's duration is (moves) x (time of one
-    // item's policy evaluation), and that grows with the item's M tiles.  Take the smallest item size that still gives every
-    // board an SM in ONE round (512 boards on 148 SMs: 4 boards -- layer 0 then fits one pass); with more boards than
-    // 5 x SMs the items are full groups of 5 (best throughput per board) and the CTAs play several items one after the other.
+    // Boards per item.  An item keeps its boards for the whole playout, so the run lasts (rounds of the grid) x (time of one
+    // item's move), and an item's move grows with its M tiles: measured on the B200 (profiles/r02k_playout_per_move.jsonl)
+    // 48 / 66 / 76 / 85 / 100 us for 1 .. 5 boards (3 and 4 boards run their last tile as a half tile, 5 boards need two layer-0
+    // passes).  Up to two rounds of full groups take the size that minimises rounds x move time (512 boards -> 4 per item in one
+    // round, 1,024 -> 4 per item in two rounds); beyond that full groups of 5, the best throughput per board.
     const int n_clusters = ds.n_sm / 2;
-    int grp = (B + 2 * n_clusters - 1) / (2 * n_clusters);
-    if (grp > BK_GROUP) grp = BK_GROUP;
+    static const double move_us[BK_GROUP + 1] = {0.0, 48.0, 66.0, 76.0, 85.0, 100.0};
+    int grp = BK_GROUP;
+    double best = 1e30;
+    for (int g = 1; g <= BK_GROUP && B <= 2 * BK_GROUP * ds.n_sm; ++g) {
+        const int pairs = ((B + g - 1) / g + 1) / 2;
+        const double t = (double)((pairs + n_clusters - 1) / n_clusters) * move_us[g];
+        if (t < best - 1e-9) { best = t; grp = g; }
+    }
     a.play_group = grp;
     a.n_sub = (B + grp - 1) / grp;
     a.g_whole = a.n_sub; a.split = 1;

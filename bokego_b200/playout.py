@@ -66,10 +66,12 @@ def record_to_sgf(record, out_path, **kwargs):
 def persistent_pays(B, device):
     """The persistent playout kernel keeps an item of boards on its SM for the whole game, so its step phase (sample, play,
     re-encode: ~10 us per move) is serial with that item's policy evaluation, while the launch-per-move loop amortises one
-    stepping launch over all rounds of the grid.  Measured (profiles/r02f_playout_per_move.jsonl): the kernel wins while every
-    board gets an SM in ONE round (512 boards: 90 us per move against 103), and loses by ~5 % beyond (1,024 / 4,096 boards)."""
+    stepping launch over all rounds of the grid.  Measured on the B200 (profiles/r02k_playout_per_move.jsonl,
+    r02l_playout_per_move.jsonl): the kernel wins while the boards fit two rounds of 4-board items (64 boards: 47 against 54 us
+    per move; 512: 85 against 104; 1,024: 170 against 182), ties at 1,480 (212 / 208) and loses by a few per cent beyond
+    (2,048: 312 / 307; 4,096: 625 / 604)."""
     n_sm = torch.cuda.get_device_properties(device).multi_processor_count
-    return B <= 5 * n_sm
+    return B <= 8 * n_sm
 
 
 def n_steps_for(mode, max_turn, first_turn=0):
