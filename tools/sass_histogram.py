@@ -45,13 +45,13 @@ def main():
     print("| kernel | total | " + " | ".join(cols) + " |")
     print("|---|---|" + "---|" * len(cols))
     for k, c in kernels.items():
-        short = re.sub(r"\(.*", "", names[k].replace("(anonymous namespace)::", "").replace("<unnamed>::", ""))
+        short = re.sub(r"\(.*", "", names[k].replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("(int)", "").replace("(bool)", ""))
         print(f"| `{short}` | {sum(v for n, v in c.items() if '.' not in n)} | " + " | ".join(str(c[x]) for x in cols) + " |")
     print("\n## Modifiers seen on the tensor / TMA instructions\n")
     for k, c in kernels.items():
         mods = sorted(n for n in c if "." in n)
         if mods:
-            short = re.sub(r"\(.*", "", names[k].replace("(anonymous namespace)::", "").replace("<unnamed>::", ""))
+            short = re.sub(r"\(.*", "", names[k].replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("(int)", "").replace("(bool)", ""))
             print(f"- `{short}`: " + ", ".join(f"`{m}` x{c[m]}" for m in mods))
 
 
