@@ -125,3 +125,21 @@ def test_standin_value_head_fixture_matches_generator():
     assert set(fx) == set(gen)
     for k, v in gen.items():
         assert np.array_equal(fx[k], v.numpy()), k
+
+
+def test_f16_operand_emulation_is_a_bounded_perturbation_of_the_reference_nets(positions, nets_golden, sd17):
+    """oracle.nets.policy_logits_f16_operands (the yardstick of tests/test_gpu_precision.py: conv weights and inter-layer
+    activations rounded to fp16, fp32 sums) stays within the rounding floor of 16-bit operands of the reference's fp32 logits on the
+    golden positions, keeps their arg-max, and is not simply the fp32 result"""
+    import torch
+    from oracle import nets as onets
+    src = nets_golden["src"][:128]
+    x = onets.planes_to_float(positions["feats"][src])
+    want = torch.from_numpy(nets_golden["logits17"][:128])
+    exact = onets.policy_logits(sd17, x)
+    emu = onets.policy_logits_f16_operands(sd17, x)
+    assert float((exact - want).abs().max()) < 1e-4
+    err = float((emu - want).abs().max())
+    assert 1e-3 < err < 5e-2, err
+    assert bool((emu.argmax(1) == want.argmax(1)).all())
+    assert float((torch.softmax(emu, 1) - torch.softmax(want, 1)).abs().max()) < 2e-3
