@@ -639,8 +639,10 @@ def run_ours(args, rank, world, local_rank):
                         keep.append((rec, po.gather_records(rec, args.selfplay_games, rank, world)))
                     del keep[:-2]
                 main.wait_stream(side)
-            selfplay_stream(2)
-            sp_pipe_tot, _ = timed(lambda: selfplay_stream(n_pipe), 1, 0, flush_l2=False)
+            sp_pipe_tot = None
+            if world > 1:                        # (with one GPU there is no gather to overlap)
+                selfplay_stream(2)
+                sp_pipe_tot, _ = timed(lambda: selfplay_stream(n_pipe), 1, 0, flush_l2=False)
             sim = po.PlayoutGraph(args.simulate_boards, dev, pol, bk.MODE_MCTS, seed=2, game0=rank * args.simulate_boards)
             sim_tot, sim_ms = timed(lambda: sim.replay(), 2, 1, flush_l2=False)
             extra = {"selfplay": {"games": args.selfplay_games, "games_per_s": args.selfplay_games * 3 / (1e-3 * sp_tot),
@@ -649,10 +651,10 @@ def run_ours(args, rank, world, local_rank):
                                   "kernel_launches_per_batch": sp.launches, "boards_per_gpu": hi - lo, "us_per_move": 1e3 * sp_tot / 3 / 72,
                                   "engine": "persistent playout kernel (bk_playout_run: whole games in one launch)" if sp.persistent
                                   else "two launches per move (bk_forward + bk_playout_step_encode), CUDA graph",
-                                  "steady_stream": {"games_per_s": args.selfplay_games * n_pipe / (1e-3 * sp_pipe_tot),
-                                                    "ms_per_batch": sp_pipe_tot / n_pipe, "batches": n_pipe,
-                                                    "how": "batches back to back, the result gather of one batch on a side stream under the games "
-                                                           "of the next; one timed region"}},
+                                  "steady_stream": None if sp_pipe_tot is None else {
+                                      "games_per_s": args.selfplay_games * n_pipe / (1e-3 * sp_pipe_tot), "ms_per_batch": sp_pipe_tot / n_pipe,
+                                      "batches": n_pipe, "how": "batches back to back, the result gather of one batch on a side stream under "
+                                                                "the games of the next; one timed region"}},
                      "simulate": {"boards_per_gpu": args.simulate_boards, "playouts_per_s": world * args.simulate_boards * 2 / (1e-3 * sim_tot),
                                   "ms_per_batch": sim_tot / 2, "scaling": "weak", "max_turn": 80}}
             # weak-scaling self-play beside the strong-scaling line: args.selfplay_games games PER GPU
