@@ -14,7 +14,9 @@
 //     128 B/clk shared-memory port (measured 76 cycles); in the pair each CTA reads its own A rows and only
 //     HALF of B (the weights of 64 output channels), 6 KiB per MMA, and the MMA runs at its 64-cycle floor;
 //   * weights stream L2 -> shared memory in stages of four K steps (8 KiB per CTA, tensor-map TMA + mbarrier,
-//     a 6-slot ring); every stage is used by all tiles of the pass before its slot is recycled;
+//     a 6-slot ring); every stage is used by all tiles of the pass before its slot is recycled; the last three stages
+//     of a pass (and the bias K step) are issued tile by tile with one completion barrier per tile, so the read-out of
+//     tile t runs under the MMAs of the tiles behind it and only the last tile's read-out is exposed;
 //   * the folded bias enters through the tensor core as well: two extra K rows (bias split into fp16 hi + lo)
 //     multiplied by a constant all-ones operand, so the accumulators leave TMEM ready for ReLU;
 //   * 16 epilogue warps per CTA (one thread per GEMM row: TMEM lane quarter = warp % 4, tile = warp / 4) pull the
@@ -63,6 +65,15 @@ constexpr int CTA_STAGE_BYTES = BK_STAGE_BYTES / 2;   // this CTA's N half of a 
 constexpr int CTA_KSTEP_BYTES = BK_KSTEP_BYTES / 2;
 constexpr int CTA_BIAS_BYTES = BK_BIAS_BYTES / 2;  // this CTA's half of a layer's bias rows
 constexpr int N_STAGES = 6;                        // 48 KiB weight ring
+#ifndef BK_HANDOVER
+#define BK_HANDOVER 0                              // 0 = the hand-over of a pass waits for all its MMAs; 1..3 = measurement builds (see the epilogue)
+#endif
+#ifndef BK_TAIL
+#define BK_TAIL 3                                  // stages at the end of a pass that are issued tile by tile
+#endif
+#ifndef BK_TAIL_PLAYOUT
+#define BK_TAIL_PLAYOUT 2                          // the same in the persistent playout kernel (measured: 2 is 0.6 % faster per move than 3)
+#endif
 constexpr int ONES_BYTES = 4096;                   // [2 k-chunks][128 rows][8]: 1.0 in k = 0, 1
 constexpr int OFF_A = 0;
 constexpr int OFF_F = OFF_A + A_BYTES;             // F's front margin doubles as the rows behind A's last chunk
@@ -89,11 +100,12 @@ static_assert(OFF_W % 128 == 0 && OFF_ONES % 128 == 0 && OFF_BIASW % 128 == 0, "
 
 // WFULL (leader): both CTAs' halves of a stage have landed -- each CTA's tensor-map copy (cta_group::2) reports its
 // bytes to the LEADER's barrier.  WEMPTY: the pair's MMAs that read the stage are complete.  BFULL / BEMPTY: the same for
-// the layer's bias rows (single slot).  ACC: accumulators of the pass complete.  ACT (leader): both CTAs' epilogues done.
+// the layer's bias rows (single slot).  ACC[t]: accumulator tile t of the pass complete (the last stages of a pass are issued
+// tile by tile, so the read-out of the first tiles runs under the MMAs of the last).  ACT (leader): both CTAs' epilogues done.
 // FFULL / PFFULL (leader) / FEMPTY: the same for the feature planes of an item (the peer forwards its FFULL to the
 // leader's PFFULL, once per item).
-enum { BAR_WFULL = 0, BAR_WEMPTY = N_STAGES, BAR_BFULL = 2 * N_STAGES, BAR_BEMPTY, BAR_ACC, BAR_ACT, BAR_FFULL, BAR_PFFULL,
-       BAR_FEMPTY, N_BARS };
+enum { BAR_WFULL = 0, BAR_WEMPTY = N_STAGES, BAR_BFULL = 2 * N_STAGES, BAR_BEMPTY, BAR_ACC, BAR_ACT = BAR_ACC + 4, BAR_FFULL,
+       BAR_PFFULL, BAR_FEMPTY, N_BARS };
 static_assert(N_BARS * 8 <= 192, "barrier area");
 
 // the conv weights of a blob seen as a 2-D tensor of 512-byte rows (256 fp16): one CTA's half of a stage = 16 rows,
@@ -436,7 +448,8 @@ __device__ __forceinline__ void store_act32(uint8_t *smem, const uint32_t (&v)[3
         *reinterpret_cast<uint4 *>(smem + OFF_A + (chunk0 + c8) * A_LBO + (A_MARGIN + dest) * 16) = o;
     }
 }
-// 1x1 head conv: sum over 32 channels of relu(acc) * w
+// 1x1 head conv: sum over 32 channels of relu(acc) * w, continuing the chain `acc` (a row's head output is ONE chain of 128 fused
+// multiply-adds in channel order in every instantiation; four interleaved chains were measured 1.5 % slower per playout move)
 __device__ __forceinline__ float head_dot32(const uint32_t (&v)[32], const float4 *hw4, float acc)
 {
 #pragma unroll
@@ -517,6 +530,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
     const uint32_t s_base = smem_u32(smem);
     const uint32_t sA = s_base + OFF_A, sF = s_base + OFF_F, sW = s_base + OFF_W, sBar = s_base + OFF_BAR;
     float *logit = reinterpret_cast<float *>(smem + OFF_LOGIT);
+    const uint32_t sAct = sBar + 8 * BAR_ACT;
     const int rank = (int)cluster_ctarank();           // 0 = leader (issues the pair's MMAs), 1 = peer
     const int pair0 = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     constexpr bool PLAYOUT = MODE == 1, ENCODE = MODE == 2;
@@ -540,8 +554,8 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         }
         mbar_init(sBar + 8 * BAR_BFULL, 1);
         mbar_init(sBar + 8 * BAR_BEMPTY, 1);
-        mbar_init(sBar + 8 * BAR_ACC, 1);
-        mbar_init(sBar + 8 * BAR_ACT, 2 * N_EPI_WARPS);
+        for (int t = 0; t < 4; ++t) mbar_init(sBar + 8 * (BAR_ACC + t), 1);
+        mbar_init(sAct, 2 * N_EPI_WARPS);
         mbar_init(sBar + 8 * BAR_FFULL, 1);
         mbar_init(sBar + 8 * BAR_PFFULL, 1);
         mbar_init(sBar + 8 * BAR_FEMPTY, 1);
@@ -647,33 +661,46 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         const uint32_t b_lo0 = desc_lo(s_base + OFF_BIASW, 1024);
         int n_tiles = 0;
         int half_tile = -1;        // PLAYOUT, layers 1..6 of 3- / 4-board items: the last tile holds <= 64 real rows -> M = 128 MMAs
-        // one stage: up to four K steps with A windows a[0..nk-1], B = the 2 KiB K steps of ring slot `st` in both CTAs
         long long tw = 0, tp = 0, ti = 0;                  // diagnostic: cycles waiting for weights / bias rows, issuing
         const bool profiling = !PLAYOUT && args.prof != nullptr && blockIdx.x == 0;
-        auto stage = [&](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int nk, uint32_t accum0) {
-            long long c0 = 0, c1 = 0;
-            if (profiling) c0 = clock64();
-            mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x500u + st);
-            if (profiling) { c1 = clock64(); tw += c1 - c0; }
-            tc_fence_after();
-            const uint32_t w_lo = w_lo0 + st * (CTA_STAGE_BYTES >> 4);
-            if (elect_one()) {
-                const uint32_t aw[4] = {a0, a1, a2, a3};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j < nk) {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t)
-                            if (t < n_tiles)
-                                umma_f16(tmem + (uint32_t)(t * 128), aw[j] + (uint32_t)t * 128u, w_lo + (uint32_t)j * (CTA_KSTEP_BYTES >> 4),
-                                         j == 0 ? accum0 : 1u, t == half_tile ? IDESC_HALF : IDESC);
-                    }
-                }
-                umma_commit_pair(sBar + 8 * (BAR_WEMPTY + st));   // stage consumed -> both producers may refill
+        constexpr int TAIL = PLAYOUT ? BK_TAIL_PLAYOUT : BK_TAIL;   // stages at the end of a pass that are issued tile by tile
+        static_assert(TAIL >= 1 && TAIL <= 5, "the tail may only hold taps with non-negative row shifts, and must leave ring slots free");
+        // A windows of stage s of a pass (descriptor words of the pass's first tile): K steps 0, 1 at w.x, w.x + w.z and K steps
+        // 2, 3 at w.y, w.y + w.z; nk = how many of the four exist
+        auto windows = [&](const Pass &pi, int s, int &nk) -> uint3 {
+            uint3 w;
+            if (pi.layer == 0) {       // stage s = taps 2s, 2s+1; a tap is two K steps (channel chunks 0,1 / 2,3); the last stage holds tap 24 only
+                const uint32_t fb = f_lo0 + (uint32_t)(128 * pi.tile0);
+                const int t0 = 2 * s, t1 = 2 * s + 1;
+                w.x = fb + (uint32_t)((t0 / 5 - 2) * 11 + (t0 % 5 - 2));
+                w.y = fb + (uint32_t)((t1 / 5 - 2) * 11 + (t1 % 5 - 2));
+                w.z = 2u * (F_LBO >> 4);
+                nk = t1 < 25 ? 4 : 2;
+            } else {                   // stage s = half a tap: K steps with channel chunks (8*part + 2j, +1), j = 0..3
+                const int tap = s >> 1, part = s & 1;
+                const int ti = tap / 3, tj = tap - 3 * ti;
+                w.x = a_lo0 + (uint32_t)((ti - 1) * 10 + (tj - 1)) + (uint32_t)(8 * part) * (A_LBO >> 4);
+                if (args.diag & 2) w.x = a_lo0 - 4u + (uint32_t)(8 * part) * (A_LBO >> 4);   // measurement only: 128 B aligned windows
+                w.y = w.x + 4u * (A_LBO >> 4);
+                w.z = 2u * (A_LBO >> 4);
+                nk = 4;
             }
-            __syncwarp();
-            if (profiling) ti += clock64() - c1;
-            if (++st == N_STAGES) { st = 0; ph ^= 1u; }
+            return w;
+        };
+        // the K steps of one stage for tiles [t_lo, t_hi): B = the 2 KiB K steps of ring slot `slot` in both CTAs
+        auto issue = [&](const uint3 w, int nk, uint32_t slot, int t_lo, int t_hi, uint32_t accum0) {
+            const uint32_t w_lo = w_lo0 + slot * (CTA_STAGE_BYTES >> 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < nk) {
+                    const uint32_t aj = (j < 2 ? w.x : w.y) + (uint32_t)(j & 1) * w.z;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (t >= t_lo && t < t_hi)
+                            umma_f16(tmem + (uint32_t)(t * 128), aj + (uint32_t)t * 128u, w_lo + (uint32_t)j * (CTA_KSTEP_BYTES >> 4),
+                                     j == 0 ? accum0 : 1u, t == half_tile ? IDESC_HALF : IDESC);
+                }
+            }
         };
         Item it;
         int pair_nb;
@@ -691,50 +718,64 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                 const Pass pi = pass_info(pair_nb, ps);
                 n_tiles = pi.n_tiles;
                 half_tile = half_last_tile<PLAYOUT>(pair_nb, pi);
-                if (pass > 0) mbar_wait(sBar + 8 * BAR_ACT, (pass - 1) & 1u, 0x400u + pass);   // operands written, TMEM drained
+                if (pass > 0) mbar_wait(sAct, (pass - 1) & 1u, 0x400u + pass);   // operands written, TMEM drained
                 tc_fence_after();
                 if (!PLAYOUT && args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) args.prof[pass * 4 + 0] = clock64();
-                if (pi.layer == 0) {
-                    // stage s = taps 2s, 2s+1; a tap is two K steps (channel chunks 0,1 / 2,3); the last stage holds tap 24 only
-                    const uint32_t fb = f_lo0 + (uint32_t)(128 * pi.tile0);
-                    for (int s2 = 0; s2 < BK_L0_STAGES; ++s2) {
-                        const int t0 = 2 * s2, t1 = 2 * s2 + 1;
-                        const uint32_t a = fb + (uint32_t)((t0 / 5 - 2) * 11 + (t0 % 5 - 2));
-                        const uint32_t c = fb + (uint32_t)((t1 / 5 - 2) * 11 + (t1 % 5 - 2));
-                        stage(a, a + 2u * (F_LBO >> 4), c, c + 2u * (F_LBO >> 4), t1 < 25 ? 4 : 2, s2 != 0);
-                    }
-                } else {
-                    // stage s = half a tap: K steps with channel chunks (8*part + 2j, +1), j = 0..3
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int ti = tap / 3, tj = tap - 3 * ti;
-                        uint32_t a = a_lo0 + (uint32_t)((ti - 1) * 10 + (tj - 1));
-                        if (args.diag & 2) a = a_lo0 - 4u;             // measurement only: 128 B aligned windows
-#pragma unroll
-                        for (int part = 0; part < 2; ++part) {
-                            const uint32_t b = a + (uint32_t)(8 * part) * (A_LBO >> 4);
-                            stage(b, b + 2u * (A_LBO >> 4), b + 4u * (A_LBO >> 4), b + 6u * (A_LBO >> 4), 4, (tap | part) != 0);
-                        }
-                    }
-                }
-                {   // bias rows x the all-ones operand (one K step; every row of the ones operand is the same)
-                    long long c0 = 0;
+                const int S = n_stages_of(pi.layer);
+                // ---- all but the last TAIL stages: stage by stage, every tile uses the stage before its slot is handed back
+                for (int s2 = 0; s2 < S - TAIL; ++s2) {
+                    long long c0 = 0, c1 = 0;
                     if (profiling) c0 = clock64();
+                    mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x500u + st);
+                    if (profiling) { c1 = clock64(); tw += c1 - c0; }
+                    tc_fence_after();
+                    int nk;
+                    const uint3 w = windows(pi, s2, nk);
+                    if (elect_one()) {
+                        issue(w, nk, st, 0, n_tiles, s2 != 0);
+                        umma_commit_pair(sBar + 8 * (BAR_WEMPTY + st));   // stage consumed -> both producers may refill
+                    }
+                    __syncwarp();
+                    if (profiling) ti += clock64() - c1;
+                    if (++st == N_STAGES) { st = 0; ph ^= 1u; }
+                }
+                // ---- the last TAIL stages and the bias rows (x the all-ones operand: one K step, every row of the ones operand is
+                //      the same): tile by tile, so that tile t is complete (ACC[t]) while the tiles behind it are still running and
+                //      the TMEM read-out and the operand stores of its epilogue run under their MMAs
+                {
+                    long long c0 = 0, c1 = 0;
+                    if (profiling) c0 = clock64();
+                    uint32_t slot[TAIL];
+                    uint3 w[TAIL];
+                    int nk[TAIL];
+#pragma unroll
+                    for (int r = 0; r < TAIL; ++r) {
+                        slot[r] = st;
+                        mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x540u + st);
+                        if (++st == N_STAGES) { st = 0; ph ^= 1u; }
+                        w[r] = windows(pi, S - TAIL + r, nk[r]);
+                    }
                     mbar_wait(sBar + 8 * BAR_BFULL, pass & 1u, 0x5C0u);
-                    if (profiling) tp += clock64() - c0;
+                    if (profiling) { c1 = clock64(); tp += c1 - c0; }
                     tc_fence_after();
                     if (elect_one()) {
 #pragma unroll
-                        for (int t = 0; t < 4; ++t)
-                            if (t < n_tiles) umma_f16(tmem + (uint32_t)(t * 128), one_lo, b_lo0, 1u, t == half_tile ? IDESC_HALF : IDESC);
+                        for (int t = 0; t < 4; ++t) {
+                            if (t < n_tiles) {
+#pragma unroll
+                                for (int r = 0; r < TAIL; ++r) issue(w[r], nk[r], slot[r], t, t + 1, 1u);
+                                umma_f16(tmem + (uint32_t)(t * 128), one_lo, b_lo0, 1u, t == half_tile ? IDESC_HALF : IDESC);
+                            }
+                            umma_commit_pair(sBar + 8 * (BAR_ACC + t));   // (tiles the pass does not have complete with the last real one)
+                        }
+#pragma unroll
+                        for (int r = 0; r < TAIL; ++r) umma_commit_pair(sBar + 8 * (BAR_WEMPTY + slot[r]));
                         umma_commit_pair(sBar + 8 * BAR_BEMPTY);
+                        if (pi.l0_last) umma_commit_pair(sBar + 8 * BAR_FEMPTY);   // feature planes no longer needed
                     }
                     __syncwarp();
+                    if (profiling) ti += clock64() - c1;
                 }
-                if (elect_one()) {
-                    if (pi.l0_last) umma_commit_pair(sBar + 8 * BAR_FEMPTY);   // feature planes no longer needed
-                    umma_commit_pair(sBar + 8 * BAR_ACC);                      // accumulators of this pass complete
-                }
-                __syncwarp();
                 if (!PLAYOUT && args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) {
                     args.prof[pass * 4 + 1] = clock64();
                     args.prof[256 + pass * 4 + 0] = tw; args.prof[256 + pass * 4 + 1] = tp; args.prof[256 + pass * 4 + 2] = ti;
@@ -747,7 +788,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         // =========================== epilogue warps (both CTAs, each on its own rows) ===========================
         const int quad = warp & 3, wq = warp >> 2;
         const uint32_t t_lane = tmem + ((uint32_t)(32 * quad) << 16);
-        const uint32_t leader_act = mapa(sBar + 8 * BAR_ACT, 0);
+        const uint32_t leader_act = mapa(sAct, 0);
         uint32_t pass = 0;
         bool first = true;
         Item it;
@@ -831,16 +872,22 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                         }
                     }
                 }
-                mbar_wait(sBar + 8 * BAR_ACC, pass & 1u, 0x600u + pass);
+                // Tile wq is read out, and its rows rewritten in place, as soon as IT is complete (ACC[wq]): the MMAs still in
+                // flight then are the last TAIL stages -- taps 7 and 8, row shifts +10 / +11 -- of the tiles behind it, which read
+                // rows >= 128 (wq + 1) + 10 and write other TMEM columns (layer 0 reads the feature planes, not this buffer).
+                // Only the read-out of the pass's last tile is left exposed.  The hand-over (proxy fence + arrive) waits for the
+                // whole pass: see below.
+                const int half_tile = half_last_tile<PLAYOUT>(pair_nb, pi);
+                const bool own_tile = wq < pi.n_tiles;
+                mbar_wait(sBar + 8 * (BAR_ACC + (own_tile ? wq : 3)), pass & 1u, 0x600u + pass);
                 tc_fence_after();
-                const bool prof = !PLAYOUT && args.prof && blockIdx.x == 0 && pass < 64 && threadIdx.x == 0;
+                const bool prof = !PLAYOUT && args.prof && blockIdx.x == 0 && pass < 64 && threadIdx.x == 32 * 12;   // last group
                 if (prof) args.prof[pass * 4 + 2] = clock64();
                 const bool dump = args.dump && blockIdx.x == 0 && first && ps == args.dump_pass;
                 if (PLAYOUT && args.prof && blockIdx.x == 0 && first && k < 32 && threadIdx.x == 0) {
                     if (ps == 0) args.prof[16 * k + 10] = clock64();               // accumulators of the move's first pass ready
                     if (pi.layer == 6) args.prof[16 * k + 9] = clock64();          // accumulators of the last layer ready
                 }
-                const int half_tile = half_last_tile<PLAYOUT>(pair_nb, pi);
                 if (PLAYOUT && wq == half_tile) {
                     // HALF tile (M = 128 MMAs): 64 rows; lanes 0..63 hold channels 0..63 of row = lane, lanes 64..127 channels
                     // 64..127 of row = lane - 64, in the first 64 columns of the slot -- two threads per row, 64 channels each
@@ -864,8 +911,8 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                         float *hpart = reinterpret_cast<float *>(smem + OFF_A + HALF_HEAD_OFF);
                         const int slot = 32 * (quad & 1) + lane;
                         if (hc == 0) {
-                            float hsum = head_dot32(v0, hw4, 0.0f);
-                            hpart[slot] = head_dot32(v1, hw4 + 8, hsum);
+                            float hs = head_dot32(v0, hw4, 0.0f);
+                            hpart[slot] = head_dot32(v1, hw4 + 8, hs);
                         }
                         named_bar_sync(8, 128);
                         if (hc == 1) {
@@ -875,7 +922,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                             if (dest >= 0) logit[board * 81 + sq] = hsum + __ldg(reinterpret_cast<const float *>(blob + BK_W_HEADB_OFF) + sq);
                         }
                     }
-                } else if (wq < pi.n_tiles) {
+                } else if (own_tile) {
                     // one thread per GEMM row: all 128 output channels of row r (accumulator slot wq holds tile tile0 + wq)
                     const int r = 128 * (pi.tile0 + wq) + 32 * quad + lane;
                     int dest, board = 0, sq = 0;
@@ -909,13 +956,30 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     if (pi.layer == 6 && dest >= 0)   // 1x1 conv 128->1 plus the per-square bias
                         logit[board * 81 + sq] = hsum + __ldg(reinterpret_cast<const float *>(blob + BK_W_HEADB_OFF) + sq);
                 }
+                // Hand-over only when every MMA of the pass is complete (ACC[3] completes with the last tile).  Measured on the
+                // B200 (tools/gpu_r02q.sh, profiles/r02_handover_experiments.md): letting the early tiles ARRIVE while MMAs of their
+                // own pass were still in flight corrupted between 1 in 150 and 1 in 12,000 cold-L2 launches (boards 2-3 of a CTA's
+                // first item), with a relaxed arrive (BK_HANDOVER=1) and, less often, with a cluster-scope release (=3); the early
+                // read-out, the early in-place stores and even the early proxy fence are clean as long as the arrive waits (=2,
+                // and this form: 0).  No access that becomes concurrent explains it, so the rule is kept as measured: no arrive
+                // on the hand-over barrier while the pair's tensor cores are running this pass.
+#if BK_HANDOVER == 0
+                if (own_tile && wq != 3) mbar_wait(sBar + 8 * (BAR_ACC + 3), pass & 1u, 0x680u + pass);
+#endif
                 // this pass's TMEM reads are complete and the operand writes are visible to the tensor core
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();
+#if BK_HANDOVER == 2
+                if (own_tile && wq != 3) mbar_wait(sBar + 8 * (BAR_ACC + 3), pass & 1u, 0x680u + pass);
+#endif
                 if (lane == 0) {
                     __threadfence_block();     // the warp's stores are performed before the (relaxed) arrive can be observed
+#if BK_HANDOVER == 3
+                    mbar_arrive_cluster(leader_act);
+#else
                     mbar_arrive_cluster_relaxed(leader_act);
+#endif
                 }
                 if (prof) args.prof[pass * 4 + 3] = clock64();
                 if (pi.layer == 6) {
