@@ -636,11 +636,12 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         }
     } else if (warp == WARP_MMA && rank == 1) {
         // =========================== peer: tell the leader when this CTA's feature planes have landed ===============
+        // (PLAYOUT: the planes are written by the epilogue warps, which report to the leader themselves -- n_pairs loop skipped)
         uint32_t n_done = 0;
         const uint32_t leader_bar = mapa(sBar, 0);
         Item it;
         int pair_nb;
-        for (int v = pair0; v < args.n_pairs; v += n_clusters) {
+        for (int v = pair0; v < args.n_pairs && !PLAYOUT; v += n_clusters) {
             if (!decode_pair_t<PLAYOUT>(args, v, rank, it, pair_nb)) continue;
             for (int k = 0; k < n_steps; ++k) {
                 mbar_wait(sBar + 8 * BAR_FFULL, n_done & 1u, 0x300u);
@@ -789,6 +790,14 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         const int quad = warp & 3, wq = warp >> 2;
         const uint32_t t_lane = tmem + ((uint32_t)(32 * quad) << 16);
         const uint32_t leader_act = mapa(sAct, 0);
+        // PLAYOUT: "the planes of the next move are in place in this CTA" -- the leader's own FFULL, or, from the peer, straight
+        // onto the leader's PFFULL (a relaxed arrive behind the proxy fences and the barrier of the 16 warps, like the pass
+        // hand-over; no tensor work is in flight here; the forwarding warp's release.cluster round trip cost 1.4 k cycles a move)
+        const uint32_t leader_pffull = mapa(sBar + 8 * BAR_PFFULL, 0);
+        auto planes_ready = [&]() {
+            if (rank == 0) mbar_arrive(sBar + 8 * BAR_FFULL);
+            else { __threadfence_block(); mbar_arrive_cluster_relaxed(leader_pffull); }
+        };
         uint32_t pass = 0;
         bool first = true;
         Item it;
@@ -850,7 +859,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                 }
                 fence_proxy_async();
                 named_bar_sync(1, N_EPI_WARPS * 32);
-                if (threadIdx.x == 0) mbar_arrive(sBar + 8 * BAR_FFULL);
+                if (threadIdx.x == 0) planes_ready();
             }
             for (int k = 0; k < n_steps; ++k)
             for (int ps = 0; ps < np; ++ps, ++pass) {
@@ -1021,7 +1030,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                         }
                         fence_proxy_async();              // planes and zeroed scratch are visible to the tensor core
                         named_bar_sync(1, N_EPI_WARPS * 32);
-                        if (!last_move && threadIdx.x == 0) mbar_arrive(sBar + 8 * BAR_FFULL);   // planes of move k + 1 are in place
+                        if (!last_move && threadIdx.x == 0) planes_ready();                        // planes of move k + 1 are in place
                         if (stamps && threadIdx.x == 0) stamps[8] = clock64();
                     }
                 }
