@@ -66,7 +66,7 @@ constexpr int CTA_KSTEP_BYTES = BK_KSTEP_BYTES / 2;
 constexpr int CTA_BIAS_BYTES = BK_BIAS_BYTES / 2;  // this CTA's half of a layer's bias rows
 constexpr int N_STAGES = 6;                        // 48 KiB weight ring
 #ifndef BK_HANDOVER
-#define BK_HANDOVER 0                              // 0 = the hand-over of a pass waits for all its MMAs; 1..3 = measurement builds (see the epilogue)
+#define BK_HANDOVER 0                              // 1, 2 = measurement builds (see the epilogue)
 #endif
 #ifndef BK_TAIL
 #define BK_TAIL 3                                  // stages at the end of a pass that are issued tile by tile
@@ -186,6 +186,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 }
 // Bounded wait: a protocol bug must end in a trap (launch error), never in a hung GPU.
 __device__ unsigned int *g_dbg = nullptr;
+#ifdef BK_TRACE   // measurement build (tools/trace_handover.py): one hash per epilogue thread and pass of what it read out of TMEM
+__device__ unsigned int *g_trace = nullptr;
+constexpr int TRACE_PASSES = 24;
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0)
 {
     if (mbar_try_wait(bar, parity)) return;
@@ -884,11 +888,18 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                 // Tile wq is read out, and its rows rewritten in place, as soon as IT is complete (ACC[wq]): the MMAs still in
                 // flight then are the last TAIL stages -- taps 7 and 8, row shifts +10 / +11 -- of the tiles behind it, which read
                 // rows >= 128 (wq + 1) + 10 and write other TMEM columns (layer 0 reads the feature planes, not this buffer).
-                // Only the read-out of the pass's last tile is left exposed.  The hand-over (proxy fence + arrive) waits for the
-                // whole pass: see below.
+                // Only the read-out of the pass's last tile is left exposed.
+                // EVERY group waits on its OWN barrier in EVERY pass (a tile the pass does not have completes with the last real
+                // one): a parity wait cannot tell "phase k complete" from "phase k - 2 complete", so a warp may only wait on a
+                // barrier whose every phase it consumes.  Round 1's form -- idle groups waiting on ACC[3] -- let a warp of group 2
+                // run a whole pass ahead of the issuing thread (see the hand-over below).
                 const int half_tile = half_last_tile<PLAYOUT>(pair_nb, pi);
                 const bool own_tile = wq < pi.n_tiles;
+#if BK_HANDOVER == 1   // measurement build: round 1's barrier choice (fails ~1 cold-L2 launch in 150 ... 12,000)
                 mbar_wait(sBar + 8 * (BAR_ACC + (own_tile ? wq : 3)), pass & 1u, 0x600u + pass);
+#else
+                mbar_wait(sBar + 8 * (BAR_ACC + wq), pass & 1u, 0x600u + pass);
+#endif
                 tc_fence_after();
                 const bool prof = !PLAYOUT && args.prof && blockIdx.x == 0 && pass < 64 && threadIdx.x == 32 * 12;   // last group
                 if (prof) args.prof[pass * 4 + 2] = clock64();
@@ -939,12 +950,18 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     else dest = act_row_valid(r, it.nb, board, sq) ? r : -1;
                     float hsum = 0.0f;
                     const float4 *hw4 = reinterpret_cast<const float4 *>(blob + BK_W_HEADW_OFF);
+#ifdef BK_TRACE
+                    unsigned int trace_h = 17u;
+#endif
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         uint32_t v0[32], v1[32];
                         tmem_ld32(t_lane + (uint32_t)(wq * 128 + h * 64), v0);
                         tmem_ld32(t_lane + (uint32_t)(wq * 128 + h * 64 + 32), v1);
                         tc_wait_ld();
+#ifdef BK_TRACE
+                        trace_h = (trace_h * 31u + v0[5]) * 31u + v1[17];      // (a light trace: the full hash moved the failure away)
+#endif
                         if (dump) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
@@ -964,31 +981,32 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     }
                     if (pi.layer == 6 && dest >= 0)   // 1x1 conv 128->1 plus the per-square bias
                         logit[board * 81 + sq] = hsum + __ldg(reinterpret_cast<const float *>(blob + BK_W_HEADB_OFF) + sq);
-                }
-                // Hand-over only when every MMA of the pass is complete (ACC[3] completes with the last tile).  Measured on the
-                // B200 (tools/gpu_r02q.sh, profiles/r02_handover_experiments.md): letting the early tiles ARRIVE while MMAs of their
-                // own pass were still in flight corrupted between 1 in 150 and 1 in 12,000 cold-L2 launches (boards 2-3 of a CTA's
-                // first item), with a relaxed arrive (BK_HANDOVER=1) and, less often, with a cluster-scope release (=3); the early
-                // read-out, the early in-place stores and even the early proxy fence are clean as long as the arrive waits (=2,
-                // and this form: 0).  No access that becomes concurrent explains it, so the rule is kept as measured: no arrive
-                // on the hand-over barrier while the pair's tensor cores are running this pass.
-#if BK_HANDOVER == 0
-                if (own_tile && wq != 3) mbar_wait(sBar + 8 * (BAR_ACC + 3), pass & 1u, 0x680u + pass);
+#ifdef BK_TRACE
+                    if (g_trace && pass < TRACE_PASSES)   // (rows that are no square read past the operand buffers: not deterministic, never used)
+                        g_trace[((size_t)blockIdx.x * TRACE_PASSES + pass) * 512 + threadIdx.x] = dest >= 0 ? trace_h : 0u;
 #endif
-                // this pass's TMEM reads are complete and the operand writes are visible to the tensor core
+                }
+                // Hand-over: this group's TMEM reads are complete and its operand rows are visible to the tensor core; the group
+                // arrives as soon as its own tile is done -- the leader starts the next pass when all 32 warps of the pair have.
+                // Root cause of round 1's corrupted launches (1 cold-L2 launch in 150 ... 12,000, always 32-row blocks of tile 2
+                // in a CTA's first item; tools/trace_handover.py, profiles/r02_handover_experiments.md): there, a group without a
+                // tile waited on ACC[3] instead of its own barrier.  In the first item layer 0 runs as passes of 3 and 2 tiles, so
+                // group 2 waited ACC[2] (parity 0), ACC[3] (parity 1), ACC[2] (parity 0).  With a cold L2 the issuing thread can
+                // stall for a microsecond on an instruction fetch BETWEEN the commits of ACC[2] and ACC[3] of pass 0; a warp of
+                // group 2 that had finished its read-out in the meantime found ACC[3] still in phase 0, for which a parity-1 wait
+                // succeeds at once, "finished" pass 1, found ACC[2] in phase 1, for which a parity-0 wait succeeds at once, and
+                // ran pass 2's read-out -- stale TMEM into 32 rows of the operand, two extra arrives -- before pass 1 had started.
+                // Waiting for ACC[3] before the arrive (round 2's first fix, BK_HANDOVER=2) hid it because every warp then
+                // consumed every phase of ACC[3]; waiting on the own barrier only removes it.
+#if BK_HANDOVER == 2   // measurement build: the hand-over waits for the whole pass
+                if (wq != 3) mbar_wait(sBar + 8 * (BAR_ACC + 3), pass & 1u, 0x680u + pass);
+#endif
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();
-#if BK_HANDOVER == 2
-                if (own_tile && wq != 3) mbar_wait(sBar + 8 * (BAR_ACC + 3), pass & 1u, 0x680u + pass);
-#endif
                 if (lane == 0) {
                     __threadfence_block();     // the warp's stores are performed before the (relaxed) arrive can be observed
-#if BK_HANDOVER == 3
-                    mbar_arrive_cluster(leader_act);
-#else
                     mbar_arrive_cluster_relaxed(leader_act);
-#endif
                 }
                 if (prof) args.prof[pass * 4 + 3] = clock64();
                 if (pi.layer == 6) {
@@ -1276,6 +1294,14 @@ static int weight_maps(FwdDeviceState &ds, const void *blob, CUtensorMap *stage,
     *stage = victim->stage; *bias = victim->bias;
     return 0;
 }
+
+#ifdef BK_TRACE
+// measurement build: device buffer of n_blocks x 24 passes x 512 words (or null to switch the trace off)
+extern "C" int bk_debug_trace(unsigned int *dev_buf)
+{
+    return cudaMemcpyToSymbol(g_trace, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int bk_debug_words(unsigned int *out8)
 {
