@@ -68,6 +68,9 @@ constexpr int N_STAGES = 6;                        // 48 KiB weight ring
 #ifndef BK_HANDOVER
 #define BK_HANDOVER 0                              // 1, 2 = measurement builds (see the epilogue)
 #endif
+#ifndef BK_HEAD_PER_TILE
+#define BK_HEAD_PER_TILE 1                         // 0 = measurement build: every pass waits for the whole hand-over of the previous one
+#endif
 #ifndef BK_TAIL
 #define BK_TAIL 3                                  // stages at the end of a pass that are issued tile by tile
 #endif
@@ -81,7 +84,8 @@ constexpr int OFF_W = OFF_F + F_BYTES;
 constexpr int OFF_BIASW = OFF_W + N_STAGES * CTA_STAGE_BYTES;
 constexpr int OFF_ONES = OFF_BIASW + CTA_BIAS_BYTES;
 constexpr int OFF_BAR = OFF_ONES + ONES_BYTES;     // barriers, 8 B each
-constexpr int OFF_TMEM = OFF_BAR + 192;
+constexpr int BAR_BYTES = 208;
+constexpr int OFF_TMEM = OFF_BAR + BAR_BYTES;
 constexpr int OFF_LOGIT = OFF_TMEM + 16;           // float[5][81]: head output per square
 constexpr int OFF_RES = OFF_LOGIT + 1664;          // PLAYOUT: resident positions of the item's boards (BkResident[5])
 constexpr int SMEM_BYTES = OFF_RES + 240 + 128;    // 232,384 (ENCODE: logit area + resident area + tail = one group table, see below)
@@ -101,12 +105,13 @@ static_assert(OFF_W % 128 == 0 && OFF_ONES % 128 == 0 && OFF_BIASW % 128 == 0, "
 // WFULL (leader): both CTAs' halves of a stage have landed -- each CTA's tensor-map copy (cta_group::2) reports its
 // bytes to the LEADER's barrier.  WEMPTY: the pair's MMAs that read the stage are complete.  BFULL / BEMPTY: the same for
 // the layer's bias rows (single slot).  ACC[t]: accumulator tile t of the pass complete (the last stages of a pass are issued
-// tile by tile, so the read-out of the first tiles runs under the MMAs of the last).  ACT (leader): both CTAs' epilogues done.
+// tile by tile, so the read-out of the first tiles runs under the MMAs of the last).  ACT[t] (leader): the warp groups of tile t
+// of both CTAs have read their accumulators out and rewritten their rows.
 // FFULL / PFFULL (leader) / FEMPTY: the same for the feature planes of an item (the peer forwards its FFULL to the
 // leader's PFFULL, once per item).
-enum { BAR_WFULL = 0, BAR_WEMPTY = N_STAGES, BAR_BFULL = 2 * N_STAGES, BAR_BEMPTY, BAR_ACC, BAR_ACT = BAR_ACC + 4, BAR_FFULL,
-       BAR_PFFULL, BAR_FEMPTY, N_BARS };
-static_assert(N_BARS * 8 <= 192, "barrier area");
+enum { BAR_WFULL = 0, BAR_WEMPTY = N_STAGES, BAR_BFULL = 2 * N_STAGES, BAR_BEMPTY, BAR_ACC, BAR_ACT = BAR_ACC + 4,
+       BAR_FFULL = BAR_ACT + 4, BAR_PFFULL, BAR_FEMPTY, N_BARS };
+static_assert(N_BARS * 8 <= BAR_BYTES, "barrier area");
 
 // the conv weights of a blob seen as a 2-D tensor of 512-byte rows (256 fp16): one CTA's half of a stage = 16 rows,
 // its half of the bias rows = 4 rows (a second tensor map with a smaller box)
@@ -534,7 +539,6 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
     const uint32_t s_base = smem_u32(smem);
     const uint32_t sA = s_base + OFF_A, sF = s_base + OFF_F, sW = s_base + OFF_W, sBar = s_base + OFF_BAR;
     float *logit = reinterpret_cast<float *>(smem + OFF_LOGIT);
-    const uint32_t sAct = sBar + 8 * BAR_ACT;
     const int rank = (int)cluster_ctarank();           // 0 = leader (issues the pair's MMAs), 1 = peer
     const int pair0 = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     constexpr bool PLAYOUT = MODE == 1, ENCODE = MODE == 2;
@@ -559,7 +563,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         mbar_init(sBar + 8 * BAR_BFULL, 1);
         mbar_init(sBar + 8 * BAR_BEMPTY, 1);
         for (int t = 0; t < 4; ++t) mbar_init(sBar + 8 * (BAR_ACC + t), 1);
-        mbar_init(sAct, 2 * N_EPI_WARPS);
+        for (int t = 0; t < 4; ++t) mbar_init(sBar + 8 * (BAR_ACT + t), 2 * (N_EPI_WARPS / 4));
         mbar_init(sBar + 8 * BAR_FFULL, 1);
         mbar_init(sBar + 8 * BAR_PFFULL, 1);
         mbar_init(sBar + 8 * BAR_FEMPTY, 1);
@@ -669,6 +673,8 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         long long tw = 0, tp = 0, ti = 0;                  // diagnostic: cycles waiting for weights / bias rows, issuing
         const bool profiling = !PLAYOUT && args.prof != nullptr && blockIdx.x == 0;
         constexpr int TAIL = PLAYOUT ? BK_TAIL_PLAYOUT : BK_TAIL;   // stages at the end of a pass that are issued tile by tile
+        constexpr int HEAD = 2;                            // stages at the start of a pass that are issued tile by tile (tap 0)
+        static_assert(HEAD + TAIL < N_STAGES, "head and tail slots are held across all tiles: leave ring slots to prefetch into");
         static_assert(TAIL >= 1 && TAIL <= 5, "the tail may only hold taps with non-negative row shifts, and must leave ring slots free");
         // A windows of stage s of a pass (descriptor words of the pass's first tile): K steps 0, 1 at w.x, w.x + w.z and K steps
         // 2, 3 at w.y, w.y + w.z; nk = how many of the four exist
@@ -723,12 +729,50 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                 const Pass pi = pass_info(pair_nb, ps);
                 n_tiles = pi.n_tiles;
                 half_tile = half_last_tile<PLAYOUT>(pair_nb, pi);
-                if (pass > 0) mbar_wait(sAct, (pass - 1) & 1u, 0x400u + pass);   // operands written, TMEM drained
-                tc_fence_after();
-                if (!PLAYOUT && args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) args.prof[pass * 4 + 0] = clock64();
                 const int S = n_stages_of(pi.layer);
-                // ---- all but the last TAIL stages: stage by stage, every tile uses the stage before its slot is handed back
-                for (int s2 = 0; s2 < S - TAIL; ++s2) {
+                // ---- the first HEAD stages (tap 0, row shift -11: tile t reads rows 128 t - 11 .. 128 t + 116): tile by tile.
+                //      Between two 3x3 layers tile t starts as soon as the groups of tiles <= t have handed over (ACT[t]) -- the
+                //      read-out of the previous pass's last tile then runs under the head of tiles 0..2.  Everywhere else (layer
+                //      0 reads another buffer and writes this one through another raster; a new item) the pass waits for all four.
+                //      The issuing thread consumes every phase of every ACT[t]: all four are waited for in every pass.
+                {
+                    const bool per_tile = BK_HEAD_PER_TILE && pass > 0 && pi.layer >= 2;
+                    if (pass > 0 && !per_tile) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) mbar_wait(sBar + 8 * (BAR_ACT + t), (pass - 1) & 1u, 0x400u + pass);
+                    }
+                    uint32_t slot[HEAD];
+                    uint3 w[HEAD];
+                    int nk[HEAD];
+#pragma unroll
+                    for (int r = 0; r < HEAD; ++r) {
+                        slot[r] = st;
+                        mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x520u + st);
+                        if (++st == N_STAGES) { st = 0; ph ^= 1u; }
+                        w[r] = windows(pi, r, nk[r]);
+                    }
+                    tc_fence_after();
+                    if (!PLAYOUT && args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) args.prof[pass * 4 + 0] = clock64();
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        if (per_tile) {              // (tiles the pass does not have: their groups arrive with the others)
+                            mbar_wait(sBar + 8 * (BAR_ACT + t), (pass - 1) & 1u, 0x440u + pass);
+                            tc_fence_after();
+                        }
+                        if (t < n_tiles && elect_one()) {
+#pragma unroll
+                            for (int r = 0; r < HEAD; ++r) issue(w[r], nk[r], slot[r], t, t + 1, r != 0);
+                        }
+                        __syncwarp();
+                    }
+                    if (elect_one()) {
+#pragma unroll
+                        for (int r = 0; r < HEAD; ++r) umma_commit_pair(sBar + 8 * (BAR_WEMPTY + slot[r]));
+                    }
+                    __syncwarp();
+                }
+                // ---- the middle stages: stage by stage, every tile uses the stage before its slot is handed back
+                for (int s2 = HEAD; s2 < S - TAIL; ++s2) {
                     long long c0 = 0, c1 = 0;
                     if (profiling) c0 = clock64();
                     mbar_wait(sBar + 8 * (BAR_WFULL + st), ph, 0x500u + st);
@@ -737,7 +781,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     int nk;
                     const uint3 w = windows(pi, s2, nk);
                     if (elect_one()) {
-                        issue(w, nk, st, 0, n_tiles, s2 != 0);
+                        issue(w, nk, st, 0, n_tiles, 1u);
                         umma_commit_pair(sBar + 8 * (BAR_WEMPTY + st));   // stage consumed -> both producers may refill
                     }
                     __syncwarp();
@@ -793,7 +837,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         // =========================== epilogue warps (both CTAs, each on its own rows) ===========================
         const int quad = warp & 3, wq = warp >> 2;
         const uint32_t t_lane = tmem + ((uint32_t)(32 * quad) << 16);
-        const uint32_t leader_act = mapa(sAct, 0);
+        const uint32_t leader_act = mapa(sBar + 8 * (BAR_ACT + wq), 0);
         // PLAYOUT: "the planes of the next move are in place in this CTA" -- the leader's own FFULL, or, from the peer, straight
         // onto the leader's PFFULL (a relaxed arrive behind the proxy fences and the barrier of the 16 warps, like the pass
         // hand-over; no tensor work is in flight here; the forwarding warp's release.cluster round trip cost 1.4 k cycles a move)
