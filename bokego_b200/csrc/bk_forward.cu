@@ -69,7 +69,7 @@ constexpr int N_STAGES = 6;                        // 48 KiB weight ring
 #define BK_HANDOVER 0                              // 1, 2 = measurement builds (see the epilogue)
 #endif
 #ifndef BK_HEAD_PER_TILE
-#define BK_HEAD_PER_TILE 1                         // 0 = measurement build: every pass waits for the whole hand-over of the previous one
+#define BK_HEAD_PER_TILE 1                         // measurement builds: 0 = every pass waits for the whole hand-over of the previous one, 2 = per tile between 3x3 layers only
 #endif
 #ifndef BK_TAIL
 #define BK_TAIL 3                                  // stages at the end of a pass that are issued tile by tile
@@ -732,11 +732,14 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                 const int S = n_stages_of(pi.layer);
                 // ---- the first HEAD stages (tap 0, row shift -11: tile t reads rows 128 t - 11 .. 128 t + 116): tile by tile.
                 //      Between two 3x3 layers tile t starts as soon as the groups of tiles <= t have handed over (ACT[t]) -- the
-                //      read-out of the previous pass's last tile then runs under the head of tiles 0..2.  Everywhere else (layer
-                //      0 reads another buffer and writes this one through another raster; a new item) the pass waits for all four.
+                //      read-out of the previous pass's last tile then runs under the head of tiles 0..2.  Layer 0 reads the
+                //      feature planes, so its tile t only needs accumulator slot t back: a new item starts under the head
+                //      computation of the previous item's last layer, the second pass of layer 0 under the read-out of the first
+                //      (groups whose slot this pass does not use are waited for after the middle stages).  Layer 1 reads what
+                //      layer 0 wrote through another raster and waits for all four.
                 //      The issuing thread consumes every phase of every ACT[t]: all four are waited for in every pass.
+                const bool per_tile = BK_HEAD_PER_TILE && pass > 0 && (BK_HEAD_PER_TILE == 2 ? pi.layer >= 2 : pi.layer != 1);
                 {
-                    const bool per_tile = BK_HEAD_PER_TILE && pass > 0 && pi.layer >= 2;
                     if (pass > 0 && !per_tile) {
 #pragma unroll
                         for (int t = 0; t < 4; ++t) mbar_wait(sBar + 8 * (BAR_ACT + t), (pass - 1) & 1u, 0x400u + pass);
@@ -755,7 +758,7 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     if (!PLAYOUT && args.prof && blockIdx.x == 0 && pass < 64 && lane == 0) args.prof[pass * 4 + 0] = clock64();
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        if (per_tile) {              // (tiles the pass does not have: their groups arrive with the others)
+                        if (per_tile && t < n_tiles) {
                             mbar_wait(sBar + 8 * (BAR_ACT + t), (pass - 1) & 1u, 0x440u + pass);
                             tc_fence_after();
                         }
@@ -787,6 +790,12 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
                     __syncwarp();
                     if (profiling) ti += clock64() - c1;
                     if (++st == N_STAGES) { st = 0; ph ^= 1u; }
+                }
+                if (per_tile) {       // the groups of the previous pass whose accumulator slot this pass does not use
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (t >= n_tiles) mbar_wait(sBar + 8 * (BAR_ACT + t), (pass - 1) & 1u, 0x480u + pass);
+                    tc_fence_after();
                 }
                 // ---- the last TAIL stages and the bias rows (x the all-ones operand: one K step, every row of the ones operand is
                 //      the same): tile by tile, so that tile t is complete (ACC[t]) while the tiles behind it are still running and

@@ -7,7 +7,7 @@ for rep in 1 2 3; do timeout 400 python tools/stress_forward.py --iters 8000 --b
 timeout 400 python tools/stress_forward.py --iters 3000 --batches 745,4096,37,16 --max-bad 100000 --quiet >> gpurun_out/r02aa_stress.txt 2>&1
 cat gpurun_out/r02aa_stress.txt
 for rep in 1 2 3; do
-  for v in base pt0 -; do
+  for v in base pt2 -; do
     so=$D/libbokego_b200$([ "$v" = "-" ] || echo _$v).so
     BOKEGO_B200_SO=$so timeout 300 python tools/time_forward_sizes.py 740 4096 2>&1 | cut -c1-200 | sed "s/^/$v /"
     BOKEGO_B200_SO=$so timeout 300 python tools/bench_playout.py 512 4096 2>&1 | cut -c1-160 | sed "s/^/$v /"
