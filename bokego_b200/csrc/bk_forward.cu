@@ -71,6 +71,9 @@ constexpr int N_STAGES = 6;                        // 48 KiB weight ring
 #ifndef BK_HEAD_PER_TILE
 #define BK_HEAD_PER_TILE 1                         // measurement builds: 0 = every pass waits for the whole hand-over of the previous one, 2 = per tile between 3x3 layers only
 #endif
+#ifndef BK_HEAD
+#define BK_HEAD 2                                  // stages at the start of a pass that are issued tile by tile
+#endif
 #ifndef BK_TAIL
 #define BK_TAIL 3                                  // stages at the end of a pass that are issued tile by tile
 #endif
@@ -673,7 +676,8 @@ bk_forward_tc_kernel(const __grid_constant__ FwdArgs args, const __grid_constant
         long long tw = 0, tp = 0, ti = 0;                  // diagnostic: cycles waiting for weights / bias rows, issuing
         const bool profiling = !PLAYOUT && args.prof != nullptr && blockIdx.x == 0;
         constexpr int TAIL = PLAYOUT ? BK_TAIL_PLAYOUT : BK_TAIL;   // stages at the end of a pass that are issued tile by tile
-        constexpr int HEAD = 2;                            // stages at the start of a pass that are issued tile by tile (tap 0)
+        constexpr int HEAD = BK_HEAD;                      // stages at the start of a pass that are issued tile by tile (tap 0)
+        static_assert(HEAD >= 1 && HEAD <= 8, "the head may only hold taps with negative row shifts (taps 0..3)");
         static_assert(HEAD + TAIL < N_STAGES, "head and tail slots are held across all tiles: leave ring slots to prefetch into");
         static_assert(TAIL >= 1 && TAIL <= 5, "the tail may only hold taps with non-negative row shifts, and must leave ring slots free");
         // A windows of stage s of a pass (descriptor words of the pass's first tile): K steps 0, 1 at w.x, w.x + w.z and K steps
