@@ -572,7 +572,7 @@ __global__ void bk_adamw_kernel(float *p, const float *g, float *m, float *v, si
 
 // ---- workspace (floats) ----
 struct Ws {
-    size_t x0, z[7], a[7], mean[7], rstd[7], da, dz, logits, dlogit, part, dwpart, wd, wpack, wpack_lo, wdpack, wdpack_lo, wpart, total;
+    size_t x0, z[7], a[7], mean[7], rstd[7], da, dz, logits, dlogit, part, dwpart, wd, wpack, wpack_lo, wdpack, wdpack_lo, wpart, tail, total;
     int splits, rows_per_split;
 };
 
@@ -612,6 +612,7 @@ Ws ws_layout(int P)
     w.splits = splits;
     w.rows_per_split = rps;
     w.wpart = take((size_t)splits * 9 * C * C);
+    w.tail = take((size_t)BK_CONV3_TAIL_FLOATS);    // partial results of the split tail of the staged-once 3x3 kernel
     w.total = o;
     return w;
 }
@@ -669,8 +670,9 @@ extern "C" size_t bk_train_workspace_bytes(int P) { return P <= 0 ? 0 : ws_layou
 extern "C" int bk_train_launches(int which, int P, int prec)
 {
     const int tc = prec >= 4 ? 1 : 0;                               // the tcgen05 path repacks the weights once per call
-    if (which == 0) return 1 + tc + 7 * 2 + 1 + (tc && P <= SPLIT_MAX_P ? 6 : 0);
-    return 1 + tc + 1 + 2 + 7 * 4 + 6;
+    const int tail = tc && P > SPLIT_MAX_P && !getenv("BK_TC_OLD_CONV") && bk_tc_conv3_tail(P) > 0 ? 6 : 0;   // one more launch per 3x3 conv: its split tail
+    if (which == 0) return 1 + tc + 7 * 2 + 1 + (tc && P <= SPLIT_MAX_P ? 6 : 0) + tail;
+    return 1 + tc + 1 + 2 + 7 * 4 + 6 + (tc && !getenv("BK_TC_OLD_CONV") && bk_tc_conv3_tail(P) > 0 ? 6 : 0);
 }
 
 extern "C" int bk_train_forward(const float *params, const float *running, const uint8_t *planes_u8, int P, int bn_mode, int prec,
@@ -697,6 +699,7 @@ extern "C" int bk_train_forward(const float *params, const float *running, const
         a.R = l == 0 ? 5 : 3;
         a.sign = 1;
         a.ksplit = (prec >= 4 && l > 0 && P <= SPLIT_MAX_P) ? 4 : 1;
+        a.tail_part = ws + w.tail;
         launch_conv(a, prec, st);
         if (a.ksplit > 1) {
             const size_t n4 = (size_t)P * NSQ * C / 4;
@@ -757,6 +760,7 @@ extern "C" int bk_train_backward(const float *params, const int16_t *moves, cons
             a.R = 3;
             a.sign = -1;
             a.ksplit = 1;
+            a.tail_part = ws + w.tail;
             launch_conv(a, prec, st);
         }
     }

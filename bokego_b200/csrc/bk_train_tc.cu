@@ -26,6 +26,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "bk_train_args.h"
 
 namespace {
@@ -472,27 +474,46 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
 // sits at row 100 p + 10 + 10 x + y -- ten zero rows above every board, one zero column to its right -- so a tap (dx, dy) is the row
 // shift 10 dx + dy of ONE staged operand, exactly as in the inference kernel, and zero padding comes from the zero rows / column.
 // A CTA owns 128 consecutive raster rows: it gathers rows R0 - 11 .. R0 + 138 (all 128 channels) once -- 4,800 16-byte chunks
-// instead of the 36,864 of nine separate window gathers -- in four channel groups of 32 that the MMAs follow group by group, so the
-// staging of groups 1-3 runs under the MMAs of group 0; after that only the pre-split weight slabs stream (one bulk copy each).
+// instead of the 36,864 of nine separate window gathers -- in four channel groups of 32 that the MMAs follow group by group; after
+// that only the pre-split weight slabs stream (one bulk copy each).
+// Round 2 (profiles/r02n_train_conv3.md):
+//   * the channel groups go through TWO rotating group buffers (group g + 2 is staged when the MMAs of group g have finished),
+//     which leaves room for FOUR weight stages instead of two in 3xTF32 mode: with two, a refill could only be asked for when the
+//     slab before the previous one had been consumed, and the L2 round trip of a 32 KiB slab (longer than the slab's 12 MMAs) was
+//     exposed on every other slab (1,590 cycles per slab against 768 of tensor time);
+//   * the accumulation chains are split by magnitude.  What the tensor core's truncating fp32 accumulation costs is one ulp of the
+//     ACCUMULATOR per MMA, so only the hi * hi products need short chains; lo * hi and hi * lo are 2^-11 of them and accumulate over
+//     the whole K loop in an accumulator of their own (one read-out per tile, its truncation 2^-11 of an ulp of the result).  A
+//     hi * hi chain is BK_R3_CHAIN_SLABS slabs = 12 MMAs -- as many accumulations as the 12-MMA chains measured equivalent to
+//     one-K-step chains -- so the result warps read TMEM (64 KiB per read-out at 64 B/clk: 1,024 cycles) 13 times per tile
+//     instead of 36.
 // 81 of every 100 raster rows are real squares; the result threads write those to the dense [P][81][128] output.
 // Warps: 0-3 result (thread = raster row), 4-7 staging, 8 MMA issue, 9 weight loader (one thread).
 // ------------------------------------------------------------------------------------------------------------------------------
 constexpr int R3_ROWS = 152;                       // staged rows: 128 + 2 * 11 halo, rounded up to 8
 constexpr int R3_LBO = R3_ROWS * 16;               // bytes between K chunks of the staged tile
-constexpr int R3_A_BYTES = 32 * R3_LBO;            // one part (hi or lo) of the tile: 77,824
+constexpr int R3_G_BYTES = 8 * R3_LBO;             // one part (hi or lo) of one channel group of the tile: 19,456
 constexpr int R3_THREADS = 320;
+constexpr int R3_NROT = 3;                         // accumulators 0..2 rotate through the hi * hi chains, accumulator 3 holds the lo products
+#ifndef BK_R3_CHAIN_SLABS
+#define BK_R3_CHAIN_SLABS 3                        // slabs per hi * hi chain (4 MMAs each)
+#endif
+#ifndef BK_R3_ABUFS
+#define BK_R3_ABUFS 4                              // group buffers: 4 = the whole tile is staged up front, 2 = rotating (measurement build)
+#endif
 template <int PREC>
 struct R3 {
-    static constexpr int NW = PREC ? 2 : 6;                          // weight stages
+    static constexpr int NA = BK_R3_ABUFS;                           // group buffers
+    static constexpr int NW = PREC ? (NA == 2 ? 4 : 2) : 6;          // weight stages
     static constexpr int W_STAGE = (PREC ? 2 : 1) * 16384;           // B_hi (, B_lo) of a 32-deep slab
-    static constexpr int A_BYTES = (PREC ? 2 : 1) * R3_A_BYTES;
+    static constexpr int ABUF = (PREC ? 2 : 1) * R3_G_BYTES;         // one group buffer: A_hi (, A_lo)
+    static constexpr int A_BYTES = NA * ABUF;
     static constexpr int SMEM = A_BYTES + NW * W_STAGE + 256;
-    // K steps per accumulation chain: one slab (12 MMAs in 3xTF32).  Measured on the recorded reference iteration: as accurate as one
-    // K step per chain (1e-6 against FFMA) and 18 % faster -- with the staging gone, the chain hand-shakes were what was left
-    static constexpr int CHAIN = 4;
+    static constexpr int CHAIN = BK_R3_CHAIN_SLABS;
 };
-enum { R3_AFULL = 0, R3_WFULL = 4, R3_WEMPTY = 4 + MAX_STAGES, R3_ACCF = 4 + 2 * MAX_STAGES, R3_ACCE = R3_ACCF + NBUF,
+enum { R3_AFULL = 0, R3_AEMPTY = 4, R3_WFULL = 6, R3_WEMPTY = 6 + MAX_STAGES, R3_ACCF = 6 + 2 * MAX_STAGES, R3_ACCE = R3_ACCF + NBUF,
        R3_NBARS = R3_ACCE + NBUF };
+static_assert(8 * R3_NBARS + 4 <= 256, "barrier area");
 
 template <int PREC>
 __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const BkConvArgs a)
@@ -506,13 +527,25 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
     const uint32_t s_tmem = s_bar + 8 * R3_NBARS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int P = a.M / NSQ;
-    const int R0 = blockIdx.x * 128;               // first raster row of this tile
-    const int g_lo = a.ksplit > 1 ? (int)blockIdx.y : 0, g_hi = a.ksplit > 1 ? g_lo + 1 : 4;   // channel groups of this CTA
-    const int KT = (g_hi - g_lo) * 9;               // slabs: channel groups x 9 taps
-    const int n_chains = KT * 4 / CHAIN;
+    int tile = blockIdx.x, g_lo = 0, g_hi = 4;     // the tile and the channel groups of this CTA
+    if (a.ksplit > 1) {
+        g_lo = blockIdx.y;
+        g_hi = g_lo + 1;
+    } else if (a.tail_full > 0 && tile >= a.tail_full) {       // split tail: four CTAs per left-over tile
+        const int t = tile - a.tail_full;
+        tile = a.tail_full + (t >> 2);
+        g_lo = t & 3;
+        g_hi = g_lo + 1;
+    }
+    const bool tail = a.ksplit == 1 && a.tail_full > 0 && tile >= a.tail_full;
+    const int R0 = tile * 128;                     // first raster row of this tile
+    const int n_groups = g_hi - g_lo;
+    const int KT = n_groups * 9;                    // slabs: channel groups x 9 taps
+    const int n_chains = (KT + CHAIN - 1) / CHAIN;
 
     if (tid == 0) {
         for (int g = 0; g < 4; ++g) mbar_init(s_bar + 8 * (R3_AFULL + g), 128);
+        for (int i = 0; i < 2; ++i) mbar_init(s_bar + 8 * (R3_AEMPTY + i), 1);
         for (int s = 0; s < NW; ++s) {
             mbar_init(s_bar + 8 * (R3_WFULL + s), 1);
             mbar_init(s_bar + 8 * (R3_WEMPTY + s), 1);
@@ -530,32 +563,36 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem + Z::A_BYTES + NW * W_STAGE + 8 * R3_NBARS);
 
     if (warp >= 4 && warp < 8) {
-        // =============================== staging of the activation tile ===============================
+        // =============================== staging of the activation tile, group by group ===============================
         const int pw = warp - 4, r8 = lane & 7, q4 = lane >> 3;
         for (int g = g_lo; g < g_hi; ++g) {
+            const int gi = g - g_lo;
+            const int abuf = (gi % Z::NA) * Z::ABUF;
+            // rotating buffers: free when the MMAs of the group two back have finished (each AEMPTY barrier completes once)
+            if (gi >= Z::NA) mbar_wait(s_bar + 8 * (R3_AEMPTY + (gi & 1)), 0);
             // a block = 8 rows x 4 K chunks; 19 row groups x 2 chunk halves per channel group of 8 chunks
             for (int b = pw; b < 38; b += 4) {
-                const int row = (b >> 1) * 8 + r8, kc = g * 8 + (b & 1) * 4 + q4;
+                const int row = (b >> 1) * 8 + r8, kl = (b & 1) * 4 + q4, kc = g * 8 + kl;
                 const int rr = R0 - 11 + row;                                  // raster row
                 const int p = rr >= 0 ? rr / 100 : -1;
                 const int o = rr - 100 * p - 10;                               // 10 x + y, negative in the zero rows above the board
                 const int x = o / 10, y = o - 10 * x;
                 const bool ok = rr >= 0 && p < P && o >= 0 && y < 9 && row < 150;
                 const float *src = ok ? a.in + ((size_t)(p * NSQ + 9 * x + y) * C + 4 * kc) : a.in;
-                cp_async16(s_base + (uint32_t)(kc * R3_LBO + row * 16), src, ok);
+                if (!(BK_TC_DIAG & 2)) cp_async16(s_base + (uint32_t)(abuf + kl * R3_LBO + row * 16), src, ok);
             }
             cp_commit();
             cp_wait<0>();
             if constexpr (PREC != 0) {
                 for (int b = pw; b < 38; b += 4) {
-                    const int row = (b >> 1) * 8 + r8, kc = g * 8 + (b & 1) * 4 + q4;
-                    float4 *hp = reinterpret_cast<float4 *>(smem + kc * R3_LBO + row * 16);
+                    const int row = (b >> 1) * 8 + r8, kl = (b & 1) * 4 + q4;
+                    float4 *hp = reinterpret_cast<float4 *>(smem + abuf + kl * R3_LBO + row * 16);
                     const float4 v = *hp;
                     float4 h, l;
                     h.x = tf32_cut(v.x); h.y = tf32_cut(v.y); h.z = tf32_cut(v.z); h.w = tf32_cut(v.w);
                     l.x = tf32_cut(v.x - h.x); l.y = tf32_cut(v.y - h.y); l.z = tf32_cut(v.z - h.z); l.w = tf32_cut(v.w - h.w);
                     *hp = h;
-                    *reinterpret_cast<float4 *>(smem + R3_A_BYTES + kc * R3_LBO + row * 16) = l;
+                    *reinterpret_cast<float4 *>(smem + abuf + R3_G_BYTES + kl * R3_LBO + row * 16) = l;
                 }
             }
             fence_proxy_async();
@@ -570,6 +607,10 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
                 const int g = g_lo + s / 9, tap = s % 9;
                 const int k0 = tap * C + 32 * g;
                 const uint32_t bar = s_bar + 8 * (R3_WFULL + st), dst = s_w + (uint32_t)(st * W_STAGE);
+                if (BK_TC_DIAG & 16) {
+                    mbar_arrive(bar);
+                    continue;
+                }
                 mbar_arrive_expect_tx(bar, (uint32_t)W_STAGE);
                 bulk_g2s(dst, a.w + (size_t)(k0 / 4) * (4 * C), 16384, bar);
                 if (PREC) bulk_g2s(dst + 16384, a.w_lo + (size_t)(k0 / 4) * (4 * C), 16384, bar);
@@ -577,48 +618,47 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
         }
     } else if (warp == 8) {
         // =============================== MMA issue ===============================
-        int c = 0;
+        int c = 0;                                      // hi * hi chain
         for (int s = 0; s < KT; ++s) {
             const int st = s % NW;
-            const int g = g_lo + s / 9, tap = s % 9;
-            if (tap == 0) mbar_wait(s_bar + 8 * (R3_AFULL + g), 0);
+            const int gi = s / 9, tap = s - 9 * gi;
+            const bool first = s % CHAIN == 0, last = s % CHAIN == CHAIN - 1 || s == KT - 1;
+            const int b = c % R3_NROT;
+            if (tap == 0) mbar_wait(s_bar + 8 * (R3_AFULL + g_lo + gi), 0);
             mbar_wait(s_bar + 8 * (R3_WFULL + st), (s / NW) & 1);
+            if (first) mbar_wait(s_bar + 8 * (R3_ACCE + b), ((c / R3_NROT) & 1) ^ 1);     // the result warps have read the chain three back
             tc_fence_after();
             if (elect_one()) {
                 const int ti = tap / 3;
                 const int shift = a.sign * (10 * (ti - 1) + (tap - 3 * ti - 1));
-                const uint32_t a0 = s_base + (uint32_t)((11 + shift) * 16), w0 = s_w + (uint32_t)(st * W_STAGE);
-                int cc = c;
+                const uint32_t a0 = s_base + (uint32_t)((gi % Z::NA) * Z::ABUF + (11 + shift) * 16), w0 = s_w + (uint32_t)(st * W_STAGE);
+                const uint32_t d = tmem + (uint32_t)(b * 128), dlo = tmem + (uint32_t)(R3_NROT * 128);
+                // the lo products of the slab first, then its hi * hi products: the tensor core changes accumulator twice per slab
+                // (alternating per K step cost 2 % against one accumulator per chain; profiles/r02n_train_conv3.md)
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const int b = cc % NBUF;
-                    const bool first = ks % CHAIN == 0;
-                    if (first) {
-                        mbar_wait(s_bar + 8 * (R3_ACCE + b), ((cc / NBUF) & 1) ^ 1);
-                        tc_fence_after();
-                    }
-                    const uint32_t d = tmem + (uint32_t)(b * 128);
-                    const uint32_t akc = (uint32_t)((8 * g + 2 * ks) * R3_LBO);
-                    const uint64_t ah = make_desc(a0 + akc, R3_LBO, (128u >> 4) | (1u << 14));
-                    const uint64_t al = make_desc(a0 + R3_A_BYTES + akc, R3_LBO, (128u >> 4) | (1u << 14));      // 3xTF32 only
-                    const uint64_t bh = make_desc(w0 + ks * 4096, 2048, (128u >> 4) | (1u << 14));
-                    const uint64_t bl = make_desc(w0 + 16384 + ks * 4096, 2048, (128u >> 4) | (1u << 14));
-                    if constexpr ((BK_TC_DIAG & 4) != 0) {
-                    } else if constexpr (PREC != 0) {
-                        umma_tf32(d, al, bh, IDESC_BASE, first ? 0u : 1u);
-                        umma_tf32(d, ah, bl, IDESC_BASE, 1u);
-                        umma_tf32(d, ah, bh, IDESC_BASE, 1u);
-                    } else {
-                        umma_tf32(d, ah, bh, IDESC_BASE, first ? 0u : 1u);
-                    }
-                    if (ks % CHAIN == CHAIN - 1) {
-                        umma_commit(s_bar + 8 * (R3_ACCF + b));
-                        ++cc;
+                for (int pass = PREC ? 0 : 1; pass < 2; ++pass) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t akc = (uint32_t)(2 * ks * R3_LBO);
+                        const uint64_t ah = make_desc(a0 + akc, R3_LBO, (128u >> 4) | (1u << 14));
+                        const uint64_t al = make_desc(a0 + R3_G_BYTES + akc, R3_LBO, (128u >> 4) | (1u << 14));      // 3xTF32 only
+                        const uint64_t bh = make_desc(w0 + ks * 4096, 2048, (128u >> 4) | (1u << 14));
+                        const uint64_t bl = make_desc(w0 + 16384 + ks * 4096, 2048, (128u >> 4) | (1u << 14));
+                        if constexpr ((BK_TC_DIAG & 4) != 0) {
+                        } else if (pass == 0) {
+                            umma_tf32(dlo, al, bh, IDESC_BASE, (s | ks) ? 1u : 0u);
+                            umma_tf32(dlo, ah, bl, IDESC_BASE, 1u);
+                        } else {
+                            umma_tf32(d, ah, bh, IDESC_BASE, (first && ks == 0) ? 0u : 1u);
+                        }
                     }
                 }
-                umma_commit(s_bar + 8 * (R3_WEMPTY + st));
+                umma_commit(s_bar + 8 * (R3_WEMPTY + st));                                   // slab consumed -> the loader may refill it
+                if (tap == 8 && gi + Z::NA < n_groups) umma_commit(s_bar + 8 * (R3_AEMPTY + (gi & 1)));   // group consumed -> its buffer may be restaged
+                if (last) umma_commit(s_bar + 8 * (R3_ACCF + b));                            // this chain is complete
+                if (PREC != 0 && s == KT - 1) umma_commit(s_bar + 8 * (R3_ACCF + R3_NROT));  // ... and so are the lo products
             }
-            c += 4 / CHAIN;
+            if (last) ++c;
             __syncwarp();
         }
     } else {
@@ -627,13 +667,15 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
 #pragma unroll
         for (int i = 0; i < C; ++i) acc[i] = 0.0f;
         const uint32_t t_lane = tmem + ((uint32_t)(32 * warp) << 16);
-        for (int c = 0; c < n_chains; ++c) {
-            const int b = c % NBUF;
-            mbar_wait(s_bar + 8 * (R3_ACCF + b), (c / NBUF) & 1);
+        for (int c = 0; c < n_chains + (PREC ? 1 : 0); ++c) {
+            const bool lo = c == n_chains;
+            const int b = lo ? R3_NROT : c % R3_NROT;
+            mbar_wait(s_bar + 8 * (R3_ACCF + b), lo ? 0 : (c / R3_NROT) & 1);
             tc_fence_after();
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
                 uint32_t v[32];
+                if (BK_TC_DIAG & 8) continue;
                 tmem_ld32(t_lane + (uint32_t)(b * 128 + h * 32), v);
                 tc_wait_ld();
 #pragma unroll
@@ -646,7 +688,10 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
         const int p = rr / 100, o = rr - 100 * p - 10;
         const int x = o / 10, y = o - 10 * x;
         if (p < P && o >= 0 && y < 9) {
-            float4 *out = reinterpret_cast<float4 *>(a.out + ((size_t)g_lo * (a.ksplit > 1 ? a.M : 0) + p * NSQ + 9 * x + y) * C);
+            // split tail: partial result [group][tail tile][row][128]; else the dense output (ksplit: one copy of it per group)
+            const int n_tail = (int)(gridDim.x - a.tail_full) >> 2;
+            float4 *out = tail ? reinterpret_cast<float4 *>(a.tail_part + ((size_t)(g_lo * n_tail + tile - a.tail_full) * 128 + 32 * warp + lane) * C)
+                               : reinterpret_cast<float4 *>(a.out + ((size_t)g_lo * (a.ksplit > 1 ? a.M : 0) + p * NSQ + 9 * x + y) * C);
 #pragma unroll
             for (int i = 0; i < C / 4; ++i) {
                 float4 v = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
@@ -666,7 +711,49 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
     }
 }
 
+// the split tail of bk_train_conv3_tc_kernel: out[real square of raster row row0 + r] = part[0][r] + part[1][r] + part[2][r] + part[3][r]
+__global__ void bk_train_conv3_tail_kernel(const float4 *__restrict__ part, float *__restrict__ out, int row0, int n_rows, int P)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = i >> 5, q = i & 31;
+    if (r >= n_rows) return;
+    const int rr = row0 + r;
+    const int p = rr / 100, o = rr - 100 * p - 10;
+    const int x = o / 10, y = o - 10 * x;
+    if (p >= P || o < 0 || y >= 9) return;
+    float4 v = part[(size_t)r * 32 + q];
+#pragma unroll
+    for (int g = 1; g < 4; ++g) {
+        const float4 u = part[((size_t)g * n_rows + r) * 32 + q];
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    reinterpret_cast<float4 *>(out + (size_t)(p * NSQ + 9 * x + y) * C)[q] = v;
+}
+
 }   // namespace
+
+// SM count of the current device (per device, queried once)
+static int bk_tc_sm_count()
+{
+    static std::mutex mu;
+    static int cached[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!cached[dev] && cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached[dev] = 0;
+    return cached[dev];
+}
+
+// The tiles left over after the last complete wave of the grid run as four quarter-length CTAs each when those fit beside each
+// other: returns the number of tiles that run whole (a multiple of the SM count), 0 = no split tail for P positions on this device.
+int bk_tc_conv3_tail(int P)
+{
+    static const bool off = getenv("BK_TC_NO_TAIL") != nullptr;      // measurement
+    const int n_tiles = (P * 100 + 127) / 128;
+    const int n_sm = bk_tc_sm_count();
+    const int full = n_sm > 0 ? n_tiles / n_sm * n_sm : 0, rest = n_tiles - full;
+    return (!off && full > 0 && rest > 0 && rest <= BK_CONV3_TAIL_MAX && 4 * rest <= n_sm) ? full : 0;
+}
 
 static bool getenv_old_conv()
 {
@@ -691,9 +778,17 @@ int bk_tc_set_attrs(void)
 void bk_tc_launch_conv(const BkConvArgs &a, int three_x, cudaStream_t st)
 {
     if (a.R == 3 && a.Cin == C && !getenv_old_conv()) {          // the 3x3 layers and their data gradients: tile staged once
-        const dim3 tiles((a.M / NSQ * 100 + 127) / 128, a.ksplit > 1 ? 4 : 1);
-        if (three_x) bk_train_conv3_tc_kernel<1><<<tiles, R3_THREADS, R3<1>::SMEM, st>>>(a);
-        else bk_train_conv3_tc_kernel<0><<<tiles, R3_THREADS, R3<0>::SMEM, st>>>(a);
+        const int n_tiles = (a.M / NSQ * 100 + 127) / 128;
+        dim3 tiles(n_tiles, a.ksplit > 1 ? 4 : 1);
+        BkConvArgs b = a;
+        b.tail_full = a.ksplit == 1 && a.tail_part ? bk_tc_conv3_tail(a.M / NSQ) : 0;
+        const int rest = n_tiles - b.tail_full;
+        if (b.tail_full > 0) tiles.x = b.tail_full + 4 * rest;
+        if (three_x) bk_train_conv3_tc_kernel<1><<<tiles, R3_THREADS, R3<1>::SMEM, st>>>(b);
+        else bk_train_conv3_tc_kernel<0><<<tiles, R3_THREADS, R3<0>::SMEM, st>>>(b);
+        if (b.tail_full > 0)
+            bk_train_conv3_tail_kernel<<<(rest * 128 * 32 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4 *>(a.tail_part), a.out,
+                                                                                       b.tail_full * 128, rest * 128, a.M / NSQ);
         return;
     }
     const int grid = (a.M + 127) / 128;

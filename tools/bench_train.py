@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--positions", type=int, nargs="+", default=[36, 576, 2048])
     ap.add_argument("--out", default=None)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--precs", type=int, nargs="+", default=[5, 4, 0, 1, 2])
+    ap.add_argument("--no-iterations", action="store_true", help="skip the whole reinforce() iterations")
     args = ap.parse_args()
     from bokego_b200 import reinforce as rf, batched as bk, nnet
     dev = torch.device("cuda", 0)
@@ -49,6 +51,8 @@ def main():
         moves = torch.randint(0, 81, (P,), device=dev).to(torch.int16)
         coef = torch.full((P,), 1.0 / 16, device=dev)
         for prec, name in ((5, "tc_3xtf32"), (4, "tc_tf32"), (0, "tf32"), (1, "3xtf32"), (2, "ffma")):
+            if prec not in args.precs:
+                continue
             tr = rf.PolicyTrainer(sd17, dev, prec=prec)
             f = timed(lambda: tr.forward(planes), args.iters)
             tr.forward(planes)
@@ -65,7 +69,7 @@ def main():
     opp.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd19.items()})
     pi.to(dev).train()
     opp.to(dev).eval()
-    for bs, acc in ((16, "reference"), (16, "batch"), (256, "batch")):
+    for bs, acc in (() if args.no_iterations else ((16, "reference"), (16, "batch"), (256, "batch"))):
         opt = torch.optim.AdamW(pi.parameters(), lr=1e-5)
         rf.reinforce(pi, opp, opt, "black", n_itrs=1, bs=bs, device=dev, stats=[], accumulate=acc)
         torch.cuda.synchronize()
