@@ -20,6 +20,7 @@ struct BkConvArgs {
                             loop), write their partial results here and bk_train_conv3_tail_kernel adds them in group order --
                             576 positions: 450 tiles on 148 SMs = three waves and a quarter instead of four. */
     int tail_full = 0;   /* set by bk_tc_launch_conv: tiles below this index run whole, 0 = no split tail */
+    int n_items = 0;     /* set by bk_tc_launch_conv: work items of the persistent CTAs (whole tiles + single-group items) */
 };
 #define BK_CONV3_TAIL_MAX 24                                  /* most tiles a split tail may have */
 #define BK_CONV3_TAIL_FLOATS (4 * BK_CONV3_TAIL_MAX * 128 * 128)

@@ -473,47 +473,88 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
 // kernel above asks for; profiles/r01h_tc_stage_breakdown.md).  GEMM rows are the rows of a padded raster: position p, square (x, y)
 // sits at row 100 p + 10 + 10 x + y -- ten zero rows above every board, one zero column to its right -- so a tap (dx, dy) is the row
 // shift 10 dx + dy of ONE staged operand, exactly as in the inference kernel, and zero padding comes from the zero rows / column.
-// A CTA owns 128 consecutive raster rows: it gathers rows R0 - 11 .. R0 + 138 (all 128 channels) once -- 4,800 16-byte chunks
-// instead of the 36,864 of nine separate window gathers -- in four channel groups of 32 that the MMAs follow group by group; after
-// that only the pre-split weight slabs stream (one bulk copy each).
-// Round 2 (profiles/r02n_train_conv3.md):
-//   * the channel groups go through TWO rotating group buffers (group g + 2 is staged when the MMAs of group g have finished),
-//     which leaves room for FOUR weight stages instead of two in 3xTF32 mode: with two, a refill could only be asked for when the
-//     slab before the previous one had been consumed, and the L2 round trip of a 32 KiB slab (longer than the slab's 12 MMAs) was
-//     exposed on every other slab (1,590 cycles per slab against 768 of tensor time);
+// A tile is 128 consecutive raster rows: rows R0 - 11 .. R0 + 138 (all 128 channels) are gathered once -- 4,800 16-byte chunks
+// instead of the 36,864 of nine separate window gathers -- in four channel groups of 32 that the MMAs follow group by group; beside
+// that only the pre-split weight slabs stream (one bulk copy each).  81 of every 100 raster rows are real squares; the result
+// threads write those to the dense [P][81][128] output.
+// Round 2 (profiles/r02q_train_conv3.md):
+//   * PERSISTENT CTAs, one per SM, each working through its tiles as ONE pipeline: with one tile per CTA (round 1) the prologue
+//     (barriers, TMEM allocation, the first group's gather, the first weight slabs) and the epilogue (last read-out, stores) of
+//     every tile were exposed -- 57 k cycles per tile against 28 k of tensor time, and switching the MMAs off saved only a third.
+//     Now all roles run loops over the CTA's work items with ring positions that carry over from item to item: the staging warps
+//     gather the first groups of the next tile into free group buffers (three rotating buffers) while the MMAs of the current one
+//     run, the weight loader never stops, and the result warps store tile t while the tensor pipe is in the first chains of t + 1;
 //   * the accumulation chains are split by magnitude.  What the tensor core's truncating fp32 accumulation costs is one ulp of the
 //     ACCUMULATOR per MMA, so only the hi * hi products need short chains; lo * hi and hi * lo are 2^-11 of them and accumulate over
-//     the whole K loop in an accumulator of their own (one read-out per tile, its truncation 2^-11 of an ulp of the result).  A
-//     hi * hi chain is BK_R3_CHAIN_SLABS slabs = 12 MMAs -- as many accumulations as the 12-MMA chains measured equivalent to
-//     one-K-step chains -- so the result warps read TMEM (64 KiB per read-out at 64 B/clk: 1,024 cycles) 13 times per tile
-//     instead of 36.
-// 81 of every 100 raster rows are real squares; the result threads write those to the dense [P][81][128] output.
+//     the whole item in an accumulator of their own (two, alternating from item to item).  A hi * hi chain is BK_R3_CHAIN_SLABS
+//     slabs = 12 MMAs -- as many accumulations as the 12-MMA chains measured equivalent to one-K-step chains -- so the result
+//     warps read TMEM (64 KiB per read-out at 64 B/clk) 13 times per tile instead of 36;
+//   * work items: whole tiles; for small batches (ksplit) one channel group of a tile each; and the tiles left over after the last
+//     full round of the grid as four channel-group items each (see BkConvArgs::tail_part).
 // Warps: 0-3 result (thread = raster row), 4-7 staging, 8 MMA issue, 9 weight loader (one thread).
+// Barrier rule (profiles/r02_handover_experiments.md): every waiter consumes every phase of the barriers it waits on -- ring
+// position and phase advance together, once per use, in every role.
 // ------------------------------------------------------------------------------------------------------------------------------
 constexpr int R3_ROWS = 152;                       // staged rows: 128 + 2 * 11 halo, rounded up to 8
 constexpr int R3_LBO = R3_ROWS * 16;               // bytes between K chunks of the staged tile
 constexpr int R3_G_BYTES = 8 * R3_LBO;             // one part (hi or lo) of one channel group of the tile: 19,456
 constexpr int R3_THREADS = 320;
-constexpr int R3_NROT = 3;                         // accumulators 0..2 rotate through the hi * hi chains, accumulator 3 holds the lo products
+constexpr int R3_NA = 3;                           // rotating group buffers
+constexpr int R3_NROT = 2;                         // accumulators 0, 1: the hi * hi chains in turn; 2, 3: the lo products of even / odd items
 #ifndef BK_R3_CHAIN_SLABS
 #define BK_R3_CHAIN_SLABS 3                        // slabs per hi * hi chain (4 MMAs each)
 #endif
-#ifndef BK_R3_ABUFS
-#define BK_R3_ABUFS 4                              // group buffers: 4 = the whole tile is staged up front, 2 = rotating (measurement build)
-#endif
 template <int PREC>
 struct R3 {
-    static constexpr int NA = BK_R3_ABUFS;                           // group buffers
-    static constexpr int NW = PREC ? (NA == 2 ? 4 : 2) : 6;          // weight stages
+    static constexpr int NW = PREC ? 3 : 6;                          // weight stages
     static constexpr int W_STAGE = (PREC ? 2 : 1) * 16384;           // B_hi (, B_lo) of a 32-deep slab
     static constexpr int ABUF = (PREC ? 2 : 1) * R3_G_BYTES;         // one group buffer: A_hi (, A_lo)
-    static constexpr int A_BYTES = NA * ABUF;
-    static constexpr int SMEM = A_BYTES + NW * W_STAGE + 256;
+    static constexpr int A_BYTES = R3_NA * ABUF;
+    static constexpr int SMEM = A_BYTES + NW * W_STAGE + 256 + 4 * 32 * 33 * 4;      // + the result warps' transposition buffers
     static constexpr int CHAIN = BK_R3_CHAIN_SLABS;
+    static_assert(SMEM <= 227 * 1024, "shared memory");
 };
-enum { R3_AFULL = 0, R3_AEMPTY = 4, R3_WFULL = 6, R3_WEMPTY = 6 + MAX_STAGES, R3_ACCF = 6 + 2 * MAX_STAGES, R3_ACCE = R3_ACCF + NBUF,
-       R3_NBARS = R3_ACCE + NBUF };
+enum { R3_AFULL = 0, R3_AEMPTY = R3_NA, R3_WFULL = 2 * R3_NA, R3_WEMPTY = R3_WFULL + MAX_STAGES, R3_ACCF = R3_WEMPTY + MAX_STAGES,
+       R3_ACCE = R3_ACCF + R3_NROT, R3_LOF = R3_ACCE + R3_NROT, R3_LOE = R3_LOF + 2, R3_NBARS = R3_LOE + 2 };
 static_assert(8 * R3_NBARS + 4 <= 256, "barrier area");
+
+#ifndef BK_R3_STORE
+#define BK_R3_STORE 2                              // measurement builds: 0 = no output stores, 1 = thread = row stores
+#endif
+#ifndef BK_R3_PROF
+#define BK_R3_PROF 0                               // measurement build: clock64 stamps of CTA 0 (tools/prof_train_conv3.py)
+#endif
+#if BK_R3_PROF
+__device__ long long g_r3_prof[3 * 1024];          // [role: MMA issue / weight loader / result][use < 256][4 stamps]
+#define R3_STAMP(role, idx, k) do { if (blockIdx.x == 0 && (idx) < 256) g_r3_prof[(role) * 1024 + (idx) * 4 + (k)] = clock64(); } while (0)
+#else
+#define R3_STAMP(role, idx, k) do {} while (0)
+#endif
+struct R3Ring {                                    // position in a ring of n buffers and the phase of its current use
+    int i;
+    uint32_t ph;
+    __device__ __forceinline__ void next(int n)
+    {
+        if (++i == n) {
+            i = 0;
+            ph ^= 1u;
+        }
+    }
+};
+struct R3Item { int tile, g_lo, ng, kind; };       // kind: 0 = whole tile, 1 = one group of a small batch (ksplit), 2 = one group of a tail tile
+__device__ __forceinline__ R3Item r3_item(const BkConvArgs &a, int it)
+{
+    R3Item w;
+    if (a.ksplit > 1) {
+        w.tile = it >> 2; w.g_lo = it & 3; w.ng = 1; w.kind = 1;
+    } else if (a.tail_full > 0 && it >= a.tail_full) {
+        const int t = it - a.tail_full;
+        w.tile = a.tail_full + (t >> 2); w.g_lo = t & 3; w.ng = 1; w.kind = 2;
+    } else {
+        w.tile = it; w.g_lo = 0; w.ng = 4; w.kind = 0;
+    }
+    return w;
+}
 
 template <int PREC>
 __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const BkConvArgs a)
@@ -527,187 +568,259 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
     const uint32_t s_tmem = s_bar + 8 * R3_NBARS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int P = a.M / NSQ;
-    int tile = blockIdx.x, g_lo = 0, g_hi = 4;     // the tile and the channel groups of this CTA
-    if (a.ksplit > 1) {
-        g_lo = blockIdx.y;
-        g_hi = g_lo + 1;
-    } else if (a.tail_full > 0 && tile >= a.tail_full) {       // split tail: four CTAs per left-over tile
-        const int t = tile - a.tail_full;
-        tile = a.tail_full + (t >> 2);
-        g_lo = t & 3;
-        g_hi = g_lo + 1;
-    }
-    const bool tail = a.ksplit == 1 && a.tail_full > 0 && tile >= a.tail_full;
-    const int R0 = tile * 128;                     // first raster row of this tile
-    const int n_groups = g_hi - g_lo;
-    const int KT = n_groups * 9;                    // slabs: channel groups x 9 taps
-    const int n_chains = (KT + CHAIN - 1) / CHAIN;
 
     if (tid == 0) {
-        for (int g = 0; g < 4; ++g) mbar_init(s_bar + 8 * (R3_AFULL + g), 128);
-        for (int i = 0; i < 2; ++i) mbar_init(s_bar + 8 * (R3_AEMPTY + i), 1);
-        for (int s = 0; s < NW; ++s) {
-            mbar_init(s_bar + 8 * (R3_WFULL + s), 1);
-            mbar_init(s_bar + 8 * (R3_WEMPTY + s), 1);
+        for (int i = 0; i < R3_NA; ++i) {
+            mbar_init(s_bar + 8 * (R3_AFULL + i), 128);        // every staging thread
+            mbar_init(s_bar + 8 * (R3_AEMPTY + i), 1);         // tcgen05.commit
         }
-        for (int b = 0; b < NBUF; ++b) {
-            mbar_init(s_bar + 8 * (R3_ACCF + b), 1);
-            mbar_init(s_bar + 8 * (R3_ACCE + b), 128);
+        for (int s = 0; s < NW; ++s) {
+            mbar_init(s_bar + 8 * (R3_WFULL + s), 1);          // the loader's expect_tx
+            mbar_init(s_bar + 8 * (R3_WEMPTY + s), 1);         // tcgen05.commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(s_bar + 8 * (R3_ACCF + b), 1);           // tcgen05.commit
+            mbar_init(s_bar + 8 * (R3_ACCE + b), 128);         // every result thread
+            mbar_init(s_bar + 8 * (R3_LOF + b), 1);
+            mbar_init(s_bar + 8 * (R3_LOE + b), 128);
         }
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(s_tmem, 128 * NBUF);
+    if (warp == 4) tmem_alloc(s_tmem, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem + Z::A_BYTES + NW * W_STAGE + 8 * R3_NBARS);
 
     if (warp >= 4 && warp < 8) {
-        // =============================== staging of the activation tile, group by group ===============================
+        // =============================== staging of the activation tiles, group by group ===============================
         const int pw = warp - 4, r8 = lane & 7, q4 = lane >> 3;
-        for (int g = g_lo; g < g_hi; ++g) {
-            const int gi = g - g_lo;
-            const int abuf = (gi % Z::NA) * Z::ABUF;
-            // rotating buffers: free when the MMAs of the group two back have finished (each AEMPTY barrier completes once)
-            if (gi >= Z::NA) mbar_wait(s_bar + 8 * (R3_AEMPTY + (gi & 1)), 0);
-            // a block = 8 rows x 4 K chunks; 19 row groups x 2 chunk halves per channel group of 8 chunks
-            for (int b = pw; b < 38; b += 4) {
-                const int row = (b >> 1) * 8 + r8, kl = (b & 1) * 4 + q4, kc = g * 8 + kl;
-                const int rr = R0 - 11 + row;                                  // raster row
-                const int p = rr >= 0 ? rr / 100 : -1;
-                const int o = rr - 100 * p - 10;                               // 10 x + y, negative in the zero rows above the board
-                const int x = o / 10, y = o - 10 * x;
-                const bool ok = rr >= 0 && p < P && o >= 0 && y < 9 && row < 150;
-                const float *src = ok ? a.in + ((size_t)(p * NSQ + 9 * x + y) * C + 4 * kc) : a.in;
-                if (!(BK_TC_DIAG & 2)) cp_async16(s_base + (uint32_t)(abuf + kl * R3_LBO + row * 16), src, ok);
-            }
-            cp_commit();
-            cp_wait<0>();
-            if constexpr (PREC != 0) {
+        R3Ring ra = {0, 0};
+        for (int it = blockIdx.x; it < a.n_items; it += gridDim.x) {
+            const R3Item w = r3_item(a, it);
+            const int R0 = w.tile * 128;                                       // first raster row of the tile
+            for (int g = w.g_lo; g < w.g_lo + w.ng; ++g) {
+                mbar_wait(s_bar + 8 * (R3_AEMPTY + ra.i), ra.ph ^ 1u);         // the MMAs of the buffer's previous group have finished
+                const int abuf = ra.i * Z::ABUF;
+                // a block = 8 rows x 4 K chunks; 19 row groups x 2 chunk halves per channel group of 8 chunks
                 for (int b = pw; b < 38; b += 4) {
-                    const int row = (b >> 1) * 8 + r8, kl = (b & 1) * 4 + q4;
-                    float4 *hp = reinterpret_cast<float4 *>(smem + abuf + kl * R3_LBO + row * 16);
-                    const float4 v = *hp;
-                    float4 h, l;
-                    h.x = tf32_cut(v.x); h.y = tf32_cut(v.y); h.z = tf32_cut(v.z); h.w = tf32_cut(v.w);
-                    l.x = tf32_cut(v.x - h.x); l.y = tf32_cut(v.y - h.y); l.z = tf32_cut(v.z - h.z); l.w = tf32_cut(v.w - h.w);
-                    *hp = h;
-                    *reinterpret_cast<float4 *>(smem + abuf + R3_G_BYTES + kl * R3_LBO + row * 16) = l;
+                    const int row = (b >> 1) * 8 + r8, kl = (b & 1) * 4 + q4, kc = g * 8 + kl;
+                    const int rr = R0 - 11 + row;                              // raster row
+                    const int p = rr >= 0 ? rr / 100 : -1;
+                    const int o = rr - 100 * p - 10;                           // 10 x + y, negative in the zero rows above the board
+                    const int x = o / 10, y = o - 10 * x;
+                    const bool ok = rr >= 0 && p < P && o >= 0 && y < 9 && row < 150;
+                    const float *src = ok ? a.in + ((size_t)(p * NSQ + 9 * x + y) * C + 4 * kc) : a.in;
+                    if (!(BK_TC_DIAG & 2)) cp_async16(s_base + (uint32_t)(abuf + kl * R3_LBO + row * 16), src, ok);
                 }
+                cp_commit();
+                cp_wait<0>();
+                if constexpr (PREC != 0) {
+                    for (int b = pw; b < 38; b += 4) {
+                        const int row = (b >> 1) * 8 + r8, kl = (b & 1) * 4 + q4;
+                        float4 *hp = reinterpret_cast<float4 *>(smem + abuf + kl * R3_LBO + row * 16);
+                        const float4 v = *hp;
+                        float4 h, l;
+                        h.x = tf32_cut(v.x); h.y = tf32_cut(v.y); h.z = tf32_cut(v.z); h.w = tf32_cut(v.w);
+                        l.x = tf32_cut(v.x - h.x); l.y = tf32_cut(v.y - h.y); l.z = tf32_cut(v.z - h.z); l.w = tf32_cut(v.w - h.w);
+                        *hp = h;
+                        *reinterpret_cast<float4 *>(smem + abuf + R3_G_BYTES + kl * R3_LBO + row * 16) = l;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(s_bar + 8 * (R3_AFULL + ra.i));
+                ra.next(R3_NA);
             }
-            fence_proxy_async();
-            mbar_arrive(s_bar + 8 * (R3_AFULL + g));
         }
     } else if (warp == 9) {
         // =============================== weight slabs: one bulk copy per part ===============================
         if (lane == 0) {
-            for (int s = 0; s < KT; ++s) {
-                const int st = s % NW;
-                if (s >= NW) mbar_wait(s_bar + 8 * (R3_WEMPTY + st), ((s / NW) & 1) ^ 1);
-                const int g = g_lo + s / 9, tap = s % 9;
-                const int k0 = tap * C + 32 * g;
-                const uint32_t bar = s_bar + 8 * (R3_WFULL + st), dst = s_w + (uint32_t)(st * W_STAGE);
-                if (BK_TC_DIAG & 16) {
-                    mbar_arrive(bar);
-                    continue;
+            R3Ring rw = {0, 0};
+            int n_slab = 0;
+            for (int it = blockIdx.x; it < a.n_items; it += gridDim.x) {
+                const R3Item w = r3_item(a, it);
+                for (int s = 0; s < 9 * w.ng; ++s, ++n_slab) {
+                    R3_STAMP(1, n_slab, 0);
+                    mbar_wait(s_bar + 8 * (R3_WEMPTY + rw.i), rw.ph ^ 1u);     // the MMAs of the stage's previous slab have finished
+                    R3_STAMP(1, n_slab, 1);
+                    const int g = w.g_lo + s / 9, tap = s % 9;
+                    const int k0 = tap * C + 32 * g;
+                    const uint32_t bar = s_bar + 8 * (R3_WFULL + rw.i), dst = s_w + (uint32_t)(rw.i * W_STAGE);
+                    if (BK_TC_DIAG & 16) {
+                        mbar_arrive(bar);
+                    } else {
+                        mbar_arrive_expect_tx(bar, (uint32_t)W_STAGE);
+                        bulk_g2s(dst, a.w + (size_t)(k0 / 4) * (4 * C), 16384, bar);
+                        if (PREC) bulk_g2s(dst + 16384, a.w_lo + (size_t)(k0 / 4) * (4 * C), 16384, bar);
+                    }
+                    rw.next(NW);
                 }
-                mbar_arrive_expect_tx(bar, (uint32_t)W_STAGE);
-                bulk_g2s(dst, a.w + (size_t)(k0 / 4) * (4 * C), 16384, bar);
-                if (PREC) bulk_g2s(dst + 16384, a.w_lo + (size_t)(k0 / 4) * (4 * C), 16384, bar);
             }
         }
     } else if (warp == 8) {
         // =============================== MMA issue ===============================
-        int c = 0;                                      // hi * hi chain
-        for (int s = 0; s < KT; ++s) {
-            const int st = s % NW;
-            const int gi = s / 9, tap = s - 9 * gi;
-            const bool first = s % CHAIN == 0, last = s % CHAIN == CHAIN - 1 || s == KT - 1;
-            const int b = c % R3_NROT;
-            if (tap == 0) mbar_wait(s_bar + 8 * (R3_AFULL + g_lo + gi), 0);
-            mbar_wait(s_bar + 8 * (R3_WFULL + st), (s / NW) & 1);
-            if (first) mbar_wait(s_bar + 8 * (R3_ACCE + b), ((c / R3_NROT) & 1) ^ 1);     // the result warps have read the chain three back
-            tc_fence_after();
-            if (elect_one()) {
-                const int ti = tap / 3;
-                const int shift = a.sign * (10 * (ti - 1) + (tap - 3 * ti - 1));
-                const uint32_t a0 = s_base + (uint32_t)((gi % Z::NA) * Z::ABUF + (11 + shift) * 16), w0 = s_w + (uint32_t)(st * W_STAGE);
-                const uint32_t d = tmem + (uint32_t)(b * 128), dlo = tmem + (uint32_t)(R3_NROT * 128);
-                // the lo products of the slab first, then its hi * hi products: the tensor core changes accumulator twice per slab
-                // (alternating per K step cost 2 % against one accumulator per chain; profiles/r02n_train_conv3.md)
+        R3Ring ra = {0, 0}, rw = {0, 0}, rc = {0, 0};
+        uint32_t n_item = 0;
+        int n_slab = 0;
+        for (int it = blockIdx.x; it < a.n_items; it += gridDim.x, ++n_item) {
+            const R3Item w = r3_item(a, it);
+            const int KT = 9 * w.ng;
+            const int lob = (int)(n_item & 1u);
+            if (PREC != 0) mbar_wait(s_bar + 8 * (R3_LOE + lob), ((n_item >> 1) & 1u) ^ 1u);   // the lo products of the item two back have been read
+            for (int s = 0; s < KT; ++s, ++n_slab) {
+                const int gi = s / 9, tap = s - 9 * gi;
+                const bool first = s % CHAIN == 0, last = s % CHAIN == CHAIN - 1 || s == KT - 1;
+                if (lane == 0) R3_STAMP(0, n_slab, 0);
+                if (tap == 0) mbar_wait(s_bar + 8 * (R3_AFULL + ra.i), ra.ph);
+                if (lane == 0) R3_STAMP(0, n_slab, 1);
+                mbar_wait(s_bar + 8 * (R3_WFULL + rw.i), rw.ph);
+                if (lane == 0) R3_STAMP(0, n_slab, 2);
+                if (first) mbar_wait(s_bar + 8 * (R3_ACCE + rc.i), rc.ph ^ 1u);                // the result warps have read the chain two back
+                if (lane == 0) R3_STAMP(0, n_slab, 3);
+                tc_fence_after();
+                if (elect_one()) {
+                    const int ti = tap / 3;
+                    const int shift = (BK_TC_DIAG & 32) ? -11 + 8 * (tap % 3) : a.sign * (10 * (ti - 1) + (tap - 3 * ti - 1));   // 32: windows on 8-row boundaries
+                    const uint32_t a0 = s_base + (uint32_t)(ra.i * Z::ABUF + (11 + shift) * 16), w0 = s_w + (uint32_t)(rw.i * W_STAGE);
+                    const uint32_t d = tmem + (uint32_t)(rc.i * 128), dlo = tmem + (uint32_t)((R3_NROT + lob) * 128);
+                    // the lo products of the slab first, then its hi * hi products
 #pragma unroll
-                for (int pass = PREC ? 0 : 1; pass < 2; ++pass) {
+                    for (int pass = PREC ? 0 : 1; pass < 2; ++pass) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t akc = (uint32_t)(2 * ks * R3_LBO);
-                        const uint64_t ah = make_desc(a0 + akc, R3_LBO, (128u >> 4) | (1u << 14));
-                        const uint64_t al = make_desc(a0 + R3_G_BYTES + akc, R3_LBO, (128u >> 4) | (1u << 14));      // 3xTF32 only
-                        const uint64_t bh = make_desc(w0 + ks * 4096, 2048, (128u >> 4) | (1u << 14));
-                        const uint64_t bl = make_desc(w0 + 16384 + ks * 4096, 2048, (128u >> 4) | (1u << 14));
-                        if constexpr ((BK_TC_DIAG & 4) != 0) {
-                        } else if (pass == 0) {
-                            umma_tf32(dlo, al, bh, IDESC_BASE, (s | ks) ? 1u : 0u);
-                            umma_tf32(dlo, ah, bl, IDESC_BASE, 1u);
-                        } else {
-                            umma_tf32(d, ah, bh, IDESC_BASE, (first && ks == 0) ? 0u : 1u);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t akc = (uint32_t)(2 * ks * R3_LBO);
+                            const uint64_t ah = make_desc(a0 + akc, R3_LBO, (128u >> 4) | (1u << 14));
+                            const uint64_t al = make_desc(a0 + R3_G_BYTES + akc, R3_LBO, (128u >> 4) | (1u << 14));      // 3xTF32 only
+                            const uint64_t bh = make_desc(w0 + ks * 4096, 2048, (128u >> 4) | (1u << 14));
+                            const uint64_t bl = make_desc(w0 + 16384 + ks * 4096, 2048, (128u >> 4) | (1u << 14));
+                            if constexpr ((BK_TC_DIAG & 4) != 0) {
+                            } else if constexpr ((BK_TC_DIAG & 64) != 0) {     // measurement: no two consecutive MMAs into the same accumulator
+                                if (pass == 0) {
+                                    umma_tf32(tmem + (uint32_t)(((2 * ks) & 3) * 128), al, bh, IDESC_BASE, 1u);
+                                    umma_tf32(tmem + (uint32_t)(((2 * ks + 1) & 3) * 128), ah, bl, IDESC_BASE, 1u);
+                                } else {
+                                    umma_tf32(tmem + (uint32_t)((ks & 3) * 128), ah, bh, IDESC_BASE, 1u);
+                                }
+                            } else if (pass == 0) {
+                                umma_tf32(dlo, al, bh, IDESC_BASE, (s | ks) ? 1u : 0u);
+                                umma_tf32(dlo, ah, bl, IDESC_BASE, 1u);
+                            } else {
+                                umma_tf32(d, ah, bh, IDESC_BASE, (first && ks == 0) ? 0u : 1u);
+                            }
                         }
                     }
+                    umma_commit(s_bar + 8 * (R3_WEMPTY + rw.i));                            // slab consumed -> the loader may refill the stage
+                    if (tap == 8) umma_commit(s_bar + 8 * (R3_AEMPTY + ra.i));               // group consumed -> its buffer may be restaged
+                    if (last) umma_commit(s_bar + 8 * (R3_ACCF + rc.i));                     // this chain is complete
+                    if (PREC != 0 && s == KT - 1) umma_commit(s_bar + 8 * (R3_LOF + lob));   // ... and so are the item's lo products
                 }
-                umma_commit(s_bar + 8 * (R3_WEMPTY + st));                                   // slab consumed -> the loader may refill it
-                if (tap == 8 && gi + Z::NA < n_groups) umma_commit(s_bar + 8 * (R3_AEMPTY + (gi & 1)));   // group consumed -> its buffer may be restaged
-                if (last) umma_commit(s_bar + 8 * (R3_ACCF + b));                            // this chain is complete
-                if (PREC != 0 && s == KT - 1) umma_commit(s_bar + 8 * (R3_ACCF + R3_NROT));  // ... and so are the lo products
+                __syncwarp();
+                rw.next(NW);
+                if (tap == 8) ra.next(R3_NA);
+                if (last) rc.next(R3_NROT);
             }
-            if (last) ++c;
-            __syncwarp();
         }
     } else {
         // =============================== result warps (thread = raster row) ===============================
-        float acc[C];
-#pragma unroll
-        for (int i = 0; i < C; ++i) acc[i] = 0.0f;
         const uint32_t t_lane = tmem + ((uint32_t)(32 * warp) << 16);
-        for (int c = 0; c < n_chains + (PREC ? 1 : 0); ++c) {
-            const bool lo = c == n_chains;
-            const int b = lo ? R3_NROT : c % R3_NROT;
-            mbar_wait(s_bar + 8 * (R3_ACCF + b), lo ? 0 : (c / R3_NROT) & 1);
-            tc_fence_after();
+        const int n_tiles = (P * 100 + 127) / 128;
+        R3Ring rc = {0, 0};
+        uint32_t n_item = 0;
+        for (int it = blockIdx.x; it < a.n_items; it += gridDim.x, ++n_item) {
+            const R3Item w = r3_item(a, it);
+            const int n_chains = (9 * w.ng + CHAIN - 1) / CHAIN;
+            const int lob = (int)(n_item & 1u);
+            float acc[C];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                uint32_t v[32];
-                if (BK_TC_DIAG & 8) continue;
-                tmem_ld32(t_lane + (uint32_t)(b * 128 + h * 32), v);
-                tc_wait_ld();
+            for (int i = 0; i < C; ++i) acc[i] = 0.0f;
+            for (int c = 0; c < n_chains + (PREC ? 1 : 0); ++c) {
+                const bool lo = c == n_chains;
+                const int b = lo ? R3_NROT + lob : rc.i;
+                if (tid == 0) R3_STAMP(2, (int)n_item * 14 + c, 0);
+                if (lo) mbar_wait(s_bar + 8 * (R3_LOF + lob), (n_item >> 1) & 1u);
+                else mbar_wait(s_bar + 8 * (R3_ACCF + rc.i), rc.ph);
+                if (tid == 0) R3_STAMP(2, (int)n_item * 14 + c, 1);
+                tc_fence_after();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[h * 32 + i] += __uint_as_float(v[i]);
-            }
-            tc_fence_before();
-            mbar_arrive(s_bar + 8 * (R3_ACCE + b));
-        }
-        const int rr = R0 + 32 * warp + lane;
-        const int p = rr / 100, o = rr - 100 * p - 10;
-        const int x = o / 10, y = o - 10 * x;
-        if (p < P && o >= 0 && y < 9) {
-            // split tail: partial result [group][tail tile][row][128]; else the dense output (ksplit: one copy of it per group)
-            const int n_tail = (int)(gridDim.x - a.tail_full) >> 2;
-            float4 *out = tail ? reinterpret_cast<float4 *>(a.tail_part + ((size_t)(g_lo * n_tail + tile - a.tail_full) * 128 + 32 * warp + lane) * C)
-                               : reinterpret_cast<float4 *>(a.out + ((size_t)g_lo * (a.ksplit > 1 ? a.M : 0) + p * NSQ + 9 * x + y) * C);
+                for (int h = 0; h < 4; ++h) {
+                    uint32_t v[32];
+                    if (BK_TC_DIAG & 8) continue;
+                    tmem_ld32(t_lane + (uint32_t)(b * 128 + h * 32), v);
+                    tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < C / 4; ++i) {
-                float4 v = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
-                if (a.bias && g_lo == 0) {
-                    const float4 bb = *reinterpret_cast<const float4 *>(a.bias + 4 * i);
-                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                    for (int i = 0; i < 32; ++i) acc[h * 32 + i] += __uint_as_float(v[i]);
                 }
-                out[i] = v;
+                tc_fence_before();
+                if (tid == 0) R3_STAMP(2, (int)n_item * 14 + c, 2);
+                if (lo) {
+                    mbar_arrive(s_bar + 8 * (R3_LOE + lob));
+                } else {
+                    mbar_arrive(s_bar + 8 * (R3_ACCE + rc.i));
+                    rc.next(R3_NROT);
+                }
             }
+            if (tid == 0) R3_STAMP(2, (int)n_item * 14 + 13, 3);       // acc complete
+            // ---- the rows go out through a per-warp transposition buffer: a thread owns a ROW of 128 floats, and written from there
+            // a warp's store touches 32 different lines, 16 bytes each (measured: 10 k cycles per tile during which the result warps
+            // could not take the next tile's chains; profiles/r02q_train_conv3.md).  32 columns at a time: thread = row writes its 32
+            // values (pitch 33: conflict-free), then lane = column reads the 32 rows back -- ALL loads before the first store: a loop
+            // of load / store pairs took as long as the direct stores, 110 cycles per row -- and every store is one whole 128-byte
+            // line of one row: 5 k cycles per tile, under the first two chains of the next one.
+            const int row = 32 * warp + lane;
+            const int rr = w.tile * 128 + row;
+            const int p = rr / 100, o = rr - 100 * p - 10;
+            const int x = o / 10, y = o - 10 * x;
+            // whole tile: the dense output; small batch: one dense copy per group (bk_train_sum4_kernel adds them); tail tile:
+            // partial result [group][tail tile][row][128] (bk_train_conv3_tail_kernel adds them)
+            const int at = !(p < P && o >= 0 && y < 9) ? -1
+                           : w.kind == 2 ? (w.g_lo * (n_tiles - a.tail_full) + w.tile - a.tail_full) * 128 + row
+                                         : (w.kind == 1 ? w.g_lo : 0) * a.M + p * NSQ + 9 * x + y;
+            float *obase = w.kind == 2 ? a.tail_part : a.out;
+            float *sst = reinterpret_cast<float *>(smem + Z::A_BYTES + NW * W_STAGE + 256) + warp * (32 * 33);
+            const bool with_bias = a.bias && w.g_lo == 0;
+#if BK_R3_STORE == 0
+            if (at == -2) obase[0] = acc[0];       // measurement: no stores
+#elif BK_R3_STORE == 1
+            if (at >= 0) {                          // measurement: thread = row, 32 16-byte stores per thread
+                float4 *out = reinterpret_cast<float4 *>(obase + (size_t)at * C);
+#pragma unroll
+                for (int i = 0; i < C / 4; ++i) {
+                    float4 v = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                    if (with_bias) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(a.bias + 4 * i);
+                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                    }
+                    out[i] = v;
+                }
+            }
+#else
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                const float bias = with_bias ? a.bias[ch * 32 + lane] : 0.0f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sst[lane * 33 + i] = acc[ch * 32 + i];
+                __syncwarp();
+                if (tid == 0 && ch == 0) R3_STAMP(2, (int)n_item * 14 + 13, 0);
+                float v[32];
+#pragma unroll
+                for (int r = 0; r < 32; ++r) v[r] = sst[r * 33 + lane] + bias;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const int at_r = __shfl_sync(0xffffffffu, at, r);
+                    if (at_r >= 0) obase[(size_t)at_r * C + ch * 32 + lane] = v[r];
+                }
+                __syncwarp();
+                if (tid == 0 && ch == 0) R3_STAMP(2, (int)n_item * 14 + 13, 1);
+            }
+#endif
+            if (tid == 0) R3_STAMP(2, (int)n_item * 14 + 13, 2);       // stores issued
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
-        tmem_dealloc(tmem, 128 * NBUF);
+        tmem_dealloc(tmem, 512);
     }
 }
 
@@ -731,6 +844,10 @@ __global__ void bk_train_conv3_tail_kernel(const float4 *__restrict__ part, floa
 }
 
 }   // namespace
+
+#if BK_R3_PROF
+extern "C" int bk_r3_prof_read(long long *host) { return (int)cudaMemcpyFromSymbol(host, g_r3_prof, sizeof(g_r3_prof)); }
+#endif
 
 // SM count of the current device (per device, queried once)
 static int bk_tc_sm_count()
@@ -779,11 +896,13 @@ void bk_tc_launch_conv(const BkConvArgs &a, int three_x, cudaStream_t st)
 {
     if (a.R == 3 && a.Cin == C && !getenv_old_conv()) {          // the 3x3 layers and their data gradients: tile staged once
         const int n_tiles = (a.M / NSQ * 100 + 127) / 128;
-        dim3 tiles(n_tiles, a.ksplit > 1 ? 4 : 1);
         BkConvArgs b = a;
         b.tail_full = a.ksplit == 1 && a.tail_part ? bk_tc_conv3_tail(a.M / NSQ) : 0;
         const int rest = n_tiles - b.tail_full;
-        if (b.tail_full > 0) tiles.x = b.tail_full + 4 * rest;
+        // work items of the persistent CTAs (one per SM): whole tiles, or one channel group of a tile (small batches, split tail)
+        b.n_items = a.ksplit > 1 ? 4 * n_tiles : (b.tail_full > 0 ? b.tail_full + 4 * rest : n_tiles);
+        const int n_sm = bk_tc_sm_count();
+        const int tiles = n_sm > 0 && n_sm < b.n_items ? n_sm : b.n_items;
         if (three_x) bk_train_conv3_tc_kernel<1><<<tiles, R3_THREADS, R3<1>::SMEM, st>>>(b);
         else bk_train_conv3_tc_kernel<0><<<tiles, R3_THREADS, R3<0>::SMEM, st>>>(b);
         if (b.tail_full > 0)
