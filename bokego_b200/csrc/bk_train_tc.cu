@@ -68,6 +68,7 @@ struct Sizes {
 
 // instruction descriptor: D = f32 (bit 4), A = B = TF32 (2 at bits 7, 10), majors at bits 15 / 16 (1 = MN-major), N >> 3 at 17, M >> 4 at 24
 constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_N256 = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);   // N = 256
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
@@ -484,11 +485,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
 //     Now all roles run loops over the CTA's work items with ring positions that carry over from item to item: the staging warps
 //     gather the first groups of the next tile into free group buffers (three rotating buffers) while the MMAs of the current one
 //     run, the weight loader never stops, and the result warps store tile t while the tensor pipe is in the first chains of t + 1;
+//   * a kind::tf32 MMA of 128 x 128 x 8 reads 8 KiB of operands from shared memory and takes ~104 cycles, not the 64 of the tensor
+//     pipe (clock stamps: the issuing thread waits on no barrier, windows on 8-row boundaries / no weight copies / other
+//     accumulators change nothing) -- the operand fetch is the limit.  So the two products that share the operand A_hi are ONE
+//     MMA with N = 256: A_hi x [B_hi | B_lo] -> [hi | lo] halves of a 256-column accumulator (12 KiB of operands for the work of
+//     two MMAs), and A_lo x B_hi goes into the lo half: two MMAs per K step instead of three;
 //   * the accumulation chains are split by magnitude.  What the tensor core's truncating fp32 accumulation costs is one ulp of the
-//     ACCUMULATOR per MMA, so only the hi * hi products need short chains; lo * hi and hi * lo are 2^-11 of them and accumulate over
-//     the whole item in an accumulator of their own (two, alternating from item to item).  A hi * hi chain is BK_R3_CHAIN_SLABS
-//     slabs = 12 MMAs -- as many accumulations as the 12-MMA chains measured equivalent to one-K-step chains -- so the result
-//     warps read TMEM (64 KiB per read-out at 64 B/clk) 13 times per tile instead of 36;
+//     ACCUMULATOR per MMA, so the large hi * hi products are kept apart from the lo * hi and hi * lo products (2^-11 of them);
+//     a chain is BK_R3_CHAIN_SLABS slabs = 12 accumulations per half -- as many as the 12-MMA chains measured equivalent to
+//     one-K-step chains -- and the result warps add both halves of a finished chain into fp32 registers with IEEE adds: 12
+//     read-outs per tile instead of 36;
 //   * work items: whole tiles; for small batches (ksplit) one channel group of a tile each; and the tiles left over after the last
 //     full round of the grid as four channel-group items each (see BkConvArgs::tail_part).
 // Warps: 0-3 result (thread = raster row), 4-7 staging, 8 MMA issue, 9 weight loader (one thread).
@@ -500,7 +506,7 @@ constexpr int R3_LBO = R3_ROWS * 16;               // bytes between K chunks of 
 constexpr int R3_G_BYTES = 8 * R3_LBO;             // one part (hi or lo) of one channel group of the tile: 19,456
 constexpr int R3_THREADS = 320;
 constexpr int R3_NA = 3;                           // rotating group buffers
-constexpr int R3_NROT = 2;                         // accumulators 0, 1: the hi * hi chains in turn; 2, 3: the lo products of even / odd items
+constexpr int R3_NROT = 2;                         // two accumulators of 256 columns ([hi | lo] halves), the chains take them in turn
 #ifndef BK_R3_CHAIN_SLABS
 #define BK_R3_CHAIN_SLABS 3                        // slabs per hi * hi chain (4 MMAs each)
 #endif
@@ -515,7 +521,7 @@ struct R3 {
     static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 enum { R3_AFULL = 0, R3_AEMPTY = R3_NA, R3_WFULL = 2 * R3_NA, R3_WEMPTY = R3_WFULL + MAX_STAGES, R3_ACCF = R3_WEMPTY + MAX_STAGES,
-       R3_ACCE = R3_ACCF + R3_NROT, R3_LOF = R3_ACCE + R3_NROT, R3_LOE = R3_LOF + 2, R3_NBARS = R3_LOE + 2 };
+       R3_ACCE = R3_ACCF + R3_NROT, R3_NBARS = R3_ACCE + R3_NROT };
 static_assert(8 * R3_NBARS + 4 <= 256, "barrier area");
 
 #ifndef BK_R3_STORE
@@ -581,8 +587,6 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
         for (int b = 0; b < 2; ++b) {
             mbar_init(s_bar + 8 * (R3_ACCF + b), 1);           // tcgen05.commit
             mbar_init(s_bar + 8 * (R3_ACCE + b), 128);         // every result thread
-            mbar_init(s_bar + 8 * (R3_LOF + b), 1);
-            mbar_init(s_bar + 8 * (R3_LOE + b), 128);
         }
         fence_barrier_init();
     }
@@ -650,8 +654,14 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
                         mbar_arrive(bar);
                     } else {
                         mbar_arrive_expect_tx(bar, (uint32_t)W_STAGE);
-                        bulk_g2s(dst, a.w + (size_t)(k0 / 4) * (4 * C), 16384, bar);
-                        if (PREC) bulk_g2s(dst + 16384, a.w_lo + (size_t)(k0 / 4) * (4 * C), 16384, bar);
+                        if (PREC) {                // K chunk by K chunk [B_hi: 128 rows | B_lo: 128 rows]: one 256-row operand
+                            for (int c = 0; c < 8; ++c) {
+                                bulk_g2s(dst + c * 4096, a.w + (size_t)(k0 / 4 + c) * (4 * C), 2048, bar);
+                                bulk_g2s(dst + c * 4096 + 2048, a.w_lo + (size_t)(k0 / 4 + c) * (4 * C), 2048, bar);
+                            }
+                        } else {
+                            bulk_g2s(dst, a.w + (size_t)(k0 / 4) * (4 * C), 16384, bar);
+                        }
                     }
                     rw.next(NW);
                 }
@@ -660,13 +670,10 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
     } else if (warp == 8) {
         // =============================== MMA issue ===============================
         R3Ring ra = {0, 0}, rw = {0, 0}, rc = {0, 0};
-        uint32_t n_item = 0;
         int n_slab = 0;
-        for (int it = blockIdx.x; it < a.n_items; it += gridDim.x, ++n_item) {
+        for (int it = blockIdx.x; it < a.n_items; it += gridDim.x) {
             const R3Item w = r3_item(a, it);
             const int KT = 9 * w.ng;
-            const int lob = (int)(n_item & 1u);
-            if (PREC != 0) mbar_wait(s_bar + 8 * (R3_LOE + lob), ((n_item >> 1) & 1u) ^ 1u);   // the lo products of the item two back have been read
             for (int s = 0; s < KT; ++s, ++n_slab) {
                 const int gi = s / 9, tap = s - 9 * gi;
                 const bool first = s % CHAIN == 0, last = s % CHAIN == CHAIN - 1 || s == KT - 1;
@@ -682,37 +689,25 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
                     const int ti = tap / 3;
                     const int shift = (BK_TC_DIAG & 32) ? -11 + 8 * (tap % 3) : a.sign * (10 * (ti - 1) + (tap - 3 * ti - 1));   // 32: windows on 8-row boundaries
                     const uint32_t a0 = s_base + (uint32_t)(ra.i * Z::ABUF + (11 + shift) * 16), w0 = s_w + (uint32_t)(rw.i * W_STAGE);
-                    const uint32_t d = tmem + (uint32_t)(rc.i * 128), dlo = tmem + (uint32_t)((R3_NROT + lob) * 128);
-                    // the lo products of the slab first, then its hi * hi products
+                    const uint32_t d = tmem + (uint32_t)(rc.i * 256);
 #pragma unroll
-                    for (int pass = PREC ? 0 : 1; pass < 2; ++pass) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint32_t akc = (uint32_t)(2 * ks * R3_LBO);
-                            const uint64_t ah = make_desc(a0 + akc, R3_LBO, (128u >> 4) | (1u << 14));
-                            const uint64_t al = make_desc(a0 + R3_G_BYTES + akc, R3_LBO, (128u >> 4) | (1u << 14));      // 3xTF32 only
-                            const uint64_t bh = make_desc(w0 + ks * 4096, 2048, (128u >> 4) | (1u << 14));
-                            const uint64_t bl = make_desc(w0 + 16384 + ks * 4096, 2048, (128u >> 4) | (1u << 14));
-                            if constexpr ((BK_TC_DIAG & 4) != 0) {
-                            } else if constexpr ((BK_TC_DIAG & 64) != 0) {     // measurement: no two consecutive MMAs into the same accumulator
-                                if (pass == 0) {
-                                    umma_tf32(tmem + (uint32_t)(((2 * ks) & 3) * 128), al, bh, IDESC_BASE, 1u);
-                                    umma_tf32(tmem + (uint32_t)(((2 * ks + 1) & 3) * 128), ah, bl, IDESC_BASE, 1u);
-                                } else {
-                                    umma_tf32(tmem + (uint32_t)((ks & 3) * 128), ah, bh, IDESC_BASE, 1u);
-                                }
-                            } else if (pass == 0) {
-                                umma_tf32(dlo, al, bh, IDESC_BASE, (s | ks) ? 1u : 0u);
-                                umma_tf32(dlo, ah, bl, IDESC_BASE, 1u);
-                            } else {
-                                umma_tf32(d, ah, bh, IDESC_BASE, (first && ks == 0) ? 0u : 1u);
-                            }
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t akc = (uint32_t)(2 * ks * R3_LBO);
+                        const uint32_t acc_flag = (first && ks == 0) ? 0u : 1u;
+                        const uint64_t ah = make_desc(a0 + akc, R3_LBO, (128u >> 4) | (1u << 14));
+                        if constexpr ((BK_TC_DIAG & 4) != 0) {
+                        } else if constexpr (PREC != 0) {
+                            const uint64_t al = make_desc(a0 + R3_G_BYTES + akc, R3_LBO, (128u >> 4) | (1u << 14));
+                            const uint64_t bw = make_desc(w0 + ks * 8192, 4096, (128u >> 4) | (1u << 14));     // rows 0..127 = B_hi, 128..255 = B_lo
+                            umma_tf32(d, ah, bw, IDESC_N256, acc_flag);              // [hi | lo] (+)= A_hi x [B_hi | B_lo]
+                            umma_tf32(d + 128u, al, bw, IDESC_BASE, 1u);             // lo += A_lo x B_hi
+                        } else {
+                            umma_tf32(d, ah, make_desc(w0 + ks * 4096, 2048, (128u >> 4) | (1u << 14)), IDESC_BASE, acc_flag);
                         }
                     }
                     umma_commit(s_bar + 8 * (R3_WEMPTY + rw.i));                            // slab consumed -> the loader may refill the stage
                     if (tap == 8) umma_commit(s_bar + 8 * (R3_AEMPTY + ra.i));               // group consumed -> its buffer may be restaged
                     if (last) umma_commit(s_bar + 8 * (R3_ACCF + rc.i));                     // this chain is complete
-                    if (PREC != 0 && s == KT - 1) umma_commit(s_bar + 8 * (R3_LOF + lob));   // ... and so are the item's lo products
                 }
                 __syncwarp();
                 rw.next(NW);
@@ -729,35 +724,27 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
         for (int it = blockIdx.x; it < a.n_items; it += gridDim.x, ++n_item) {
             const R3Item w = r3_item(a, it);
             const int n_chains = (9 * w.ng + CHAIN - 1) / CHAIN;
-            const int lob = (int)(n_item & 1u);
             float acc[C];
 #pragma unroll
             for (int i = 0; i < C; ++i) acc[i] = 0.0f;
-            for (int c = 0; c < n_chains + (PREC ? 1 : 0); ++c) {
-                const bool lo = c == n_chains;
-                const int b = lo ? R3_NROT + lob : rc.i;
+            for (int c = 0; c < n_chains; ++c) {
                 if (tid == 0) R3_STAMP(2, (int)n_item * 14 + c, 0);
-                if (lo) mbar_wait(s_bar + 8 * (R3_LOF + lob), (n_item >> 1) & 1u);
-                else mbar_wait(s_bar + 8 * (R3_ACCF + rc.i), rc.ph);
+                mbar_wait(s_bar + 8 * (R3_ACCF + rc.i), rc.ph);
                 if (tid == 0) R3_STAMP(2, (int)n_item * 14 + c, 1);
                 tc_fence_after();
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
+                for (int h = 0; h < (PREC ? 8 : 4); ++h) {                 // the hi half, then the lo half
                     uint32_t v[32];
                     if (BK_TC_DIAG & 8) continue;
-                    tmem_ld32(t_lane + (uint32_t)(b * 128 + h * 32), v);
+                    tmem_ld32(t_lane + (uint32_t)(rc.i * 256 + h * 32), v);
                     tc_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[h * 32 + i] += __uint_as_float(v[i]);
+                    for (int i = 0; i < 32; ++i) acc[(h & 3) * 32 + i] += __uint_as_float(v[i]);
                 }
                 tc_fence_before();
                 if (tid == 0) R3_STAMP(2, (int)n_item * 14 + c, 2);
-                if (lo) {
-                    mbar_arrive(s_bar + 8 * (R3_LOE + lob));
-                } else {
-                    mbar_arrive(s_bar + 8 * (R3_ACCE + rc.i));
-                    rc.next(R3_NROT);
-                }
+                mbar_arrive(s_bar + 8 * (R3_ACCE + rc.i));
+                rc.next(R3_NROT);
             }
             if (tid == 0) R3_STAMP(2, (int)n_item * 14 + 13, 3);       // acc complete
             // ---- the rows go out through a per-warp transposition buffer: a thread owns a ROW of 128 floats, and written from there
