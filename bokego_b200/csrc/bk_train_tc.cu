@@ -37,7 +37,8 @@ constexpr int NSQ = 81;
 constexpr int SLAB = 32;                 // reduction depth of one stage
 constexpr int MAX_STAGES = 6;
 // measurement only (results are wrong): 1 = no 3xTF32 split in the conv producers, 2 = no gathers / loads of the A and dZ operands,
-// 4 = no MMAs (commits only), 8 = no TMEM read-out / adds in the result warps, 16 = no weight bulk copies
+// 4 = no MMAs (commits only), 8 = no TMEM read-out / adds in the result warps, 16 = no weight bulk copies, 32 = 3x3 kernel: operand
+// windows on 8-row boundaries
 #ifndef BK_TC_DIAG
 #define BK_TC_DIAG 0
 #endif
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
 // instead of the 36,864 of nine separate window gathers -- in four channel groups of 32 that the MMAs follow group by group; beside
 // that only the pre-split weight slabs stream (one bulk copy each).  81 of every 100 raster rows are real squares; the result
 // threads write those to the dense [P][81][128] output.
-// Round 2 (profiles/r02q_train_conv3.md):
+// Round 2 (profiles/r02u_train_conv3.md):
 //   * PERSISTENT CTAs, one per SM, each working through its tiles as ONE pipeline: with one tile per CTA (round 1) the prologue
 //     (barriers, TMEM allocation, the first group's gather, the first weight slabs) and the epilogue (last read-out, stores) of
 //     every tile were exposed -- 57 k cycles per tile against 28 k of tensor time, and switching the MMAs off saved only a third.
@@ -749,7 +750,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
             if (tid == 0) R3_STAMP(2, (int)n_item * 14 + 13, 3);       // acc complete
             // ---- the rows go out through a per-warp transposition buffer: a thread owns a ROW of 128 floats, and written from there
             // a warp's store touches 32 different lines, 16 bytes each (measured: 10 k cycles per tile during which the result warps
-            // could not take the next tile's chains; profiles/r02q_train_conv3.md).  32 columns at a time: thread = row writes its 32
+            // could not take the next tile's chains; profiles/r02u_train_conv3.md).  32 columns at a time: thread = row writes its 32
             // values (pitch 33: conflict-free), then lane = column reads the 32 rows back -- ALL loads before the first store: a loop
             // of load / store pairs took as long as the direct stores, 110 cycles per row -- and every store is one whole 128-byte
             // line of one row: 5 k cycles per tile, under the first two chains of the next one.
