@@ -178,6 +178,32 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
     return ((uint64_t)hi << 32) | (((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16));
 }
 
+// The result rows of a 128 x 128 tile leave through a per-warp transposition buffer (32 x 33 floats).  A thread owns a ROW of 128
+// floats, and stored from there a warp instruction touches 32 different lines, 16 bytes each: 12 k cycles per tile
+// (profiles/r02u_train_conv3.md).  Instead, 32 columns at a time: thread = row writes its 32 values (pitch 33: conflict-free), then
+// lane = column reads the 32 rows back -- ALL loads before the first store; a loop of load / store pairs took as long as the direct
+// stores, 110 cycles per row -- and every store is one whole 128-byte line of one row: 5 k cycles per tile.
+// at = this thread's output row (in rows of 128 floats from obase), -1 = none; bias = one value per column or null.
+__device__ __forceinline__ void store_rows_transposed(const float (&acc)[128], float *sst, float *obase, int at, const float *bias, int lane)
+{
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        const float bv = bias ? bias[ch * 32 + lane] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sst[lane * 33 + i] = acc[ch * 32 + i];
+        __syncwarp();
+        float v[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = sst[r * 33 + lane] + bv;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int at_r = __shfl_sync(0xffffffffu, at, r);
+            if (at_r >= 0) obase[(size_t)at_r * 128 + ch * 32 + lane] = v[r];
+        }
+        __syncwarp();
+    }
+}
+
 // MODE 0: convolution / data gradient (BkConvArgs).  MODE 1: weight gradient (BkWgradArgs), grid = (k tiles, splits).
 template <int MODE, int PREC, typename Args>
 __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Args a)
@@ -437,6 +463,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
             tc_fence_before();
             mbar_arrive(s_bar + 8 * (BAR_ACCE + b));
         }
+        // (thread = row stores; through the transposition buffer of the 3x3 kernel this epilogue, which nothing overlaps, was 2 % slower)
         const int row = 32 * warp + lane;
         if constexpr (MODE == 0) {
             const int m = m0 + row;
@@ -748,12 +775,8 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
                 rc.next(R3_NROT);
             }
             if (tid == 0) R3_STAMP(2, (int)n_item * 14 + 13, 3);       // acc complete
-            // ---- the rows go out through a per-warp transposition buffer: a thread owns a ROW of 128 floats, and written from there
-            // a warp's store touches 32 different lines, 16 bytes each (measured: 10 k cycles per tile during which the result warps
-            // could not take the next tile's chains; profiles/r02u_train_conv3.md).  32 columns at a time: thread = row writes its 32
-            // values (pitch 33: conflict-free), then lane = column reads the 32 rows back -- ALL loads before the first store: a loop
-            // of load / store pairs took as long as the direct stores, 110 cycles per row -- and every store is one whole 128-byte
-            // line of one row: 5 k cycles per tile, under the first two chains of the next one.
+            // ---- the rows go out through the warp's transposition buffer (store_rows_transposed): 5 k cycles per tile, under the first
+            // two chains of the next one; stored straight from the row-owning threads they took 12 k, and the MMA issuer waited for them
             const int row = 32 * warp + lane;
             const int rr = w.tile * 128 + row;
             const int p = rr / 100, o = rr - 100 * p - 10;
@@ -782,24 +805,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
                 }
             }
 #else
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                const float bias = with_bias ? a.bias[ch * 32 + lane] : 0.0f;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) sst[lane * 33 + i] = acc[ch * 32 + i];
-                __syncwarp();
-                if (tid == 0 && ch == 0) R3_STAMP(2, (int)n_item * 14 + 13, 0);
-                float v[32];
-#pragma unroll
-                for (int r = 0; r < 32; ++r) v[r] = sst[r * 33 + lane] + bias;
-#pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    const int at_r = __shfl_sync(0xffffffffu, at, r);
-                    if (at_r >= 0) obase[(size_t)at_r * C + ch * 32 + lane] = v[r];
-                }
-                __syncwarp();
-                if (tid == 0 && ch == 0) R3_STAMP(2, (int)n_item * 14 + 13, 1);
-            }
+            store_rows_transposed(acc, sst, obase, at, with_bias ? a.bias : nullptr, lane);
 #endif
             if (tid == 0) R3_STAMP(2, (int)n_item * 14 + 13, 2);       // stores issued
         }
@@ -853,7 +859,7 @@ static int bk_tc_sm_count()
 // other: returns the number of tiles that run whole (a multiple of the SM count), 0 = no split tail for P positions on this device.
 int bk_tc_conv3_tail(int P)
 {
-    static const bool off = getenv("BK_TC_NO_TAIL") != nullptr;      // measurement
+    const bool off = getenv("BK_TC_NO_TAIL") != nullptr;             // measurement / tests: read per call, so one process can compare both
     const int n_tiles = (P * 100 + 127) / 128;
     const int n_sm = bk_tc_sm_count();
     const int full = n_sm > 0 ? n_tiles / n_sm * n_sm : 0, rest = n_tiles - full;

@@ -131,6 +131,43 @@ def test_gradients_vs_autograd(env, sd17, prec, bn):
     assert float((tr.grads - 2 * g1).abs().max()) <= 1e-5 * float(g1.abs().max())
 
 
+@pytest.mark.parametrize("P", [190, 200, 220, 576])
+def test_conv3_split_tail_equals_whole_tiles(env, sd17, P):
+    """the persistent 3x3 kernel's work items at the sizes where the schedule changes (148 SMs; a tile = 128 rows of the 100-row-per-position
+    raster): 190 positions = 149 tiles = one full round of the grid and a split tail of 1 tile (4 single-channel-group items whose
+    partial results a small kernel adds), 200 -> 9 tail tiles, 220 -> 24 (the most a tail may have), 576 -> 3 rounds + 6.  The same
+    kernel with the tail switched off (BK_TC_NO_TAIL, read per launch) runs those tiles whole: only the order of four partial sums
+    differs, so logits and every gradient tensor agree to round-off (measured 2e-7 .. 5e-7: profiles/r02w_tail_check.txt).  Against
+    the FFMA path both differ by the same 1e-3 .. 9e-3 -- ReLU branches of pre-activations within round-off of zero -- hence this
+    pairing and not that one."""
+    rf, dev, G = env
+    calls = np.concatenate([G["black3/calls"], G["white2/calls"]])
+    planes = _dev(calls[np.arange(P) % len(calls)], dev, torch.uint8)
+    rng = np.random.default_rng(P)
+    moves = _dev(rng.integers(0, 81, P), dev, torch.int16)
+    coef = _dev(rng.uniform(-1, 1, P), dev, torch.float32)
+    out = []
+    try:
+        for off in (False, True):
+            if off:
+                os.environ["BK_TC_NO_TAIL"] = "1"
+            tr = rf.PolicyTrainer(sd17, dev, prec=5)
+            logits = tr.forward(planes)[0].clone()
+            tr.backward(moves, coef)
+            out.append((logits, tr.grads_dict()))
+    finally:
+        os.environ.pop("BK_TC_NO_TAIL", None)
+    assert float((out[0][0] - out[1][0]).abs().max()) <= 2e-6 * float(out[1][0].abs().max())
+    differs = False
+    for k, want in out[1][1].items():
+        w, m = want.numpy(), out[0][1][k].numpy()
+        amax = float(np.abs(w).max())
+        differs = differs or not np.array_equal(w, m)
+        if amax >= 1e-4:                                           # (conv biases in front of a BatchNorm: zero up to round-off)
+            assert np.abs(m - w).max() <= 2e-6 * amax, (P, k, float(np.abs(m - w).max() / amax))
+    assert differs, "the split tail was not exercised (the two runs are bit-identical)"
+
+
 def test_clamped_log_prob_has_no_gradient(env, sd17):
     """Categorical clamps probabilities to [eps, 1 - eps] before the log: a move below eps costs -log(eps) and has zero gradient"""
     rf, dev, G = env
