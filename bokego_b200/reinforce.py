@@ -390,7 +390,8 @@ def reinforce(pi, pi_opp, optimizer, train_color, **kwargs):
         stats_rows = gather_games(trainer._rec_stats, bs, group).reshape(n_mine * bs, 7, 2, 128)
         # only the calls the reference makes: no net call follows the end of a game (legal_sample returns None, selfplay.py:44-45,
         # and the replay is bounded by len(g), selfplay.py:91-100), so rows of finished games are left out of the filter
-        played_all = gather_games(mine.unsqueeze(-1), bs, group)[..., 0] >= 0            # [step][game], all ranks' games
+        # (gathered as bytes: NCCL has no 16-bit integer type)
+        played_all = gather_games(played.to(torch.uint8).unsqueeze(-1), bs, group)[..., 0] != 0   # [step][game], all ranks' games
         seq = order[played_all.t().reshape(-1)]
         trainer.update_running(stats_rows, torch.cat([seq, seq]))
         # positions are independent under per-position BatchNorm, so games with a zero coefficient are skipped

@@ -48,7 +48,9 @@ else:
                   "grad_err_rel": float(np.abs(d["grads"] - base[f"{a}/grads"]).max() / gs),
                   "param_err": float(np.abs(d["params"] - base[f"{a}/params"]).max()),
                   "running_err": float(np.abs(d["running"] - base[f"{a}/running"]).max())}
-        assert rep[a]["wins_equal"] and rep[a]["grad_err_rel"] < 1e-3 and rep[a]["param_err"] <= 2.1e-5 and rep[a]["running_err"] < 1e-3, rep
+        # parameters: an entry whose gradient is at round-off level (the conv biases in front of a BatchNorm) gets a step of +-lr from
+        # AdamW's normalisation whatever its sign, and the order of the gradient sum decides the sign: up to 2 lr per iteration
+        assert rep[a]["wins_equal"] and rep[a]["grad_err_rel"] < 1e-3 and rep[a]["param_err"] <= 2 * 2.1e-5 and rep[a]["running_err"] < 1e-3, rep
     # replicas identical across ranks
     p = tr.params.clone()
     dist.broadcast(p, 0)
