@@ -293,6 +293,8 @@ def gather_games(local, n_games, group=None):
     from .playout import shard_range
     sizes = [hi - lo for lo, hi in (shard_range(n_games, r, world) for r in range(world))]
     most = max(sizes)
+    if local.dtype == torch.int16:                       # NCCL carries no 16-bit integers: int32 on the wire
+        return gather_games(local.to(torch.int32), n_games, group).to(torch.int16)
     pad = torch.zeros((local.shape[0], most) + tuple(local.shape[2:]), dtype=local.dtype, device=local.device)
     pad[:, : local.shape[1]] = local
     parts = [torch.empty_like(pad) for _ in range(world)]
