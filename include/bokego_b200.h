@@ -186,7 +186,9 @@ int bk_tree_finish(int64_t *N, double *V, const double *val, const int32_t *pend
 #define BK_TP_COUNT 990033
 size_t bk_train_param_count(void);
 size_t bk_train_workspace_bytes(int P);
-int bk_train_launches(int which, int P, int prec); /* kernels launched by bk_train_forward (0) / bk_train_backward (1) for P positions */
+int bk_train_launches(int which, int P, int prec); /* kernels launched by bk_train_forward (0) / bk_train_backward (1) for P positions on the
+                                                      current device (the tcgen05 3x3 kernel adds a launch per layer when the tiles left over
+                                                      after the last full round of the SMs are split, which depends on the SM count) */
 int bk_train_forward(const float *params, const float *running, const uint8_t *planes_u8, int P, int bn_mode, int prec,
                      void *workspace, float *logits, float *probs, float *stats_out, void *stream);
 int bk_train_backward(const float *params, const int16_t *moves, const float *coef, int P, int bn_mode, int prec,
