@@ -304,12 +304,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {                 // the activation chunks this thread gathered
                         const uint32_t o = off[i];
-                        float4 *hp = reinterpret_cast<float4 *>(st + o);
-                        const float4 v = *hp;
-                        float4 h, l;
-                        h.x = tf32_cut(v.x); h.y = tf32_cut(v.y); h.z = tf32_cut(v.z); h.w = tf32_cut(v.w);
-                        l.x = tf32_cut(v.x - h.x); l.y = tf32_cut(v.y - h.y); l.z = tf32_cut(v.z - h.z); l.w = tf32_cut(v.w - h.w);
-                        *hp = h;
+                        const float4 v = *reinterpret_cast<const float4 *>(st + o);   // stays as the high part: the tensor core cuts it
+                        float4 l;
+                        l.x = v.x - tf32_cut(v.x); l.y = v.y - tf32_cut(v.y); l.z = v.z - tf32_cut(v.z); l.w = v.w - tf32_cut(v.w);
                         *reinterpret_cast<float4 *>(st + 2 * OP_BYTES + o) = l;
                     }
                 }
@@ -339,20 +336,25 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
             const int dx = ti - half, dy = tap - ti * a.R - half;
             float4 va[2][4], vb[2][4], na[2][4], nb[2][4];
             auto fetch = [&](int kt, float4 (&A)[2][4], float4 (&B)[2][4]) {
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const int mc = pw + 4 * u;
+                    // four consecutive rows: one division for the first, the others by stepping (x, y); the shifted row of a valid tap
+                    // is row m + 9 dx + dy of the dense layout (the producers are instruction-bound: every row used to divide twice)
+                    const int mf = r_lo + kt * SLAB + 4 * (pw + 4 * u);
+                    const int sq0 = mf - (mf / NSQ) * NSQ;
+                    int x = sq0 / 9, y = sq0 - 9 * x;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const int m = r_lo + kt * SLAB + 4 * mc + r;
+                        const int m = mf + r;
                         const bool in_rows = m < r_hi;
-                        const int p = m / NSQ, sq = m - p * NSQ;
-                        const int x = sq / 9 + dx, y = sq - 9 * (sq / 9) + dy;
-                        const bool ok = in_rows && tap_ok && (unsigned)x < 9u && (unsigned)y < 9u;
-                        A[u][r] = (ok && !(BK_TC_DIAG & 2)) ? __ldg(reinterpret_cast<const float4 *>(a.act + ((size_t)(p * NSQ + 9 * x + y) * a.Cin + ci)))
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-                        B[u][r] = (in_rows && !(BK_TC_DIAG & 2)) ? __ldg(reinterpret_cast<const float4 *>(a.dz + (size_t)m * C + 4 * j))
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const bool ok = in_rows && tap_ok && (unsigned)(x + dx) < 9u && (unsigned)(y + dy) < 9u;
+                        A[u][r] = (ok && !(BK_TC_DIAG & 2)) ? __ldg(reinterpret_cast<const float4 *>(a.act + ((size_t)(m + 9 * dx + dy) * a.Cin + ci))) : zero;
+                        B[u][r] = (in_rows && !(BK_TC_DIAG & 2)) ? __ldg(reinterpret_cast<const float4 *>(a.dz + (size_t)m * C + 4 * j)) : zero;
+                        if (++y == 9) {
+                            y = 0;
+                            if (++x == 9) x = 0;
+                        }
                     }
                 }
             };
@@ -374,10 +376,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
                         const int c = (t + rot) & 3;
                         float4 h = c == 0 ? c0 : (c == 1 ? c1 : (c == 2 ? c2 : c3));
                         if constexpr (PREC != 0) {
+                            // the tensor core cuts the words it reads to TF32 itself: the raw value serves as the high part and the
+                            // exact remainder as the low part, bit for bit what explicit cuts of both would give
                             float4 l;
-                            const float4 x = h;
-                            h.x = tf32_cut(x.x); h.y = tf32_cut(x.y); h.z = tf32_cut(x.z); h.w = tf32_cut(x.w);
-                            l.x = tf32_cut(x.x - h.x); l.y = tf32_cut(x.y - h.y); l.z = tf32_cut(x.z - h.z); l.w = tf32_cut(x.w - h.w);
+                            l.x = h.x - tf32_cut(h.x); l.y = h.y - tf32_cut(h.y); l.z = h.z - tf32_cut(h.z); l.w = h.w - tf32_cut(h.w);
                             *reinterpret_cast<float4 *>(st + 2 * OP_BYTES + base + ((4 * j + c) >> 3) * SBO + ((4 * j + c) & 7) * 16) = l;
                         }
                         *reinterpret_cast<float4 *>(st + base + ((4 * j + c) >> 3) * SBO + ((4 * j + c) & 7) * 16) = h;
@@ -650,12 +652,11 @@ __global__ void __launch_bounds__(R3_THREADS, 1) bk_train_conv3_tc_kernel(const 
                 if constexpr (PREC != 0) {
                     for (int b = pw; b < 38; b += 4) {
                         const int row = (b >> 1) * 8 + r8, kl = (b & 1) * 4 + q4;
-                        float4 *hp = reinterpret_cast<float4 *>(smem + abuf + kl * R3_LBO + row * 16);
-                        const float4 v = *hp;
-                        float4 h, l;
-                        h.x = tf32_cut(v.x); h.y = tf32_cut(v.y); h.z = tf32_cut(v.z); h.w = tf32_cut(v.w);
-                        l.x = tf32_cut(v.x - h.x); l.y = tf32_cut(v.y - h.y); l.z = tf32_cut(v.z - h.z); l.w = tf32_cut(v.w - h.w);
-                        *hp = h;
+                        // the raw words stay where they landed as the high part (the tensor core cuts what it reads to TF32); the low
+                        // part is the exact remainder, cut by the tensor core as well
+                        const float4 v = *reinterpret_cast<const float4 *>(smem + abuf + kl * R3_LBO + row * 16);
+                        float4 l;
+                        l.x = v.x - tf32_cut(v.x); l.y = v.y - tf32_cut(v.y); l.z = v.z - tf32_cut(v.z); l.w = v.w - tf32_cut(v.w);
                         *reinterpret_cast<float4 *>(smem + abuf + R3_G_BYTES + kl * R3_LBO + row * 16) = l;
                     }
                 }
