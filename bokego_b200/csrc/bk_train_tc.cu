@@ -178,6 +178,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
     return ((uint64_t)hi << 32) | (((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16));
 }
 
+#ifndef BK_R3_PROF
+#define BK_R3_PROF 0                               // measurement build: clock64 stamps of CTA 0 (tools/prof_train_conv3.py)
+#endif
+#if BK_R3_PROF
+__device__ long long g_r3_prof[5 * 1024];          // [role: MMA issue / weight loader / result of the 3x3 kernel, MMA issue / producer warp 4 of a 3x3 weight gradient][use < 256][4 stamps]
+#define R3_STAMP(role, idx, k) do { if (blockIdx.x == 0 && (idx) < 256) g_r3_prof[(role) * 1024 + (idx) * 4 + (k)] = clock64(); } while (0)
+#else
+#define R3_STAMP(role, idx, k) do {} while (0)
+#endif
+
 // The result rows of a 128 x 128 tile leave through a per-warp transposition buffer (32 x 33 floats).  A thread owns a ROW of 128
 // floats, and stored from there a warp instruction touches 32 different lines, 16 bytes each: 12 k cycles per tile
 // (profiles/r02u_train_conv3.md).  Instead, 32 columns at a time: thread = row writes its 32 values (pitch 33: conflict-free), then
@@ -362,10 +372,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
             // the kernel was 25 % slower with it, so every lane stores its columns in order)
             constexpr int rot = 0;
             if (KT > 0) fetch(0, va, vb);
+            // Clock stamps of a slab (profiles/r02z_wgrad_clocks.txt; 1,820 cycles against 1,250 of tensor time): issuing the 16 loads of
+            // the next slab 530 (32 KiB per slab and SM is what the L2 port delivers in that time; the warp waits in the issue),
+            // transposing and storing 860, the register copies at the end 290.  Tried and slower: half of the loads between the stores
+            // (2,470 per slab: the later loads are then waited for), two register sets that swap roles instead of the copies
+            // (+0.5 % on the step).
             for (int kt = 0; kt < KT; ++kt) {
                 const int s = kt % STAGES;
+                const bool stamp = PREC != 0 && a.Cin == C && blockIdx.y == 0 && ptid == 0;
+                if (stamp) R3_STAMP(4, kt, 0);
                 if (kt + 1 < KT) fetch(kt + 1, na, nb);           // the next slab's loads are in flight while this one is stored
+                if (stamp) R3_STAMP(4, kt, 1);
                 if (kt >= STAGES) mbar_wait(s_bar + 8 * (BAR_EMPTY + s), ((kt / STAGES) & 1) ^ 1);
+                if (stamp) R3_STAMP(4, kt, 2);
                 uint8_t *st = smem + s * STAGE;
                 auto put = [&](const float4 (&v)[4], uint32_t base) {
                     // column c of the block = the four rows' c-th components: one 16-byte K chunk of row (4 j + c)
@@ -392,6 +411,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
                 }
                 fence_proxy_async();
                 mbar_arrive(s_bar + 8 * (BAR_FULL + s));
+                if (stamp) R3_STAMP(4, kt, 3);
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
 #pragma unroll
@@ -406,7 +426,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
         int c = 0;                                     // chain counter: chain c accumulates in TMEM buffer c % NBUF
         for (int kt = 0; kt < KT; ++kt) {
             const int s = kt % STAGES;
+            bool stamp = false;                       // (blockIdx.x == 0 inside the macro)
+            if constexpr (MODE == 1 && PREC != 0) stamp = a.Cin == C && blockIdx.y == 0 && lane == 0;
+            if (stamp) R3_STAMP(3, kt, 0);
             mbar_wait(s_bar + 8 * (BAR_FULL + s), (kt / STAGES) & 1);
+            if (stamp) R3_STAMP(3, kt, 1);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t st = s_base + (uint32_t)(s * STAGE);
@@ -442,6 +466,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
             }
             c += (SLAB / 8) / CHAIN;
             __syncwarp();
+            if (stamp) R3_STAMP(3, kt, 2);
         }
     } else {
         // =============================== result warps (thread = output row) ===============================
@@ -556,15 +581,6 @@ static_assert(8 * R3_NBARS + 4 <= 256, "barrier area");
 
 #ifndef BK_R3_STORE
 #define BK_R3_STORE 2                              // measurement builds: 0 = no output stores, 1 = thread = row stores
-#endif
-#ifndef BK_R3_PROF
-#define BK_R3_PROF 0                               // measurement build: clock64 stamps of CTA 0 (tools/prof_train_conv3.py)
-#endif
-#if BK_R3_PROF
-__device__ long long g_r3_prof[3 * 1024];          // [role: MMA issue / weight loader / result][use < 256][4 stamps]
-#define R3_STAMP(role, idx, k) do { if (blockIdx.x == 0 && (idx) < 256) g_r3_prof[(role) * 1024 + (idx) * 4 + (k)] = clock64(); } while (0)
-#else
-#define R3_STAMP(role, idx, k) do {} while (0)
 #endif
 struct R3Ring {                                    // position in a ring of n buffers and the phase of its current use
     int i;

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bokego_b200 import reinforce as rf, _lib  # noqa: E402
 
-P = int(sys.argv[1]) if len(sys.argv) > 1 else 576
+P = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 576
 dev = torch.device("cuda", 0)
 g = os.path.join(ROOT, "tests", "golden")
 sd17 = dict(np.load(os.path.join(g, "weights_policy_17.npz")))
@@ -27,11 +27,28 @@ for _ in range(3):
     tr.forward(planes)
 torch.cuda.synchronize()
 L = _lib.lib()
-buf = np.zeros(3 * 1024, dtype=np.int64)
+if "--backward" in sys.argv:                      # also a backward pass: stamps of the MMA issuer of the last 3x3 weight gradient (CTA (0, 0))
+    moves = torch.randint(0, 81, (P,), device=dev).to(torch.int16)
+    tr.backward(moves, torch.full((P,), 1.0 / 16, device=dev))
+    torch.cuda.synchronize()
+buf = np.zeros(5 * 1024, dtype=np.int64)
 L.bk_r3_prof_read.restype = C.c_int
 L.bk_r3_prof_read.argtypes = [C.c_void_p]
 assert L.bk_r3_prof_read(buf.ctypes.data) == 0
-mma, ld, res = (buf[i * 1024:(i + 1) * 1024].reshape(256, 4) for i in range(3))
+mma, ld, res, wg, wp = (buf[i * 1024:(i + 1) * 1024].reshape(256, 4) for i in range(5))
+nw = int((wg[:, 0] > 0).sum())
+if nw:
+    per = np.diff(wg[:nw, 0])
+    print(f"weight gradient, MMA issuer of CTA (0, 0): {nw} slabs, period mean {per.mean():.0f} (median {np.median(per):.0f}); waits for the "
+          f"producers' slab mean {(wg[:nw, 1] - wg[:nw, 0]).mean():.0f}, issue (incl. waiting for an accumulator) {(wg[:nw, 2] - wg[:nw, 1]).mean():.0f}")
+    npd = int((wp[:, 0] > 0).sum())
+    if npd > 1:
+        print(f"weight gradient, producer warp 4: period mean {np.diff(wp[:npd, 0]).mean():.0f}; issuing the next slab's loads {(wp[:npd, 1] - wp[:npd, 0]).mean():.0f}, "
+              f"waiting for the stage {(wp[:npd, 2] - wp[:npd, 1]).mean():.0f}, transposing / splitting / storing (incl. waiting for the loads) "
+              f"{(wp[:npd, 3] - wp[:npd, 2]).mean():.0f}, rest {(np.diff(wp[:npd, 0]) - (wp[:npd - 1, 3] - wp[:npd - 1, 0])).mean():.0f}")
+    print("  slab: period wait_full issue")
+    for i in range(min(nw - 1, 46)):
+        print(f"  {i:3d} {per[i]:6d} {wg[i, 1] - wg[i, 0]:6d} {wg[i, 2] - wg[i, 1]:6d}")
 n = int((mma[:, 0] > 0).sum())
 t0 = mma[0, 0]
 print(f"P={P}: {n} slabs on CTA 0, {mma[n - 1, 3] - t0} cycles from the first slab's top to the last slab's issue")
