@@ -17,6 +17,7 @@
 // moments are flat float32 buffers in the GEMM layout (offsets in include/bokego_b200.h); everything is deterministic
 // (no atomics).  This first version of the row keeps the training GEMMs on the warp-level MMA path; moving them onto
 // tcgen05 like the inference kernel is the next step.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -354,7 +355,9 @@ __global__ void bk_train_transpose_kernel(const float *w, float *wd, int n_mat)
 
 // The K-major B operand of the tcgen05 kernels (bk_train_tc.cu), split for 3xTF32 once per step instead of once per tile:
 // hi[k / 4][co][k % 4] = rna_tf32(w[k][co]), lo[...] = rna_tf32(w - hi); n floats in total
-__global__ void bk_train_pack_w_kernel(const float *w, float *hi, float *lo, int n)
+// bh / bl: the same two parts rounded to bf16 and packed [k / 8][co][k % 8] (K-major operands of kind::f16: the 3x3 kernel's
+// BK_R3_LO_BF16 build computes the low-order products with them)
+__global__ void bk_train_pack_w_kernel(const float *w, float *hi, float *lo, __nv_bfloat16 *bh, __nv_bfloat16 *bl, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -363,6 +366,11 @@ __global__ void bk_train_pack_w_kernel(const float *w, float *hi, float *lo, int
     const float x = w[i], h = __uint_as_float(f2tf32(x));
     hi[o] = h;
     lo[o] = __uint_as_float(f2tf32(x - h));
+    if (bh) {                                     // only the BK_R3_LO_BF16 measurement build of the 3x3 kernel reads these
+        const size_t o8 = (size_t)(k >> 3) * (8 * C) + co * 8 + (k & 7);
+        bh[o8] = __float2bfloat16_rn(x);
+        bl[o8] = __float2bfloat16_rn(x - h);
+    }
 }
 
 // z[i] = z[i] + z[n + i] + z[2n + i] + z[3n + i] (in that order): the four channel-group partial results of a small-batch conv
@@ -572,7 +580,7 @@ __global__ void bk_adamw_kernel(float *p, const float *g, float *m, float *v, si
 
 // ---- workspace (floats) ----
 struct Ws {
-    size_t x0, z[7], a[7], mean[7], rstd[7], da, dz, logits, dlogit, part, dwpart, wd, wpack, wpack_lo, wdpack, wdpack_lo, wpart, tail, total;
+    size_t x0, z[7], a[7], mean[7], rstd[7], da, dz, logits, dlogit, part, dwpart, wd, wpack, wpack_lo, wdpack, wdpack_lo, wpart, tail, wb16, wdb16, total;
     int splits, rows_per_split;
 };
 
@@ -613,6 +621,8 @@ Ws ws_layout(int P)
     w.rows_per_split = rps;
     w.wpart = take((size_t)splits * 9 * C * C);
     w.tail = take((size_t)BK_CONV3_TAIL_FLOATS);    // partial results of the split tail of the staged-once 3x3 kernel
+    w.wb16 = take((size_t)BK_TP_VEC);               // all conv weights as bf16 high parts, then bf16 low parts (BK_TP_VEC elements each)
+    w.wdb16 = take((size_t)6 * 9 * C * C);          // ... of the data gradient's transposed weights
     w.total = o;
     return w;
 }
@@ -686,12 +696,17 @@ extern "C" int bk_train_forward(const float *params, const float *running, const
     float *ws = static_cast<float *>(workspace);
     const int n0 = P * NSQ * C0;
     bk_train_pack_kernel<<<(n0 + 255) / 256, 256, 0, st>>>(planes_u8, ws + w.x0, P);
-    if (prec >= 4) bk_train_pack_w_kernel<<<(BK_TP_VEC + 255) / 256, 256, 0, st>>>(params, ws + w.wpack, ws + w.wpack_lo, BK_TP_VEC);
+    __nv_bfloat16 *wb = bk_tc_lo_bf16() ? reinterpret_cast<__nv_bfloat16 *>(ws + w.wb16) : nullptr;
+    if (prec >= 4) bk_train_pack_w_kernel<<<(BK_TP_VEC + 255) / 256, 256, 0, st>>>(params, ws + w.wpack, ws + w.wpack_lo, wb, wb ? wb + BK_TP_VEC : nullptr, BK_TP_VEC);
     for (int l = 0; l < 7; ++l) {
         ConvArgs a;
         a.in = l == 0 ? ws + w.x0 : ws + w.a[l - 1];
         a.w = prec >= 4 ? ws + w.wpack + w_off(l) : params + w_off(l);
         a.w_lo = ws + w.wpack_lo + w_off(l);
+        if (wb) {
+            a.w_bh = reinterpret_cast<const unsigned short *>(wb + w_off(l));
+            a.w_bl = reinterpret_cast<const unsigned short *>(wb + BK_TP_VEC + w_off(l));
+        }
         a.bias = params + vec_off(l, 0);
         a.out = ws + w.z[l];
         a.M = P * NSQ;
@@ -726,7 +741,8 @@ extern "C" int bk_train_backward(const float *params, const int16_t *moves, cons
     float *ws = static_cast<float *>(workspace);
     const int M = P * NSQ;
     bk_train_transpose_kernel<<<dim3(4, 4, 54), dim3(32, 8), 0, st>>>(params + BK_TP_W1, ws + w.wd, 54);
-    if (prec >= 4) bk_train_pack_w_kernel<<<(6 * 9 * C * C + 255) / 256, 256, 0, st>>>(ws + w.wd, ws + w.wdpack, ws + w.wdpack_lo, 6 * 9 * C * C);
+    __nv_bfloat16 *wdb = bk_tc_lo_bf16() ? reinterpret_cast<__nv_bfloat16 *>(ws + w.wdb16) : nullptr;
+    if (prec >= 4) bk_train_pack_w_kernel<<<(6 * 9 * C * C + 255) / 256, 256, 0, st>>>(ws + w.wd, ws + w.wdpack, ws + w.wdpack_lo, wdb, wdb ? wdb + 6 * 9 * C * C : nullptr, 6 * 9 * C * C);
     bk_train_head_bwd_kernel<<<P, 128, 0, st>>>(ws + w.logits, ws + w.a[6], params + BK_TP_HEADW, moves, coef, nlp_out,
                                                 ws + w.dlogit, ws + w.da, ws + w.dwpart);
     bk_train_colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(ws + w.dwpart, grads + BK_TP_HEADW, P, C, accumulate);
@@ -753,6 +769,10 @@ extern "C" int bk_train_backward(const float *params, const int16_t *moves, cons
             a.in = ws + w.dz;
             a.w = (prec >= 4 ? ws + w.wdpack : ws + w.wd) + (size_t)(l - 1) * 9 * C * C;
             a.w_lo = ws + w.wdpack_lo + (size_t)(l - 1) * 9 * C * C;
+            if (wdb) {
+                a.w_bh = reinterpret_cast<const unsigned short *>(wdb + (size_t)(l - 1) * 9 * C * C);
+                a.w_bl = reinterpret_cast<const unsigned short *>(wdb + (size_t)(6 + l - 1) * 9 * C * C);
+            }
             a.bias = nullptr;
             a.out = ws + w.da;
             a.M = M;

@@ -21,6 +21,8 @@ struct BkConvArgs {
                             576 positions: 450 tiles on 148 SMs = three waves and a quarter instead of four. */
     int tail_full = 0;   /* set by bk_tc_launch_conv: tiles below this index run whole, 0 = no split tail */
     int n_items = 0;     /* set by bk_tc_launch_conv: work items of the persistent CTAs (whole tiles + single-group items) */
+    const unsigned short *w_bh = nullptr, *w_bl = nullptr;   /* staged-once 3x3 kernel built with BK_R3_LO_BF16: the weights' high and low
+                            parts as bf16, packed [k / 8][co][k % 8] (the low-order products of 3xTF32 on kind::f16) */
 };
 #define BK_CONV3_TAIL_MAX 24                                  /* most tiles a split tail may have */
 #define BK_CONV3_TAIL_FLOATS (4 * BK_CONV3_TAIL_MAX * 128 * 128)
@@ -34,6 +36,7 @@ struct BkWgradArgs {
 
 /* tcgen05 versions (bk_train_tc.cu); three_x != 0: 3xTF32 split operands.  Return a cudaError_t as int. */
 int bk_tc_set_attrs(void);
+int bk_tc_lo_bf16(void);       /* 1 in the BK_R3_LO_BF16 measurement build of the 3x3 kernel (it reads w_bh / w_bl) */
 int bk_tc_conv3_tail(int P);   /* tiles of a P-position 3x3 conv that run whole on this device when its tail is split (see tail_part), else 0 */
 void bk_tc_launch_conv(const BkConvArgs &a, int three_x, cudaStream_t st);
 void bk_tc_launch_wgrad(const BkWgradArgs &a, int splits, int three_x, cudaStream_t st);
