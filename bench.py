@@ -359,8 +359,8 @@ def reinforce_leg(dev, sd17, sd19, with_cpu):
                                    "frac_of_tf32_peak": ach / tf_peak, "precision": name}
     out["peak"] = {"tflops": tf_peak, "source": "half of the measured 16-bit dense peak (TF32 operands)",
                    "note": "clock stamps of the 3x3 kernel (profiles/r02u_train_conv3.md): a kind::tf32 MMA of 128x128x8 takes ~104 cycles, "
-                           "~745 TFLOP/s at 1.92 GHz; a 3xTF32 product issues three times its useful work, so ~248 TFLOP/s of useful work is "
-                           "the ceiling of the default precision"}
+                           "~745 TFLOP/s at 1.92 GHz with M = N = 128 cta_group::1 MMAs; a 3xTF32 product issues three times its useful work, so "
+                           "~248 TFLOP/s of useful work is the ceiling of the default precision with these MMAs"}
     # the same step on a batch that fills the GPU (2,048 positions = one forward / backward chunk), default precision
     P2 = 2048
     planes2 = torch.from_numpy(np.ascontiguousarray(calls[np.arange(P2) % len(calls)])).to(dev)
