@@ -189,3 +189,46 @@ def test_training_symbols_exported():
     # 576 positions: 23 on a B200, one more launch per 3x3 conv for its split tail
     assert L.bk_train_launches(0, 576, 5) in (17, 23) and L.bk_train_launches(0, 16, 5) == 23 and L.bk_train_launches(1, 576, 1) == 38
     assert L.bk_train_workspace_bytes(0) == 0 and L.bk_train_workspace_bytes(16) > 16 * 81 * 128 * 4 * 14
+
+
+def _tf32_cut(x):
+    """the tensor core's own cut of an fp32 word to TF32 (10 mantissa bits, toward zero) = csrc/bk_train_tc.cu tf32_cut"""
+    return (np.asarray(x, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def _tf32_rna(x):
+    """cvt.rna.tf32.f32 (round to nearest, ties away) as the weight pack kernel applies it"""
+    u = np.asarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64) + np.uint64(0x1000)
+    return (u & np.uint64(0xFFFFE000)).astype(np.uint32).view(np.float32)
+
+
+def _bf16_rn(x):
+    u = np.asarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = u + np.uint64(0x7FFF) + ((u >> np.uint64(16)) & np.uint64(1))
+    return (u & np.uint64(0xFFFF0000)).astype(np.uint32).view(np.float32)
+
+
+def test_3xtf32_split_is_fp32_grade_and_bf16_low_parts_are_not():
+    """the arithmetic of the tcgen05 training GEMMs restated in numpy (exact products and sums in float64, so only the SPLIT is
+    measured): activations x = hi + lo with hi = the word cut to TF32 and lo = the exact remainder, cut again by the tensor core;
+    weights w = rna(w) + rna(w - rna(w)); the product is hi*hi + hi*lo + lo*hi (csrc/bk_train_tc.cu: the N = 256 MMA
+    A_hi x [B_hi | B_lo] and A_lo x B_hi).  What is dropped is lo*lo and the second cut: ~2^-21 per product, so a K = 1,152 dot product
+    keeps fp32 accuracy.  With the low-order products on bf16 copies (the rejected BK_R3_LO_BF16 build, profiles/r02zz_lo_bf16.txt)
+    every product carries 2^-20 .. 2^-18 instead: 1e-6 of the largest entry where the split leaves 1.4e-7, several times worse already
+    in one dot product, which the data gradient's cancellation then amplifies past the fp32-grade bar of the recorded iteration."""
+    rng = np.random.default_rng(5)
+    x = np.maximum(rng.standard_normal((256, 1152)), 0).astype(np.float32)          # post-ReLU activations
+    w = (0.05 * rng.standard_normal((1152, 128))).astype(np.float32)
+    exact = x.astype(np.float64) @ w.astype(np.float64)
+    xh = _tf32_cut(x)
+    xl = _tf32_cut(x - xh)
+    wh = _tf32_rna(w)
+    wl = _tf32_rna(w - wh)
+    assert np.array_equal(xh.astype(np.float64) + (x - xh).astype(np.float64), x.astype(np.float64))   # the remainder is exact
+    f = lambda a: a.astype(np.float64)
+    split = f(xh) @ f(wh) + f(xh) @ f(wl) + f(xl) @ f(wh)
+    bf = f(xh) @ f(wh) + f(_bf16_rn(x)) @ f(_bf16_rn(w - wh)) + f(_bf16_rn(x - xh)) @ f(_bf16_rn(w))
+    scale = np.abs(exact).max()
+    e_split, e_bf = np.abs(split - exact).max() / scale, np.abs(bf - exact).max() / scale
+    assert e_split < 2e-7, e_split                      # below fp32's own 6e-8 .. 1e-7 per rounding of the result
+    assert e_bf > 4 * e_split and e_bf < 1e-4, (e_bf, e_split)
