@@ -68,6 +68,8 @@ def _sig(L):
     L.bk_train_workspace_bytes.argtypes = [i32]
     L.bk_train_launches.restype = i32
     L.bk_train_launches.argtypes = [i32, i32, i32]
+    L.bk_train_conv3_schedule.restype = i32
+    L.bk_train_conv3_schedule.argtypes = [i32, i32, i32, vp]
     L.bk_train_forward.restype = i32
     L.bk_train_forward.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     L.bk_train_backward.restype = i32

@@ -919,15 +919,37 @@ static int bk_tc_sm_count()
     return cached[dev];
 }
 
-// The tiles left over after the last complete wave of the grid run as four quarter-length CTAs each when those fit beside each
-// other: returns the number of tiles that run whole (a multiple of the SM count), 0 = no split tail for P positions on this device.
+// The tiles left over after the last complete round of the grid run as four quarter-length work items each when those fit beside
+// each other: the number of tiles that run whole (a multiple of the SM count), 0 = no split tail.  Pure arithmetic: bk_train_conv3_schedule
+// exposes it to the tests.
+static int conv3_tail_full(int P, int n_sm)
+{
+    const int n_tiles = (P * 100 + 127) / 128;
+    const int full = n_sm > 0 ? n_tiles / n_sm * n_sm : 0, rest = n_tiles - full;
+    return (full > 0 && rest > 0 && rest <= BK_CONV3_TAIL_MAX && 4 * rest <= n_sm) ? full : 0;
+}
+
+// ... for P positions on the current device
 int bk_tc_conv3_tail(int P)
 {
     const bool off = getenv("BK_TC_NO_TAIL") != nullptr;             // measurement / tests: read per call, so one process can compare both
+    return off ? 0 : conv3_tail_full(P, bk_tc_sm_count());
+}
+
+// Work items of the persistent 3x3 training kernel for P positions on a device of n_sm SMs (ksplit = 4: the small-batch forward, one
+// channel group per item): out[0] = tiles of 128 raster rows, out[1] = tiles that run whole when the tail is split (0 = no split),
+// out[2] = work items, out[3] = CTAs launched.  No device needed.
+extern "C" int bk_train_conv3_schedule(int P, int n_sm, int ksplit, int *out)
+{
+    if (P <= 0 || n_sm <= 0 || !out || (ksplit != 1 && ksplit != 4)) return -1;
     const int n_tiles = (P * 100 + 127) / 128;
-    const int n_sm = bk_tc_sm_count();
-    const int full = n_sm > 0 ? n_tiles / n_sm * n_sm : 0, rest = n_tiles - full;
-    return (!off && full > 0 && rest > 0 && rest <= BK_CONV3_TAIL_MAX && 4 * rest <= n_sm) ? full : 0;
+    const int full = ksplit == 1 ? conv3_tail_full(P, n_sm) : 0;
+    const int n_items = ksplit > 1 ? 4 * n_tiles : (full > 0 ? full + 4 * (n_tiles - full) : n_tiles);
+    out[0] = n_tiles;
+    out[1] = full;
+    out[2] = n_items;
+    out[3] = n_sm < n_items ? n_sm : n_items;
+    return 0;
 }
 
 static bool getenv_old_conv()

@@ -189,6 +189,10 @@ size_t bk_train_workspace_bytes(int P);
 int bk_train_launches(int which, int P, int prec); /* kernels launched by bk_train_forward (0) / bk_train_backward (1) for P positions on the
                                                       current device (the tcgen05 3x3 kernel adds a launch per layer when the tiles left over
                                                       after the last full round of the SMs are split, which depends on the SM count) */
+int bk_train_conv3_schedule(int P, int n_sm, int ksplit, int *out4); /* host arithmetic only: the work items of the persistent tcgen05 3x3
+                                                      kernel for P positions on n_sm SMs -- out4 = tiles of 128 raster rows, tiles that run
+                                                      whole when the left-over tiles are split into single-channel-group items (0 = no split),
+                                                      work items, CTAs; ksplit = 4 is the small-batch forward.  -1 on bad arguments */
 int bk_train_forward(const float *params, const float *running, const uint8_t *planes_u8, int P, int bn_mode, int prec,
                      void *workspace, float *logits, float *probs, float *stats_out, void *stream);
 int bk_train_backward(const float *params, const int16_t *moves, const float *coef, int P, int bn_mode, int prec,

@@ -232,3 +232,34 @@ def test_3xtf32_split_is_fp32_grade_and_bf16_low_parts_are_not():
     e_split, e_bf = np.abs(split - exact).max() / scale, np.abs(bf - exact).max() / scale
     assert e_split < 2e-7, e_split                      # below fp32's own 6e-8 .. 1e-7 per rounding of the result
     assert e_bf > 4 * e_split and e_bf < 1e-4, (e_bf, e_split)
+
+
+def test_conv3_work_item_schedule():
+    """the persistent 3x3 training kernel's work items (csrc/bk_train_tc.cu: bk_train_conv3_schedule, host arithmetic): whole tiles of
+    128 raster rows (100 per position), the tiles left over after the last full round of the SMs as four single-channel-group items
+    each when they are few, one channel group per item for the small-batch forward"""
+    import ctypes as C
+    from bokego_b200 import _lib
+    L = _lib.lib()
+
+    def sched(P, n_sm=148, ksplit=1):
+        out = (C.c_int * 4)()
+        assert L.bk_train_conv3_schedule(P, n_sm, ksplit, out) == 0
+        return list(out)
+
+    assert sched(576) == [450, 444, 444 + 4 * 6, 148]           # 16 games x 36 moves: three rounds and six tiles split four ways
+    assert sched(190) == [149, 148, 152, 148]
+    assert sched(220) == [172, 148, 148 + 4 * 24, 148]          # 24 tail tiles: the most
+    assert sched(221) == [173, 0, 173, 148]                     # 25: run whole
+    assert sched(2048) == [1600, 0, 1600, 148]                  # 120 left over: too many to split
+    assert sched(100) == [79, 0, 79, 79]                        # less than one round: one CTA per tile
+    assert sched(148 * 128 // 100) == [148, 0, 148, 148]        # exactly one round
+    assert sched(16, ksplit=4) == [13, 0, 52, 52]               # the 16-position forward of a self-play move
+    assert sched(64, ksplit=4) == [50, 0, 200, 148]
+    assert sched(576, n_sm=132) == [450, 0, 450, 132]           # 54 left over on 132 SMs: no split
+    for P in range(1, 700, 7):                                   # every tile is covered exactly once
+        n_tiles, full, items, ctas = sched(P)
+        assert n_tiles == (100 * P + 127) // 128 and ctas == min(items, 148)
+        assert items == (n_tiles if full == 0 else full + 4 * (n_tiles - full)) and full % 148 == 0 and full <= n_tiles
+    out = (C.c_int * 4)()
+    assert L.bk_train_conv3_schedule(0, 148, 1, out) == -1 and L.bk_train_conv3_schedule(16, 148, 2, out) == -1
