@@ -43,6 +43,12 @@ constexpr int MAX_STAGES = 6;
 #ifndef BK_TC_DIAG
 #define BK_TC_DIAG 0
 #endif
+#ifndef BK_R3_LO_BF16
+#define BK_R3_LO_BF16 0                            // measurement build, rejected: the low-order products (A_hi x B_lo, A_lo x B_hi: 2^-11 of the
+#endif                                             // result) on kind::f16 with bf16 copies of the four parts, one K = 16 MMA where two TF32 MMAs
+                                                   // run.  3.5 % off the step, but 2^-20 per product is not enough under the cancellation of the
+                                                   // data gradient: nine in ten entries of conv.1.weight's gradient within 2.5e-4 instead of
+                                                   // 1e-4 of the largest (test_reference_iteration fails; profiles/r02zz_lo_bf16.txt)
 #ifndef BK_TC_CHAIN
 #define BK_TC_CHAIN 4    // K steps per 3xTF32 accumulation chain = one slab (12 MMAs).  Measured on the recorded reference iteration: 1, 2 and 4
 #endif                   // are equally accurate (1e-6 against FFMA) and 4 is 5 % faster; 16 (four slabs, 48 MMAs) leaves 1e-3 in the early layers
@@ -150,6 +156,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+#if BK_R3_LO_BF16
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
 {
     asm volatile(
@@ -159,6 +166,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+#endif
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile(
@@ -574,12 +582,6 @@ constexpr int R3_G_BYTES = 8 * R3_LBO;             // one part (hi or lo) of one
 constexpr int R3_THREADS = 320;
 constexpr int R3_NA = 3;                           // rotating group buffers
 constexpr int R3_NROT = 2;                         // two accumulators of 256 columns ([hi | lo] halves), the chains take them in turn
-#ifndef BK_R3_LO_BF16
-#define BK_R3_LO_BF16 0                            // measurement build, rejected: the low-order products (A_hi x B_lo, A_lo x B_hi: 2^-11 of the
-#endif                                             // result) on kind::f16 with bf16 copies of the four parts, one K = 16 MMA where two TF32 MMAs
-                                                   // run.  3.5 % off the step, but 2^-20 per product is not enough under the cancellation of the
-                                                   // data gradient: nine in ten entries of conv.1.weight's gradient within 2.5e-4 instead of
-                                                   // 1e-4 of the largest (test_reference_iteration fails; profiles/r02zz_lo_bf16.txt)
 #ifndef BK_R3_CHAIN_SLABS
 #define BK_R3_CHAIN_SLABS 3                        // slabs per hi * hi chain (4 MMAs each)
 #endif
