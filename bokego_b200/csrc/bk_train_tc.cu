@@ -560,11 +560,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) bk_train_gemm_tc_kernel(const Ar
 //     Now all roles run loops over the CTA's work items with ring positions that carry over from item to item: the staging warps
 //     gather the first groups of the next tile into free group buffers (three rotating buffers) while the MMAs of the current one
 //     run, the weight loader never stops, and the result warps store tile t while the tensor pipe is in the first chains of t + 1;
-//   * a kind::tf32 MMA of 128 x 128 x 8 reads 8 KiB of operands from shared memory and takes ~104 cycles, not the 64 of the tensor
-//     pipe (clock stamps: the issuing thread waits on no barrier, windows on 8-row boundaries / no weight copies / other
-//     accumulators change nothing) -- the operand fetch is the limit.  So the two products that share the operand A_hi are ONE
-//     MMA with N = 256: A_hi x [B_hi | B_lo] -> [hi | lo] halves of a 256-column accumulator (12 KiB of operands for the work of
-//     two MMAs), and A_lo x B_hi goes into the lo half: two MMAs per K step instead of three;
+//   * a kind::tf32 MMA of 128 x 128 x 8 (cta_group::1, both operands in shared memory) takes ~104 cycles here, not 64 (clock stamps:
+//     the issuing thread waits on no barrier; windows on 8-row boundaries / no weight copies / other accumulators change nothing).
+//     The two products that share the operand A_hi are ONE MMA with N = 256, A_hi x [B_hi | B_lo] -> the [hi | lo] halves of a
+//     256-column accumulator, and A_lo x B_hi goes into the lo half: two MMAs per K step instead of three.  The N = 256 form takes
+//     ~190 cycles -- the cost follows the tensor work, not the operand bytes -- so this bought 5 % per slab, and what it really gave is
+//     the next point;
 //   * the accumulation chains are split by magnitude.  What the tensor core's truncating fp32 accumulation costs is one ulp of the
 //     ACCUMULATOR per MMA, so the large hi * hi products are kept apart from the lo * hi and hi * lo products (2^-11 of them);
 //     a chain is BK_R3_CHAIN_SLABS slabs = 12 accumulations per half -- as many as the 12-MMA chains measured equivalent to
