@@ -159,3 +159,66 @@ def test_bias_rows_reproduce_fp32_bias(sd17):
         b = _bias_step(blob, off, n_full)
         assert np.abs(b[:2].sum(0) - bias[layer]).max() <= 2e-6 * max(1.0, np.abs(bias[layer]).max())
         assert not b[2:].any()
+
+
+def test_training_raster_of_the_persistent_3x3_kernel():
+    """the index arithmetic of bk_train_conv3_tc_kernel (csrc/bk_train_tc.cu) in numpy: GEMM rows are the rows of a padded raster --
+    position p, square (x, y) at row 100 p + 10 + 10 x + y, ten zero rows above every board and one zero column to its right -- a tile
+    is 128 rows staged with an 11-row halo on both sides, a tap (dx, dy) is the row shift sign * (10 dx + dy) of the staged rows, the
+    reduction runs channel group by channel group (the split tail gives each group to a work item of its own and adds the four partial
+    results in group order), and 81 of every 100 rows go to the dense [P][81][C] output.  Forward convolution (sign = +1) and data
+    gradient (sign = -1, weights mirrored and transposed per tap by the caller) against torch's conv2d / its autograd."""
+    rng = np.random.default_rng(3)
+    P, Cc = 5, 8                                    # 5 positions = 500 raster rows = 4 tiles, the last one partial; 8 channels = 4 groups of 2
+    x = rng.standard_normal((P, 81, Cc)).astype(np.float32)
+
+    def staged_row(rr):                             # the staging warps' gather of raster row rr (zero fill outside the boards)
+        if rr < 0:
+            return np.zeros(Cc, np.float32)
+        p, o = rr // 100, rr % 100 - 10
+        xx, yy = o // 10, o % 10                    # floor division: o < 0 (the ten zero rows) gives xx < 0
+        ok = p < P and o >= 0 and yy < 9
+        return x[p, 9 * xx + yy] if ok else np.zeros(Cc, np.float32)
+
+    def kernel(w_taps, sign, split_groups):
+        """w_taps[tap][ci][co]; returns the dense [P][81][Cc] output the result warps write"""
+        out = np.zeros((P, 81, Cc), np.float64)
+        n_tiles = (100 * P + 127) // 128
+        for tile in range(n_tiles):
+            R0 = 128 * tile
+            stage = np.stack([staged_row(R0 - 11 + r) for r in range(150)])          # rows R0 - 11 .. R0 + 138
+            acc = np.zeros((128, Cc), np.float64)
+            parts = []
+            for g in range(4):                      # channel groups; every group runs its nine taps
+                part = np.zeros((128, Cc), np.float64)
+                for tap in range(9):
+                    ti = tap // 3
+                    shift = sign * (10 * (ti - 1) + (tap - 3 * ti - 1))
+                    a = stage[11 + shift: 11 + shift + 128, 2 * g: 2 * g + 2].astype(np.float64)
+                    part += a @ w_taps[tap][2 * g: 2 * g + 2].astype(np.float64)
+                parts.append(part)
+                acc += part
+            if split_groups:                        # the tail kernel: partial results added in group order
+                acc = parts[0] + parts[1] + parts[2] + parts[3]
+            for row in range(128):
+                rr = R0 + row
+                p, o = rr // 100, rr % 100 - 10
+                xx, yy = o // 10, o % 10
+                if p < P and o >= 0 and yy < 9:
+                    out[p, 9 * xx + yy] = acc[row]
+        return out
+
+    w = (0.3 * rng.standard_normal((Cc, Cc, 3, 3))).astype(np.float32)              # torch layout [co][ci][kx][ky]
+    xt = torch.from_numpy(x).reshape(P, 9, 9, Cc).permute(0, 3, 1, 2).double().requires_grad_(True)
+    y = torch.nn.functional.conv2d(xt, torch.from_numpy(w).double(), padding=1)
+    want = y.permute(0, 2, 3, 1).reshape(P, 81, Cc).detach().numpy()
+    w_fwd = np.stack([w[:, :, tap // 3, tap % 3].T for tap in range(9)])              # [tap][ci][co]
+    for split in (False, True):
+        assert np.abs(kernel(w_fwd, +1, split) - want).max() < 1e-5
+    # data gradient: d x = conv of d y with the mirrored taps and transposed weights (bk_train.cu: bk_train_transpose_kernel), sign = -1
+    dy = rng.standard_normal((P, 81, Cc)).astype(np.float32)
+    y.backward(torch.from_numpy(dy).reshape(P, 9, 9, Cc).permute(0, 3, 1, 2).double())
+    want_dx = xt.grad.permute(0, 2, 3, 1).reshape(P, 81, Cc).numpy()
+    x = dy                                                                            # the kernel's input is now d y
+    w_bwd = np.stack([w[:, :, tap // 3, tap % 3] for tap in range(9)])                # [tap][co as input channel][ci as output channel]
+    assert np.abs(kernel(w_bwd, -1, False) - want_dx).max() < 1e-5
